@@ -1,0 +1,171 @@
+/*
+ * include/sdx.h — C ABI of libsdx.so, the B200 (sm_100a) implementation of the
+ * SuperDendrix significance-and-search path.
+ *
+ * The reference (raphael-group/superdendrix) has no FFI: its boundary is a set
+ * of Python call signatures.  Each entry point below names the
+ * reference function it replaces (path:line relative to the reference root);
+ * the Python shims in superdendrix_b200/ keep the reference's names and return
+ * types and call these through ctypes.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = SDX_OK, negative = error;
+ *     sdx_last_error(ctx) gives the message.  Nothing aborts the process.
+ *   - all pointers are HOST pointers owned by the caller, C-contiguous,
+ *     little-endian.  The library owns device memory inside the ctx and copies
+ *     in/out itself; functions are synchronous (stream-synchronised on return).
+ *   - packed rows: uint32 words, bit j of word i of a row = element 32*i+j;
+ *     padding bits are zero and stay zero.
+ *   - "feature rows": F rows over S samples (words_per_row = ceil(S/32)).
+ *     "trade rows": the orientation Curveball works in — rows over the SHORTER
+ *     matrix dimension, as find_presences picks it (src/curveball.py:10-11):
+ *     samples are the rows when F >= S, features otherwise.
+ *   - one ctx per (process, GPU); calls on one ctx are serialised by the caller.
+ *   - there is no CPU fallback: without a CUDA device sdx_create fails.
+ */
+#ifndef SDX_H
+#define SDX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDX_OK 0
+#define SDX_ERR_INVALID (-1)     /* bad argument */
+#define SDX_ERR_CUDA (-2)        /* CUDA runtime error (message has the detail) */
+#define SDX_ERR_STATE (-3)       /* call order: matrix / weights not uploaded */
+#define SDX_ERR_UNSUPPORTED (-4) /* shape outside what the kernels cover */
+
+#define SDX_MAX_K 8              /* largest module size the scorer accepts */
+
+#define SDX_STAT_FIXED 0         /* null statistic: W_null(observed module) */
+#define SDX_STAT_MAXK 1          /* null statistic: max_{|M|<=k} W_null(M)  (src/superdendrix.py:191) */
+
+typedef struct sdx_ctx sdx_ctx;
+
+/* One scanned subset.  features[] are ascending feature indices, -1 padded. */
+typedef struct sdx_hit {
+    double W;
+    int32_t features[3];
+    int32_t coverage;
+} sdx_hit;
+
+/* Timings (ms, CUDA events on the ctx stream) of the kernels of the last call. */
+typedef struct sdx_timing {
+    float plan_ms;     /* trade-schedule kernels (pair draw + level sort)   */
+    float trade_ms;    /* Curveball trade (+ fused scoring) kernel          */
+    float score_ms;    /* stand-alone scorer / scanner / perm / rank kernels */
+    float total_ms;    /* first launch to last launch of the call           */
+    int32_t launches;  /* kernels launched by the call                      */
+    int32_t reserved;
+} sdx_timing;
+
+int sdx_version(void);
+int sdx_device_count(int *n);
+
+/* lifecycle */
+int sdx_create(int device, sdx_ctx **out);
+int sdx_destroy(sdx_ctx *ctx);
+const char *sdx_last_error(const sdx_ctx *ctx); /* ctx may be NULL: error of a failed sdx_create */
+int sdx_set_stream(sdx_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = the ctx's own stream */
+int sdx_get_timing(const sdx_ctx *ctx, sdx_timing *out);
+int sdx_total_launches(const sdx_ctx *ctx, int64_t *n);
+
+/* Binary sample x feature matrix as F packed feature rows over S samples.
+ * Replaces the densify step of src/generate_null_matrices.py:62-68 and the
+ * geneToCases sets of src/i_o.py:18-88 as the kernels' input. */
+int sdx_upload_matrix(sdx_ctx *ctx, const uint32_t *feature_rows, int n_features, int n_samples,
+                      int words_per_row);
+
+/* n_profiles weight vectors w[p][s] (fp64, already sign-flipped as
+ * src/superdendrix.py:97-98,105-106) and, optionally, per-profile sample masks
+ * (samples with a usable profile value, src/superdendrix.py:125,186 via
+ * src/i_o.py:57).  Weights of masked-out samples are ignored.  mask == NULL
+ * means every sample belongs to every profile. */
+int sdx_upload_weights(sdx_ctx *ctx, const double *w, const uint32_t *sample_mask, int n_profiles,
+                       int n_samples);
+
+/* SuperW (src/superdendrix.py:387-391) for n_sets modules of up to k features
+ * (rows of `sets`, -1 padded) on the uploaded matrix; profile_of_set may be
+ * NULL (all profile 0).  Also the integer outputs of src/superdendrix.py:229-236
+ * and :345-350: coverage |U|, overlap sum|g|-|U|, act_cov |U ∩ {w>0}|.
+ * Any output pointer may be NULL. */
+int sdx_score_sets(sdx_ctx *ctx, const int32_t *sets, const int32_t *profile_of_set, int64_t n_sets,
+                   int k, double *W, int32_t *coverage, int32_t *overlap, int32_t *act_cov);
+
+/* Per-feature outputs for one profile: sum of w over carriers and the argmax
+ * (first maximum wins, src/superdendrix.py:281-286), W of the singleton
+ * (:219-227, unrounded), carrier count (:229-232). */
+int sdx_feature_scores(sdx_ctx *ctx, int profile, double *sum_w, double *W1, int32_t *count,
+                       int32_t *best_single);
+
+/* Dimensions of the trade-row orientation of the uploaded matrix. */
+int sdx_trade_shape(const sdx_ctx *ctx, int *n_rows, int *n_bits, int *words_per_row,
+                    int *rows_are_samples);
+
+/* curve_ball (src/curveball.py:17-40) driven as src/generate_null_matrices.py:71-74
+ * drives it: nulls null0 .. null0+n_nulls-1, n_trades each (-1 = 5*min(S,F),
+ * src/curveball.py:20).  Null i restarts from the observed matrix when
+ * i % chain_len == 0 and continues from null i-1 otherwise (chain_len >= n
+ * = the reference's single Markov chain; 1 = independent restarts).  Random
+ * draws come from the counter-based stream keyed on (seed, global null index,
+ * trade index), so results do not depend on batching or on the GPU count.
+ * out_trade_rows: n_nulls x R x words_per_row packed trade rows, or NULL.
+ * applied: n_nulls counts of non-skipped trades (src/curveball.py:29), or NULL. */
+int sdx_curveball(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
+                  int64_t chain_len, uint32_t *out_trade_rows, int64_t *applied);
+
+/* Replay of a recorded schedule (parity with the reference under its own
+ * random draws): trade t exchanges rows a[t], b[t]; to_a[t] (words_per_row
+ * words) holds the symmetric-difference elements given to row a, i.e.
+ * tot[:L] of src/curveball.py:32-34.  start_trade_rows == NULL starts from the
+ * uploaded matrix.  Skips are detected on the device (src/curveball.py:29). */
+int sdx_curveball_replay(sdx_ctx *ctx, const uint32_t *start_trade_rows, const int32_t *a,
+                         const int32_t *b, const uint32_t *to_a, int64_t n_trades,
+                         uint32_t *out_trade_rows, int64_t *applied);
+
+/* The null loop of src/superdendrix.py:166-197 without files: generate each
+ * null as sdx_curveball does, score it for every uploaded profile and count
+ * exceedances n_ge[p] = #{i : stat_i(p) >= z_obs[p]} (:192); p = n_ge/n (:195).
+ * modules: n_profiles x k feature indices (-1 padded).  stat = SDX_STAT_FIXED
+ * scores the module itself on the null; SDX_STAT_MAXK re-optimises by
+ * exhaustive scan over |M| <= k (k <= 3) as the reference's per-null ILP does.
+ * z_obs == NULL: the library scores the observed matrix with the same kernel
+ * code and returns the values in z_obs_out (may be NULL).
+ * null_scores: n_profiles x n_nulls, or NULL. */
+int sdx_null_pvalue(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
+                    int64_t chain_len, int stat, const int32_t *modules, int k, const double *z_obs,
+                    int64_t *n_ge, double *null_scores, double *z_obs_out);
+
+/* Exhaustive scan of every feature subset of size 1..k (k <= 3) under W for
+ * one profile: the integral optimum of the ILP of src/superdendrix.py:294-313,
+ * 393-401.  hits: the topn best subsets, W descending (ties: enumeration
+ * order, size-major then lexicographic).  n_scored: number of subsets scored. */
+int sdx_scan(sdx_ctx *ctx, int profile, int k, int topn, sdx_hit *hits, int64_t *n_scored);
+
+/* conditional_permutation_test (src/superdendrix.py:361-384) for one module of
+ * one profile: counts[i] = #{t < n_perm : W(M with g_i := random |g_i|-subset
+ * of the profile's samples) >= W(M)}.  real_W: W(M) as used in the comparison.
+ * Draws: stream (PERM, id = perm_id0 + i, t). */
+int sdx_condperm(sdx_ctx *ctx, int profile, const int32_t *module, int k, uint64_t seed,
+                 uint64_t perm_id0, int64_t n_perm, int64_t *counts, double *real_W);
+
+/* scipy.stats.ranksums as called at utils/compute_p_value.py:306-318 and
+ * utils/compute_ranksum_pval.py:116-128 for n_jobs (profile, module) pairs:
+ * x = values over carriers of the union, y = over the profile's other samples.
+ * `values` are the uploaded weights of that profile.  twice_rank_sum is the
+ * exact integer 2*sum(rank(x)) with mid-ranks. */
+int sdx_ranksum(sdx_ctx *ctx, const int32_t *profile_of_job, const int32_t *modules, int64_t n_jobs,
+                int k, double *z, double *p, int64_t *twice_rank_sum, int32_t *n1);
+
+/* Self-test hooks used by tests/ (known-answer vectors of the random streams). */
+int sdx_test_philox(sdx_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, int n, uint32_t *out4);
+int sdx_test_trade_pairs(sdx_ctx *ctx, uint64_t seed, uint64_t null_id, int n_trades, int n_rows,
+                         int32_t *a, int32_t *b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDX_H */

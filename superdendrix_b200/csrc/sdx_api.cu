@@ -1,0 +1,200 @@
+// sdx_api.cu — context lifecycle, uploads and layout kernels of libsdx.so.
+#include "sdx_common.cuh"
+
+std::string g_sdx_create_error;
+
+extern "C" int sdx_version(void) { return SDX_VERSION; }
+
+extern "C" int sdx_device_count(int *n) {
+    if (!n) return SDX_ERR_INVALID;
+    int k = 0;
+    cudaError_t e = cudaGetDeviceCount(&k);
+    if (e != cudaSuccess) { *n = 0; g_sdx_create_error = cudaGetErrorString(e); return SDX_ERR_CUDA; }
+    *n = k;
+    return SDX_OK;
+}
+
+extern "C" const char *sdx_last_error(const sdx_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : g_sdx_create_error.c_str();
+}
+
+extern "C" int sdx_create(int device, sdx_ctx **out) {
+    if (!out) return SDX_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_sdx_create_error = std::string("no CUDA device available (libsdx has no CPU fallback): ") +
+                             (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return SDX_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_sdx_create_error = "device index out of range"; return SDX_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_sdx_create_error = cudaGetErrorString(e);
+        return SDX_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        char b[256];
+        snprintf(b, sizeof b, "libsdx is built for sm_100a only; device %d is sm_%d%d (%s)", device, prop.major, prop.minor, prop.name);
+        g_sdx_create_error = b;
+        return SDX_ERR_UNSUPPORTED;
+    }
+    sdx_ctx *c = new sdx_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_sdx_create_error = cudaGetErrorString(e);
+        delete c;
+        return SDX_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    for (auto &ev : c->ev) cudaEventCreate(&ev);
+    *out = c;
+    return SDX_OK;
+}
+
+static void free_matrix(sdx_ctx *c) {
+    if (c->d_feat) cudaFree(c->d_feat);
+    if (c->d_samp) cudaFree(c->d_samp);
+    if (c->d_trade_obs) cudaFree(c->d_trade_obs);
+    c->d_feat = c->d_samp = c->d_trade_obs = nullptr;
+}
+
+static void free_weights(sdx_ctx *c) {
+    if (c->d_w) cudaFree(c->d_w);
+    if (c->d_mask) cudaFree(c->d_mask);
+    if (c->d_nsamp) cudaFree(c->d_nsamp);
+    c->d_w = nullptr; c->d_mask = nullptr; c->d_nsamp = nullptr;
+    c->P = 0;
+}
+
+extern "C" int sdx_destroy(sdx_ctx *c) {
+    if (!c) return SDX_ERR_INVALID;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_matrix(c);
+    free_weights(c);
+    for (auto &b : c->scratch) if (b.p) cudaFree(b.p);
+    for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return SDX_OK;
+}
+
+extern "C" int sdx_set_stream(sdx_ctx *c, void *s) {
+    if (!c) return SDX_ERR_INVALID;
+    cudaStreamSynchronize(c->stream);
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return SDX_OK;
+}
+
+extern "C" int sdx_get_timing(const sdx_ctx *c, sdx_timing *out) {
+    if (!c || !out) return SDX_ERR_INVALID;
+    *out = c->timing;
+    return SDX_OK;
+}
+
+extern "C" int sdx_total_launches(const sdx_ctx *c, int64_t *n) {
+    if (!c || !n) return SDX_ERR_INVALID;
+    *n = c->total_launches;
+    return SDX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// bit transpose: F x wprS (feature rows) -> S x wprF (sample rows).
+// One warp per (feature word fw, sample word sw) tile of 32 x 32 bits.
+// ---------------------------------------------------------------------------
+__global__ void k_transpose_bits(const uint32_t *__restrict__ in, int n_rows, int wpr_in, int n_cols,
+                                 uint32_t *__restrict__ out, int wpr_out) {
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int tiles_c = wpr_in;
+    const int rw = tile / tiles_c, cw = tile - rw * tiles_c;     // row word (of out), col word (of in)
+    if (rw >= wpr_out) return;
+    const int r = rw * 32 + lane;
+    const uint32_t x = (r < n_rows) ? in[(size_t)r * wpr_in + cw] : 0u;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+        uint32_t v = __ballot_sync(0xffffffffu, (x >> b) & 1u);
+        int col = cw * 32 + b;
+        if (lane == 0 && col < n_cols) out[(size_t)col * wpr_out + rw] = v;
+    }
+}
+
+extern "C" int sdx_upload_matrix(sdx_ctx *c, const uint32_t *rows, int F, int S, int wpr) {
+    if (!c) return SDX_ERR_INVALID;
+    SDX_REQUIRE(c, rows && F >= 1 && S >= 1, SDX_ERR_INVALID, "matrix pointer / shape invalid");
+    SDX_REQUIRE(c, wpr == (S + 31) / 32, SDX_ERR_INVALID, "words_per_row must be ceil(n_samples/32)");
+    if (S % 32) {        // padding bits must be zero
+        const uint32_t pad = ~0u << (S % 32);
+        for (int g = 0; g < F; ++g)
+            SDX_REQUIRE(c, (rows[(size_t)g * wpr + wpr - 1] & pad) == 0, SDX_ERR_INVALID, "padding bits of a feature row are not zero");
+    }
+    SDX_CUDA(c, cudaSetDevice(c->device));
+    free_matrix(c);
+    c->F = F; c->S = S; c->wprS = wpr; c->wprF = (F + 31) / 32;
+    SDX_CUDA(c, cudaMalloc(&c->d_feat, sizeof(uint32_t) * (size_t)F * c->wprS));
+    SDX_CUDA(c, cudaMalloc(&c->d_samp, sizeof(uint32_t) * (size_t)S * c->wprF));
+    SDX_CUDA(c, cudaMemcpyAsync(c->d_feat, rows, sizeof(uint32_t) * (size_t)F * c->wprS, cudaMemcpyHostToDevice, c->stream));
+    SDX_CUDA(c, cudaMemsetAsync(c->d_samp, 0, sizeof(uint32_t) * (size_t)S * c->wprF, c->stream));
+    const int tiles = c->wprF * c->wprS;
+    k_transpose_bits<<<ceil_div(tiles, 8), 256, 0, c->stream>>>(c->d_feat, F, c->wprS, S, c->d_samp, c->wprF);
+    c->total_launches++;
+    // trade orientation (src/curveball.py:10-11): rows over the shorter dimension, samples when F >= S
+    c->rows_are_samples = F >= S;
+    c->R = c->rows_are_samples ? S : F;
+    c->L = c->rows_are_samples ? F : S;
+    c->wprL = c->rows_are_samples ? c->wprF : c->wprS;
+    c->RS = ((c->wprL + 3) / 4) * 4;
+    SDX_CUDA(c, cudaMalloc(&c->d_trade_obs, sizeof(uint32_t) * (size_t)c->R * c->RS));
+    SDX_CUDA(c, cudaMemsetAsync(c->d_trade_obs, 0, sizeof(uint32_t) * (size_t)c->R * c->RS, c->stream));
+    SDX_CUDA(c, cudaMemcpy2DAsync(c->d_trade_obs, (size_t)c->RS * 4, c->rows_are_samples ? c->d_samp : c->d_feat,
+                                  (size_t)c->wprL * 4, (size_t)c->wprL * 4, c->R, cudaMemcpyDeviceToDevice, c->stream));
+    SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    SDX_CUDA(c, cudaGetLastError());
+    return SDX_OK;
+}
+
+extern "C" int sdx_trade_shape(const sdx_ctx *c, int *R, int *L, int *wpr, int *ras) {
+    if (!c) return SDX_ERR_INVALID;
+    if (!c->d_trade_obs) return SDX_ERR_STATE;
+    if (R) *R = c->R;
+    if (L) *L = c->L;
+    if (wpr) *wpr = c->wprL;
+    if (ras) *ras = c->rows_are_samples;
+    return SDX_OK;
+}
+
+extern "C" int sdx_upload_weights(sdx_ctx *c, const double *w, const uint32_t *mask, int P, int S) {
+    if (!c) return SDX_ERR_INVALID;
+    SDX_REQUIRE(c, c->d_feat, SDX_ERR_STATE, "sdx_upload_matrix must be called before sdx_upload_weights");
+    SDX_REQUIRE(c, w && P >= 1 && S == c->S, SDX_ERR_INVALID, "weights pointer / shape invalid (n_samples must match the matrix)");
+    const int wpr = c->wprS;
+    std::vector<double> hw((size_t)P * S);
+    std::vector<uint32_t> hm((size_t)P * wpr);
+    std::vector<int> hn((size_t)P);
+    for (int p = 0; p < P; ++p) {
+        int cnt = 0;
+        for (int s = 0; s < S; ++s) {
+            bool in = mask ? ((mask[(size_t)p * wpr + (s >> 5)] >> (s & 31)) & 1u) : true;
+            double v = w[(size_t)p * S + s];
+            SDX_REQUIRE(c, !in || v == v, SDX_ERR_INVALID, "NaN weight for a sample inside the profile mask");
+            hw[(size_t)p * S + s] = in ? v : 0.0;
+            if (in) { hm[(size_t)p * wpr + (s >> 5)] |= 1u << (s & 31); ++cnt; }
+        }
+        hn[p] = cnt;
+    }
+    SDX_CUDA(c, cudaSetDevice(c->device));
+    free_weights(c);
+    SDX_CUDA(c, cudaMalloc(&c->d_w, sizeof(double) * (size_t)P * S));
+    SDX_CUDA(c, cudaMalloc(&c->d_mask, sizeof(uint32_t) * (size_t)P * wpr));
+    SDX_CUDA(c, cudaMalloc(&c->d_nsamp, sizeof(int) * (size_t)P));
+    SDX_CUDA(c, cudaMemcpyAsync(c->d_w, hw.data(), sizeof(double) * (size_t)P * S, cudaMemcpyHostToDevice, c->stream));
+    SDX_CUDA(c, cudaMemcpyAsync(c->d_mask, hm.data(), sizeof(uint32_t) * (size_t)P * wpr, cudaMemcpyHostToDevice, c->stream));
+    SDX_CUDA(c, cudaMemcpyAsync(c->d_nsamp, hn.data(), sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, c->stream));
+    SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->P = P;
+    return SDX_OK;
+}

@@ -1,0 +1,201 @@
+// sdx_common.cuh — context, error handling and device helpers shared by the
+// libsdx.so translation units (sm_100a only; no CPU fallback anywhere).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sdx.h"
+
+#define SDX_VERSION 100
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct sdx_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    sdx_timing timing{};
+    int64_t total_launches = 0;
+
+    // matrix
+    int F = 0, S = 0;
+    int wprS = 0;            // words per feature row (over samples)
+    int wprF = 0;            // words per sample row (over features)
+    uint32_t *d_feat = nullptr;   // F x wprS
+    uint32_t *d_samp = nullptr;   // S x wprF   (device-side transpose)
+    // trade orientation
+    int R = 0, L = 0, wprL = 0, RS = 0;   // RS: padded row stride (words, multiple of 4)
+    int rows_are_samples = 0;
+    uint32_t *d_trade_obs = nullptr;      // R x RS, observed matrix in trade orientation
+
+    // weights
+    int P = 0;
+    double *d_w = nullptr;        // P x S  (0 where masked out)
+    uint32_t *d_mask = nullptr;   // P x wprS (always materialised)
+    int *d_nsamp = nullptr;       // P: popcount of the mask
+
+    // reusable scratch
+    DevBuf scratch[12];
+};
+
+inline int sdx_fail(sdx_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+extern std::string g_sdx_create_error;
+
+#define SDX_CUDA(ctx, call)                                                                  \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            char b_[512];                                                                    \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
+                     __FILE__, __LINE__);                                                    \
+            return sdx_fail((ctx), SDX_ERR_CUDA, b_);                                        \
+        }                                                                                    \
+    } while (0)
+
+#define SDX_REQUIRE(ctx, cond, code, msg)                     \
+    do {                                                      \
+        if (!(cond)) return sdx_fail((ctx), (code), (msg));   \
+    } while (0)
+
+// grow-only scratch buffer
+inline int sdx_scratch(sdx_ctx *c, int slot, size_t bytes, void **out) {
+    DevBuf &b = c->scratch[slot];
+    if (b.bytes < bytes) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr; b.bytes = 0;
+        SDX_CUDA(c, cudaMalloc(&b.p, bytes));
+        b.bytes = bytes;
+    }
+    *out = b.p;
+    return SDX_OK;
+}
+
+struct LaunchTimer {      // CUDA-event bracket on the ctx stream
+    sdx_ctx *c;
+    explicit LaunchTimer(sdx_ctx *ctx) : c(ctx) {
+        memset(&c->timing, 0, sizeof c->timing);
+        cudaEventRecord(c->ev[0], c->stream);
+    }
+    void count(int n = 1) { c->timing.launches += n; c->total_launches += n; }
+    int finish() {
+        cudaEventRecord(c->ev[1], c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) return sdx_fail(c, SDX_ERR_CUDA, std::string("kernel execution failed: ") + cudaGetErrorString(e));
+        cudaEventElapsedTime(&c->timing.total_ms, c->ev[0], c->ev[1]);
+        return SDX_OK;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 and the canonical streams (oracle/sdx_oracle.c)
+// ---------------------------------------------------------------------------
+#define SDX_STREAM_PAIR 0u
+#define SDX_STREAM_DEAL 1u
+#define SDX_STREAM_PERM 2u
+
+struct PhiloxKeys {      // the ten round keys, precomputed on the host so they sit in the constant bank
+    uint32_t k0[10];
+    uint32_t k1[10];
+};
+
+inline PhiloxKeys make_keys(uint64_t seed) {
+    PhiloxKeys k;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        k.k0[r] = a; k.k1[r] = b;
+        a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    return k;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c.x;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c.z;
+        uint4 n;
+        n.x = (uint32_t)(p1 >> 32) ^ c.y ^ k.k0[r];
+        n.y = (uint32_t)p1;
+        n.z = (uint32_t)(p0 >> 32) ^ c.w ^ k.k1[r];
+        n.w = (uint32_t)p0;
+        c = n;
+    }
+    return c;
+}
+
+__device__ __forceinline__ uint4 stream_block(const PhiloxKeys &k, uint32_t kind, uint64_t id, uint32_t t, uint32_t block) {
+    uint4 c;
+    c.x = block; c.y = t; c.z = (uint32_t)id;
+    c.w = ((uint32_t)(id >> 32) & 0x3fffffffu) | (kind << 30);
+    return philox4x32_10(c, k);
+}
+
+__device__ __forceinline__ uint32_t pick4(const uint4 &v, uint32_t i) {
+    uint32_t lo = (i & 1) ? v.y : v.x;
+    uint32_t hi = (i & 1) ? v.w : v.z;
+    return (i & 2) ? hi : lo;
+}
+
+// Sequential per-thread view of one stream (used where a single thread owns a
+// whole stream: trade pairs, permutation draws).
+struct ThreadStream {
+    const PhiloxKeys &k;
+    uint32_t kind; uint64_t id; uint32_t t;
+    uint32_t block; uint32_t pos; uint4 buf;
+    __device__ __forceinline__ ThreadStream(const PhiloxKeys &keys, uint32_t kind_, uint64_t id_, uint32_t t_)
+        : k(keys), kind(kind_), id(id_), t(t_), block(0), pos(4) {}
+    __device__ __forceinline__ uint32_t next() {
+        if (pos == 4) { buf = stream_block(k, kind, id, t, block++); pos = 0; }
+        return pick4(buf, pos++);
+    }
+    // exactly uniform in [0, m)  (Lemire, with rejection)
+    __device__ __forceinline__ uint32_t below(uint32_t m) {
+        uint64_t prod = (uint64_t)next() * m;
+        uint32_t lo = (uint32_t)prod;
+        if (lo < m) {
+            uint32_t thr = (0u - m) % m;
+            while (lo < thr) { prod = (uint64_t)next() * m; lo = (uint32_t)prod; }
+        }
+        return (uint32_t)(prod >> 32);
+    }
+};
+
+__device__ __forceinline__ void trade_pair(const PhiloxKeys &k, uint64_t null_id, uint32_t t, uint32_t R, uint32_t &a, uint32_t &b) {
+    ThreadStream s(k, SDX_STREAM_PAIR, null_id, t);
+    a = s.below(R);
+    b = s.below(R - 1);
+    if (b >= a) b++;
+}
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_f64(double v) {      // fixed butterfly: deterministic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum_i32(int v) { return __reduce_add_sync(0xffffffffu, v); }
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,600 @@
+// sdx_curveball.cu — Curveball null generation (+ fused fixed-set scoring).
+//
+// Replaces, behind the C ABI of include/sdx.h:
+//   src/curveball.py:17-40            curve_ball
+//   src/generate_null_matrices.py:71-74  the null loop over one mutable presence list
+//   src/superdendrix.py:166-197       the null loop / exceedance count (stat = fixed)
+//
+// Pipeline per batch of nulls (all on the ctx stream):
+//   k_plan_levels   one THREAD per null: draws the trade pairs (PAIR stream) in
+//                   order and assigns each trade the level
+//                   1 + max(level of the last trade that touched row a, row b).
+//                   Trades of one level touch pairwise disjoint rows, and every
+//                   earlier trade on those rows is in a lower level, so running
+//                   level by level is identical to the sequential order.
+//   k_plan_sort     one WARP per null: counting sort of the trades by level into
+//                   the plan (a, b, t | END flag on the last trade of a level).
+//   k_trade         one CTA per chain segment: matrix resident in shared memory
+//                   (or in L2/global when it does not fit), groups of G lanes
+//                   execute the trades of a level concurrently, __syncthreads
+//                   between levels; then the fused scorer and the outputs.
+#include "sdx_trade.cuh"
+
+// ---------------------------------------------------------------------------
+struct NullIndexing {          // local null index (within a launch) -> global null id
+    uint64_t chain0;           // first chain of this launch
+    int64_t chain_len;
+    int64_t seg_off;           // chain-relative offset of the segment
+    int seg_len;               // nulls per chain in this launch
+    uint64_t null_lo, null_hi; // requested range [null_lo, null_hi)
+    __host__ __device__ uint64_t id(int64_t local) const {
+        return (chain0 + (uint64_t)(local / seg_len)) * (uint64_t)chain_len + (uint64_t)seg_off + (uint64_t)(local % seg_len);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// plan: levels
+// ---------------------------------------------------------------------------
+__global__ void k_plan_levels(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T,
+                              uint16_t *__restrict__ lvl, int *__restrict__ depth,
+                              uint16_t *__restrict__ last_global) {
+    extern __shared__ uint16_t last_smem[];
+    const int tid = threadIdx.x;
+    const int n = blockIdx.x * blockDim.x + tid;
+    uint16_t *last;
+    size_t stride;
+    if (last_global) { last = last_global + (size_t)blockIdx.x * blockDim.x * R + tid; stride = blockDim.x; }
+    else { last = last_smem + tid; stride = blockDim.x; }
+    if (n >= n_local) return;
+    const uint64_t null_id = ix.id(n);
+    for (int r = 0; r < R; ++r) last[(size_t)r * stride] = 0;
+    uint16_t *out = lvl + (size_t)n * T;
+    int d = 0;
+    for (int t = 0; t < T; ++t) {
+        uint32_t a, b;
+        trade_pair(keys, null_id, (uint32_t)t, (uint32_t)R, a, b);
+        int la = last[(size_t)a * stride], lb = last[(size_t)b * stride];
+        int l = (la > lb ? la : lb) + 1;
+        last[(size_t)a * stride] = (uint16_t)l;
+        last[(size_t)b * stride] = (uint16_t)l;
+        out[t] = (uint16_t)l;
+        d = l > d ? l : d;
+    }
+    depth[n] = d;
+}
+
+// ---------------------------------------------------------------------------
+// plan: counting sort by level (one warp per null)
+// ---------------------------------------------------------------------------
+#define SDX_HCAP 2048
+__global__ void k_plan_sort(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T,
+                            const uint16_t *__restrict__ lvl, const int *__restrict__ depth,
+                            uint2 *__restrict__ plan) {
+    __shared__ uint32_t hist_smem[2][SDX_HCAP + 2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n = blockIdx.x * (blockDim.x >> 5) + wid;
+    if (n >= n_local) return;
+    const int D = depth[n];
+    uint32_t *hist = hist_smem[wid];
+    const uint16_t *lv = lvl + (size_t)n * T;
+    uint2 *out = plan + (size_t)n * T;
+    const uint64_t null_id = ix.id(n);
+    if (D >= SDX_HCAP) {        // very deep schedule: fall back to the sequential order (always valid)
+        for (int t = lane; t < T; t += 32) {
+            uint32_t a, b;
+            trade_pair(keys, null_id, (uint32_t)t, (uint32_t)R, a, b);
+            out[t] = make_uint2(a | (b << 16), (uint32_t)t | SDX_PLAN_END);
+        }
+        return;
+    }
+    for (int l = lane; l <= D + 1; l += 32) hist[l] = 0;
+    __syncwarp();
+    for (int t = lane; t < T; t += 32) atomicAdd(&hist[lv[t]], 1u);
+    __syncwarp();
+    // exclusive scan of hist[1..D] -> start offsets
+    uint32_t carry = 0;
+    for (int base = 1; base <= D; base += 32) {
+        int l = base + lane;
+        uint32_t c = (l <= D) ? hist[l] : 0u, inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (l <= D) hist[l] = carry + inc - c;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    __syncwarp();
+    for (int t = lane; t < T; t += 32) {
+        uint32_t a, b;
+        trade_pair(keys, null_id, (uint32_t)t, (uint32_t)R, a, b);
+        uint32_t pos = atomicAdd(&hist[lv[t]], 1u);
+        out[pos] = make_uint2(a | (b << 16), (uint32_t)t);
+    }
+    __syncwarp();
+    __threadfence_block();
+    for (int l = 1 + lane; l <= D; l += 32) {     // hist[l] is now the end offset of level l
+        uint32_t e = hist[l];
+        if (e > 0) out[e - 1].y |= SDX_PLAN_END;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// trade kernel
+// ---------------------------------------------------------------------------
+struct ScoreArgs {
+    int n_profiles, k;
+    const int32_t *modules;           // P x k
+    const double *w;                  // P x S
+    const uint32_t *mask;             // P x wprS
+    const double *z_obs;              // P
+    unsigned long long *n_ge;         // P
+    double *null_scores;              // P x n_total, or null
+    int64_t n_total;                  // row length of null_scores
+    int S, wprS;
+    int rows_are_samples;
+};
+
+struct TradeArgs {
+    PhiloxKeys keys;
+    NullIndexing ix;
+    const uint32_t *observed;         // R x RS
+    uint32_t *work;                   // gridDim.x x R x RS (global-resident variant only)
+    uint32_t *carry;                  // n_units x R x RS: chain state between launches (or null)
+    const uint2 *plan;                // n_local x T
+    int n_units;                      // chain segments in this launch
+    int R, RS, T, wprL;
+    int save_carry;
+    uint32_t *out_rows;               // staging: rows of launch-local null l go to out_rows + l * R * wprL
+    unsigned long long *applied;      // (i - ix.null_lo)
+    ScoreArgs sc;
+};
+
+template <int G, int V, bool SMEM>
+__global__ void __launch_bounds__(512) k_trade(const __grid_constant__ TradeArgs p) {
+    extern __shared__ __align__(16) uint32_t smem_rows[];
+    __shared__ unsigned int s_applied;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NW = blockDim.x >> 5;
+    constexpr int GPW = 32 / G;                 // groups per warp
+    const int NG = NW * GPW;                    // groups per CTA (<= 32)
+    const int sub = lane & (G - 1);
+    const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const int myg = wid * GPW + (lane / G);
+    const int R = p.R, RS = p.RS, T = p.T;
+    const int nvec = R * RS / 4;
+    uint32_t *rows = SMEM ? smem_rows : p.work + (size_t)blockIdx.x * R * RS;
+
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        for (int j = 0; j < p.ix.seg_len; ++j) {
+            const int64_t local = (int64_t)u * p.ix.seg_len + j;
+            const uint64_t null_id = p.ix.id(local);
+            if (null_id >= p.ix.null_hi) break;
+            const bool restart = (null_id % (uint64_t)p.ix.chain_len) == 0;
+            if (restart || j == 0) {
+                const uint32_t *src = restart ? p.observed : p.carry + (size_t)u * R * RS;
+                for (int i = tid; i < nvec; i += blockDim.x)
+                    reinterpret_cast<uint4 *>(rows)[i] = reinterpret_cast<const uint4 *>(src)[i];
+            }
+            if (tid == 0) s_applied = 0;
+            __syncthreads();
+
+            // ---- trades, level by level -------------------------------------
+            const uint2 *pl = p.plan + (size_t)local * T;
+            unsigned int my_applied = 0;
+            int wb = 0, wpos = 0;                 // window base (entries), position inside the 64-entry window
+            const uint2 none = make_uint2(0u, SDX_PLAN_END);
+            uint2 e0 = (lane < T) ? pl[lane] : none;
+            uint2 e1 = (32 + lane < T) ? pl[32 + lane] : none;
+            uint32_t f0 = __ballot_sync(0xffffffffu, e0.y & SDX_PLAN_END);
+            uint32_t f1 = __ballot_sync(0xffffffffu, e1.y & SDX_PLAN_END);
+            int pos = 0;
+            while (pos < T) {
+                const uint64_t flags = ((uint64_t)f1 << 32 | f0) >> wpos;
+                int cnt = NG;
+                const uint32_t fl = (uint32_t)flags & ((NG == 32) ? 0xffffffffu : ((1u << NG) - 1u));
+                const bool level_end = fl != 0;
+                if (level_end) cnt = __ffs(fl);
+                if (cnt > T - pos) cnt = T - pos;
+                const int idx = wpos + myg;
+                uint32_t x0 = __shfl_sync(0xffffffffu, e0.x, idx & 31), y0 = __shfl_sync(0xffffffffu, e0.y, idx & 31);
+                uint32_t x1 = __shfl_sync(0xffffffffu, e1.x, idx & 31), y1 = __shfl_sync(0xffffffffu, e1.y, idx & 31);
+                const uint32_t ex = idx < 32 ? x0 : x1, ey = idx < 32 ? y0 : y1;
+                if (myg < cnt) {
+                    bool ap = trade_rows<G, V>(rows, RS, ex & 0xffffu, ex >> 16, ey & ~SDX_PLAN_END, null_id, p.keys, sub, gmask);
+                    my_applied += (ap && sub == 0) ? 1u : 0u;
+                }
+                __syncwarp();
+                pos += cnt; wpos += cnt;
+                if (wpos >= 32) {
+                    wpos -= 32; wb += 32;
+                    e0 = e1; f0 = f1;
+                    e1 = (wb + 32 + lane < T) ? pl[wb + 32 + lane] : none;
+                    f1 = __ballot_sync(0xffffffffu, e1.y & SDX_PLAN_END);
+                }
+                if (level_end) __syncthreads();
+            }
+            __syncthreads();
+
+            // ---- outputs -----------------------------------------------------
+            const bool emit = null_id >= p.ix.null_lo;
+            if (emit && p.applied) {
+                my_applied = __reduce_add_sync(0xffffffffu, my_applied);
+                if (lane == 0 && my_applied) atomicAdd(&s_applied, my_applied);
+            }
+            if (emit && p.out_rows) {
+                uint32_t *dst = p.out_rows + (size_t)local * R * p.wprL;
+                for (int i = tid; i < R * p.wprL; i += blockDim.x) {
+                    int r = i / p.wprL, c = i - r * p.wprL;
+                    dst[i] = rows[(size_t)r * RS + c];
+                }
+            }
+            if (emit && p.sc.n_profiles > 0) {
+                for (int pr = wid; pr < p.sc.n_profiles; pr += NW) {
+                    SetScore sc = score_module(rows, RS, p.sc.rows_are_samples != 0, p.sc.modules + (size_t)pr * p.sc.k,
+                                               p.sc.k, p.sc.w + (size_t)pr * p.sc.S, p.sc.mask + (size_t)pr * p.sc.wprS,
+                                               p.sc.S, lane);
+                    if (lane == 0) {
+                        if (sc.W >= p.sc.z_obs[pr]) atomicAdd(&p.sc.n_ge[pr], 1ull);
+                        if (p.sc.null_scores) p.sc.null_scores[(size_t)pr * p.sc.n_total + (null_id - p.ix.null_lo)] = sc.W;
+                    }
+                }
+            }
+            __syncthreads();
+            if (emit && p.applied && tid == 0) p.applied[null_id - p.ix.null_lo] = s_applied;
+        }
+        if (p.save_carry) {
+            uint32_t *dst = p.carry + (size_t)u * R * RS;
+            for (int i = tid; i < nvec; i += blockDim.x)
+                reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(rows)[i];
+        }
+        __syncthreads();
+    }
+}
+
+// score the observed matrix with the very same device code (z_obs for the exceedance test)
+__global__ void k_score_observed(const uint32_t *rows, int RS, ScoreArgs sc, double *z_out) {
+    const int lane = threadIdx.x & 31;
+    const int pr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pr >= sc.n_profiles) return;
+    SetScore s = score_module(rows, RS, sc.rows_are_samples != 0, sc.modules + (size_t)pr * sc.k, sc.k,
+                              sc.w + (size_t)pr * sc.S, sc.mask + (size_t)pr * sc.wprS, sc.S, lane);
+    if (lane == 0) z_out[pr] = s.W;
+}
+
+// ---------------------------------------------------------------------------
+// replay of a recorded schedule: one warp, strictly sequential
+// ---------------------------------------------------------------------------
+__global__ void k_replay(uint32_t *rows, int RS, int wprL, const int32_t *a, const int32_t *b,
+                         const uint32_t *to_a, int64_t T, unsigned long long *applied) {
+    const int lane = threadIdx.x;
+    unsigned long long ap = 0;
+    for (int64_t t = 0; t < T; ++t) {
+        uint32_t *ra = rows + (size_t)a[t] * RS, *rb = rows + (size_t)b[t] * RS;
+        const uint32_t *m = to_a + (size_t)t * wprL;
+        int la = 0, lb = 0;
+        for (int i = lane; i < wprL; i += 32) {
+            uint32_t x = ra[i], y = rb[i];
+            la += __popc(x & ~y); lb += __popc(y & ~x);
+        }
+        la = warp_sum_i32(la); lb = warp_sum_i32(lb);
+        if (la != 0 && lb != 0) {
+            for (int i = lane; i < wprL; i += 32) {
+                uint32_t x = ra[i], y = rb[i], ab = x & y, sym = x ^ y, mk = m[i];
+                ra[i] = ab | (sym & mk);
+                rb[i] = ab | (sym & ~mk);
+            }
+            ++ap;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) *applied = ap;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct TradeConfig {
+    int G, V;
+    bool smem;
+    int threads;
+    size_t smem_bytes;
+    int grid_cap;      // max CTAs (global variant keeps the working set near L2 size)
+};
+
+static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
+    const int w = c->wprL;
+    if (w <= 32) { cfg->G = 8; cfg->V = 4; }
+    else if (w <= 64) { cfg->G = 16; cfg->V = 4; }
+    else if (w <= 128) { cfg->G = 32; cfg->V = 4; }
+    else if (w <= 160) { cfg->G = 32; cfg->V = 5; }
+    else if (w <= 256) { cfg->G = 32; cfg->V = 8; }
+    else return sdx_fail(c, SDX_ERR_UNSUPPORTED, "trade rows longer than 8192 bits are not supported");
+    if (c->R > 65535) return sdx_fail(c, SDX_ERR_UNSUPPORTED, "more than 65535 trade rows are not supported");
+    const size_t bytes = (size_t)c->R * c->RS * 4;
+    const size_t budget = c->smem_optin > 2048 ? c->smem_optin - 1024 : 0;
+    cfg->smem = bytes <= budget;
+    if (cfg->smem) {
+        cfg->smem_bytes = bytes < 16 ? 16 : bytes;
+        int per_sm = (int)((228 * 1024) / (cfg->smem_bytes + 1024 + 64));
+        if (per_sm < 1) per_sm = 1;
+        int warps = 20 / per_sm;                  // aim at ~20 resident warps per SM
+        if (warps < 4) warps = 4;
+        if (warps > 16) warps = 16;
+        int max_warps = 32 / (32 / cfg->G);       // NG <= 32
+        if (warps > max_warps) warps = max_warps;
+        cfg->threads = warps * 32;
+        cfg->grid_cap = 1 << 30;
+    } else {
+        cfg->smem_bytes = 0;
+        int warps = 32 / (32 / cfg->G);
+        if (warps > 16) warps = 16;
+        cfg->threads = warps * 32;
+        size_t per = bytes;
+        int cap = (int)((size_t)96 * 1024 * 1024 / per);   // working set ~ within L2
+        if (cap < c->sm_count) cap = c->sm_count;
+        cfg->grid_cap = cap;
+    }
+    return SDX_OK;
+}
+
+template <int G, int V>
+static cudaError_t launch_trade(const TradeConfig &cfg, int grid, cudaStream_t st, const TradeArgs &args) {
+    if (cfg.smem) {
+        auto kern = k_trade<G, V, true>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, cfg.threads, cfg.smem_bytes, st>>>(args);
+    } else {
+        k_trade<G, V, false><<<grid, cfg.threads, 0, st>>>(args);
+    }
+    return cudaGetLastError();
+}
+
+static cudaError_t dispatch_trade(const TradeConfig &cfg, int grid, cudaStream_t st, const TradeArgs &args) {
+    if (cfg.G == 8 && cfg.V == 4) return launch_trade<8, 4>(cfg, grid, st, args);
+    if (cfg.G == 16 && cfg.V == 4) return launch_trade<16, 4>(cfg, grid, st, args);
+    if (cfg.G == 32 && cfg.V == 4) return launch_trade<32, 4>(cfg, grid, st, args);
+    if (cfg.G == 32 && cfg.V == 5) return launch_trade<32, 5>(cfg, grid, st, args);
+    return launch_trade<32, 8>(cfg, grid, st, args);
+}
+
+struct HostScore {               // optional fused scoring request
+    int k = 0;
+    const int32_t *modules = nullptr;   // host, P x k
+    const double *z_obs = nullptr;      // host, P (or null)
+    int64_t *n_ge = nullptr;            // host out, P
+    double *null_scores = nullptr;      // host out, P x n (or null)
+    double *z_obs_out = nullptr;        // host out, P (or null)
+};
+
+enum { SL_LVL = 0, SL_PLAN, SL_AUX, SL_MOD, SL_Z, SL_SCORES, SL_CARRY, SL_OUT, SL_APPLIED, SL_WORK };
+
+// The common driver behind sdx_curveball and sdx_null_pvalue (stat = fixed).
+int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
+                  uint32_t *out_rows, int64_t *applied, const HostScore *hs) {
+    SDX_REQUIRE(c, c->d_trade_obs, SDX_ERR_STATE, "sdx_upload_matrix has not been called");
+    SDX_REQUIRE(c, n_nulls >= 0 && chain_len >= 1, SDX_ERR_INVALID, "n_nulls must be >= 0 and chain_len >= 1");
+    SDX_REQUIRE(c, c->R >= 2, SDX_ERR_INVALID, "Curveball needs at least two trade rows");
+    SDX_REQUIRE(c, null0 + (uint64_t)n_nulls < (1ull << 62), SDX_ERR_INVALID, "null index out of range");
+    const int64_t T = n_trades < 0 ? 5 * (int64_t)(c->S < c->F ? c->S : c->F) : n_trades;
+    SDX_REQUIRE(c, T <= 60000, SDX_ERR_UNSUPPORTED, "more than 60000 trades per null are not supported");
+    TradeConfig cfg;
+    int rc = pick_config(c, &cfg);
+    if (rc) return rc;
+
+    LaunchTimer timer(c);
+    const PhiloxKeys keys = make_keys(seed);
+    const int R = c->R, RS = c->RS;
+    const size_t mat_words = (size_t)R * RS;
+    const size_t out_per = (size_t)R * c->wprL;
+
+    // ---- fused scoring set-up ------------------------------------------------
+    ScoreArgs sc{};
+    unsigned long long *d_nge = nullptr;
+    double *d_scores = nullptr, *d_zobs = nullptr;
+    if (hs) {
+        SDX_REQUIRE(c, c->d_w, SDX_ERR_STATE, "sdx_upload_weights has not been called");
+        SDX_REQUIRE(c, hs->k >= 1 && hs->k <= SDX_MAX_K, SDX_ERR_INVALID, "module size k must be in 1..SDX_MAX_K");
+        SDX_REQUIRE(c, hs->modules && hs->n_ge, SDX_ERR_INVALID, "modules and n_ge are required");
+        for (int64_t i = 0; i < (int64_t)c->P * hs->k; ++i)
+            SDX_REQUIRE(c, hs->modules[i] >= -1 && hs->modules[i] < c->F, SDX_ERR_INVALID, "module feature index out of range");
+        void *pm, *pz, *ps = nullptr;
+        if ((rc = sdx_scratch(c, SL_MOD, sizeof(int32_t) * c->P * hs->k + 16, &pm))) return rc;
+        if ((rc = sdx_scratch(c, SL_Z, (sizeof(double) + sizeof(unsigned long long)) * c->P + 16, &pz))) return rc;
+        d_zobs = (double *)pz;
+        d_nge = (unsigned long long *)((char *)pz + sizeof(double) * c->P);
+        SDX_CUDA(c, cudaMemcpyAsync(pm, hs->modules, sizeof(int32_t) * c->P * hs->k, cudaMemcpyHostToDevice, c->stream));
+        SDX_CUDA(c, cudaMemsetAsync(d_nge, 0, sizeof(unsigned long long) * c->P, c->stream));
+        if (hs->null_scores && n_nulls > 0) {
+            if ((rc = sdx_scratch(c, SL_SCORES, sizeof(double) * c->P * n_nulls, &ps))) return rc;
+            d_scores = (double *)ps;
+        }
+        sc.n_profiles = c->P; sc.k = hs->k; sc.modules = (const int32_t *)pm; sc.w = c->d_w; sc.mask = c->d_mask;
+        sc.z_obs = d_zobs; sc.n_ge = d_nge; sc.null_scores = d_scores; sc.n_total = n_nulls;
+        sc.S = c->S; sc.wprS = c->wprS; sc.rows_are_samples = c->rows_are_samples;
+        if (hs->z_obs) {
+            SDX_CUDA(c, cudaMemcpyAsync(d_zobs, hs->z_obs, sizeof(double) * c->P, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            k_score_observed<<<ceil_div(c->P, 4), 128, 0, c->stream>>>(c->d_trade_obs, RS, sc, d_zobs);
+            timer.count();
+        }
+    }
+
+    float plan_ms = 0, trade_ms = 0;
+    if (n_nulls > 0) {
+        // chains overlapping [null0, null0 + n)
+        const uint64_t null_hi = null0 + (uint64_t)n_nulls;
+        const uint64_t chain_first = null0 / (uint64_t)chain_len;
+        const uint64_t chain_last = (null_hi - 1) / (uint64_t)chain_len;
+        const int64_t n_chains = (int64_t)(chain_last - chain_first + 1);
+        const int64_t NB = 32768;                                   // nulls planned per launch
+        const int seg_cap = (int)(chain_len < 256 ? chain_len : 256);
+        int64_t chains_per_launch = NB / seg_cap;
+        if (chains_per_launch > n_chains) chains_per_launch = n_chains;
+        const int64_t n_segs = (chain_len + seg_cap - 1) / seg_cap;
+        const int64_t n_local_max = chains_per_launch * seg_cap;
+        const int Tn = (int)(T > 0 ? T : 1);
+
+        // level kernel geometry: last[] (R x threads u16) in shared memory when it fits
+        int lv_threads = 128;
+        const size_t smem_cap = c->smem_optin > 4096 ? c->smem_optin - 2048 : 0;
+        while (lv_threads > 32 && (size_t)lv_threads * R * 2 > (lv_threads == 128 ? (size_t)100 * 1024 : smem_cap)) lv_threads >>= 1;
+        const bool last_in_smem = (size_t)lv_threads * R * 2 <= smem_cap;
+        const size_t lv_smem = last_in_smem ? (size_t)lv_threads * R * 2 : 0;
+        if (lv_smem > 48 * 1024)
+            SDX_CUDA(c, cudaFuncSetAttribute(k_plan_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem));
+
+        void *p_lvl, *p_plan, *p_aux = nullptr, *p_carry = nullptr, *p_work = nullptr, *p_out = nullptr, *p_app = nullptr;
+        const size_t lvl_bytes = ((sizeof(uint16_t) * (size_t)n_local_max * Tn + 15) / 16) * 16;
+        if ((rc = sdx_scratch(c, SL_LVL, lvl_bytes + sizeof(int) * n_local_max + 64, &p_lvl))) return rc;
+        int *d_depth = (int *)((char *)p_lvl + lvl_bytes);
+        if ((rc = sdx_scratch(c, SL_PLAN, sizeof(uint2) * (size_t)n_local_max * Tn, &p_plan))) return rc;
+        if (!last_in_smem) {
+            const size_t nb = (size_t)ceil_div(n_local_max, lv_threads) * lv_threads;
+            if ((rc = sdx_scratch(c, SL_AUX, sizeof(uint16_t) * nb * R, &p_aux))) return rc;
+        }
+        const bool need_carry = n_segs > 1;
+        if (need_carry && (rc = sdx_scratch(c, SL_CARRY, sizeof(uint32_t) * mat_words * chains_per_launch, &p_carry))) return rc;
+        if (out_rows && (rc = sdx_scratch(c, SL_OUT, sizeof(uint32_t) * out_per * n_local_max, &p_out))) return rc;
+        if (applied) {
+            if ((rc = sdx_scratch(c, SL_APPLIED, sizeof(unsigned long long) * n_nulls, &p_app))) return rc;
+            SDX_CUDA(c, cudaMemsetAsync(p_app, 0, sizeof(unsigned long long) * n_nulls, c->stream));
+        }
+        int grid_cap = cfg.grid_cap;
+        if (!cfg.smem) {
+            if (grid_cap > chains_per_launch) grid_cap = (int)chains_per_launch;
+            if ((rc = sdx_scratch(c, SL_WORK, sizeof(uint32_t) * mat_words * grid_cap, &p_work))) return rc;
+        }
+
+        for (int64_t cb = 0; cb < n_chains; cb += chains_per_launch) {
+            const int64_t nch = (n_chains - cb) < chains_per_launch ? (n_chains - cb) : chains_per_launch;
+            for (int64_t sg = 0; sg < n_segs; ++sg) {
+                NullIndexing ix;
+                ix.chain0 = chain_first + (uint64_t)cb; ix.chain_len = chain_len; ix.seg_off = sg * seg_cap;
+                const int64_t left = chain_len - sg * seg_cap;
+                ix.seg_len = (int)(left < seg_cap ? left : seg_cap);
+                ix.null_lo = null0; ix.null_hi = null_hi;
+                const int n_local = (int)(nch * ix.seg_len);
+                cudaEventRecord(c->ev[2], c->stream);
+                if (T > 0) {
+                    k_plan_levels<<<ceil_div(n_local, lv_threads), lv_threads, lv_smem, c->stream>>>(
+                        keys, ix, n_local, R, (int)T, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux);
+                    k_plan_sort<<<ceil_div(n_local, 2), 64, 0, c->stream>>>(keys, ix, n_local, R, (int)T, (const uint16_t *)p_lvl,
+                                                                          d_depth, (uint2 *)p_plan);
+                    timer.count(2);
+                }
+                cudaEventRecord(c->ev[3], c->stream);
+                TradeArgs ta{};
+                ta.keys = keys; ta.ix = ix; ta.observed = c->d_trade_obs; ta.work = (uint32_t *)p_work;
+                ta.carry = (uint32_t *)p_carry; ta.plan = (const uint2 *)p_plan; ta.n_units = (int)nch;
+                ta.R = R; ta.RS = RS; ta.T = (int)T; ta.wprL = c->wprL;
+                ta.save_carry = need_carry && sg + 1 < n_segs;
+                ta.out_rows = (uint32_t *)p_out; ta.applied = (unsigned long long *)p_app; ta.sc = sc;
+                const int grid = (int)(nch < grid_cap ? nch : grid_cap);
+                cudaError_t e = dispatch_trade(cfg, grid, c->stream, ta);
+                if (e != cudaSuccess) return sdx_fail(c, SDX_ERR_CUDA, std::string("trade kernel launch failed: ") + cudaGetErrorString(e));
+                timer.count();
+                cudaEventRecord(c->ev[4], c->stream);
+                if (out_rows) {
+                    // staged rows are indexed by the launch-local null index; copy out the requested ids
+                    const bool contiguous = (n_segs == 1);
+                    const int64_t n_copies = contiguous ? 1 : nch;
+                    for (int64_t ci = 0; ci < n_copies; ++ci) {
+                        const int64_t l0 = contiguous ? 0 : ci * ix.seg_len;
+                        const int64_t l1 = contiguous ? n_local : l0 + ix.seg_len;
+                        uint64_t lo = ix.id(l0), hi = ix.id(l1 - 1) + 1;
+                        const uint64_t first = lo;
+                        if (lo < null0) lo = null0;
+                        if (hi > null_hi) hi = null_hi;
+                        if (hi > lo)
+                            SDX_CUDA(c, cudaMemcpyAsync(out_rows + (size_t)(lo - null0) * out_per,
+                                                        (uint32_t *)p_out + (size_t)(l0 + (int64_t)(lo - first)) * out_per,
+                                                        sizeof(uint32_t) * out_per * (hi - lo), cudaMemcpyDeviceToHost, c->stream));
+                    }
+                }
+                SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+                float a_ms = 0, b_ms = 0;
+                cudaEventElapsedTime(&a_ms, c->ev[2], c->ev[3]);
+                cudaEventElapsedTime(&b_ms, c->ev[3], c->ev[4]);
+                plan_ms += a_ms; trade_ms += b_ms;
+            }
+        }
+        if (applied) {
+            std::vector<unsigned long long> tmp((size_t)n_nulls);
+            SDX_CUDA(c, cudaMemcpyAsync(tmp.data(), p_app, sizeof(unsigned long long) * n_nulls, cudaMemcpyDeviceToHost, c->stream));
+            SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+            for (int64_t i = 0; i < n_nulls; ++i) applied[i] = (int64_t)tmp[i];
+        }
+    }
+
+    if (hs) {
+        std::vector<unsigned long long> ge((size_t)c->P);
+        SDX_CUDA(c, cudaMemcpyAsync(ge.data(), d_nge, sizeof(unsigned long long) * c->P, cudaMemcpyDeviceToHost, c->stream));
+        if (hs->z_obs_out) SDX_CUDA(c, cudaMemcpyAsync(hs->z_obs_out, d_zobs, sizeof(double) * c->P, cudaMemcpyDeviceToHost, c->stream));
+        if (hs->null_scores && n_nulls > 0)
+            SDX_CUDA(c, cudaMemcpyAsync(hs->null_scores, d_scores, sizeof(double) * c->P * n_nulls, cudaMemcpyDeviceToHost, c->stream));
+        SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int p = 0; p < c->P; ++p) hs->n_ge[p] = (int64_t)ge[p];
+    }
+    rc = timer.finish();
+    c->timing.plan_ms = plan_ms; c->timing.trade_ms = trade_ms;
+    return rc;
+}
+
+extern "C" int sdx_curveball(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
+                             int64_t chain_len, uint32_t *out_trade_rows, int64_t *applied) {
+    if (!ctx) return SDX_ERR_INVALID;
+    return sdx_run_nulls(ctx, seed, null0, n_nulls, n_trades, chain_len, out_trade_rows, applied, nullptr);
+}
+
+extern "C" int sdx_curveball_replay(sdx_ctx *c, const uint32_t *start, const int32_t *a, const int32_t *b,
+                                    const uint32_t *to_a, int64_t T, uint32_t *out, int64_t *applied) {
+    if (!c) return SDX_ERR_INVALID;
+    SDX_REQUIRE(c, c->d_trade_obs, SDX_ERR_STATE, "sdx_upload_matrix has not been called");
+    SDX_REQUIRE(c, T >= 0 && (T == 0 || (a && b && to_a)), SDX_ERR_INVALID, "schedule arrays missing");
+    const int R = c->R, RS = c->RS, wprL = c->wprL;
+    for (int64_t t = 0; t < T; ++t)
+        SDX_REQUIRE(c, a[t] >= 0 && a[t] < R && b[t] >= 0 && b[t] < R && a[t] != b[t], SDX_ERR_INVALID, "schedule row index out of range");
+    LaunchTimer timer(c);
+    void *p_rows, *p_sched;
+    int rc;
+    const size_t mat = sizeof(uint32_t) * (size_t)R * RS;
+    if ((rc = sdx_scratch(c, 6, mat + 64, &p_rows))) return rc;
+    const size_t sched_bytes = (size_t)T * (8 + 4 * (size_t)wprL) + 64;
+    if ((rc = sdx_scratch(c, 1, sched_bytes, &p_sched))) return rc;
+    uint32_t *d_rows = (uint32_t *)p_rows;
+    unsigned long long *d_ap = (unsigned long long *)((char *)p_rows + mat);
+    if (start) {
+        SDX_CUDA(c, cudaMemsetAsync(d_rows, 0, mat, c->stream));
+        SDX_CUDA(c, cudaMemcpy2DAsync(d_rows, (size_t)RS * 4, start, (size_t)wprL * 4, (size_t)wprL * 4, R, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        SDX_CUDA(c, cudaMemcpyAsync(d_rows, c->d_trade_obs, mat, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    int32_t *d_a = (int32_t *)p_sched, *d_b = d_a + T;
+    uint32_t *d_m = (uint32_t *)(d_b + T);
+    if (T > 0) {
+        SDX_CUDA(c, cudaMemcpyAsync(d_a, a, sizeof(int32_t) * T, cudaMemcpyHostToDevice, c->stream));
+        SDX_CUDA(c, cudaMemcpyAsync(d_b, b, sizeof(int32_t) * T, cudaMemcpyHostToDevice, c->stream));
+        SDX_CUDA(c, cudaMemcpyAsync(d_m, to_a, sizeof(uint32_t) * T * wprL, cudaMemcpyHostToDevice, c->stream));
+    }
+    k_replay<<<1, 32, 0, c->stream>>>(d_rows, RS, wprL, d_a, d_b, d_m, T, d_ap);
+    timer.count();
+    unsigned long long ap = 0;
+    if (out) SDX_CUDA(c, cudaMemcpy2DAsync(out, (size_t)wprL * 4, d_rows, (size_t)RS * 4, (size_t)wprL * 4, R, cudaMemcpyDeviceToHost, c->stream));
+    SDX_CUDA(c, cudaMemcpyAsync(&ap, d_ap, sizeof ap, cudaMemcpyDeviceToHost, c->stream));
+    rc = timer.finish();
+    if (applied) *applied = (int64_t)ap;
+    return rc;
+}
+
+extern "C" int sdx_null_pvalue(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
+                               int64_t chain_len, int stat, const int32_t *modules, int k, const double *z_obs,
+                               int64_t *n_ge, double *null_scores, double *z_obs_out);
+
+int sdx_null_pvalue_fixed(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
+                          int64_t chain_len, const int32_t *modules, int k, const double *z_obs,
+                          int64_t *n_ge, double *null_scores, double *z_obs_out) {
+    HostScore hs;
+    hs.k = k; hs.modules = modules; hs.z_obs = z_obs; hs.n_ge = n_ge; hs.null_scores = null_scores; hs.z_obs_out = z_obs_out;
+    return sdx_run_nulls(ctx, seed, null0, n_nulls, n_trades, chain_len, nullptr, nullptr, &hs);
+}

@@ -1,0 +1,514 @@
+// sdx_scan.cu — exhaustive scan of all feature subsets of size <= 3 under W.
+//
+// Replaces (certifies / seeds) the integral optimum of the ILP of
+// src/superdendrix.py:294-313, 393-401 (optimize_model / build_obj): the ILP's
+// objective at an integral point equals SuperW (src/superdendrix.py:387-391).
+//
+// Algebra, with w+ = max(w, 0):
+//   s_g   = 2 sum_{s in g} w+_s - sum_{s in g} |w_s|
+//   T_gh  = -2 sum_{s in g∩h} w+_s                       (pair table, upper triangle)
+//   P_ghl =    sum_{s in g∩h∩l} w+_s                     (only when g∩h∩{w>0} is non-empty)
+//   W{g} = s_g,  W{g,h} = s_g + s_h + T_gh,
+//   W{g,h,l} = s_g + s_h + s_l + T_gh + T_gl + T_hl + 2 P_ghl
+//
+// Pipeline (all on the ctx stream):
+//   k_scan_prep     w+ vector, packed {w>0} mask, s_g
+//   k_pair_table    one CTA per g: T[g][h] for h > g (bit-AND + weighted bit walk)
+//   k_scan12        singles and pairs
+//   k_scan3         persistent CTAs pull (g-tile, h-block, l-chunk) items from an atomic
+//                   counter; a thread owns NJ values of l with c[gi][j] = s_l + T[g_i][l] in
+//                   registers, streams row h of T (coalesced, L2-resident) and evaluates
+//                   GT x NJ triples per h; every triple of the enumeration is evaluated.
+//   k_scan_collect  per-warp top lists -> candidates above the global bound
+// The candidates are re-scored with the canonical scorer (score_module) so the reported W,
+// coverage and tie order do not depend on the inclusion-exclusion arithmetic.
+#include <float.h>
+
+#include <algorithm>
+
+#include "sdx_trade.cuh"
+
+#define SCAN_NT 256
+#define SCAN_GT 4
+#define SCAN_NJ 4
+#define SCAN_HB 128
+#define SCAN_E 2
+#define SCAN_NL (32 * SCAN_E)
+#define SCAN_MAXW 256          // words per feature row the triple slow path stages in shared memory
+#define SCAN_KEY_NONE 0xffffffffffffffffull
+
+int sdx_score_sets_device(sdx_ctx *c, const int32_t *d_sets, const int32_t *d_prof, int profile0, int64_t n, int k,
+                          double *d_W, int32_t *d_cov, int32_t *d_ovl, int32_t *d_act);
+
+// order-preserving map double -> u64 (for atomicMax on a lower bound)
+__host__ __device__ __forceinline__ unsigned long long enc_f64(double v) {
+    unsigned long long u;
+    memcpy(&u, &v, 8);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double dec_f64(unsigned long long e) {
+    unsigned long long u = (e >> 63) ? (e ^ 0x8000000000000000ull) : ~e;
+    double v;
+    memcpy(&v, &u, 8);
+    return v;
+}
+
+__host__ __device__ __forceinline__ unsigned long long scan_key(int size, int g, int h, int l) {
+    // ascending key == enumeration order (size-major, then lexicographic)
+    return ((unsigned long long)size << 60) | ((unsigned long long)g << 40) | ((unsigned long long)h << 20) | (unsigned long long)l;
+}
+
+// ---------------------------------------------------------------------------
+// Per-warp list of the SCAN_NL best (W, key) seen, one/two entries per lane, in registers.
+// All 32 lanes call every method together.
+// ---------------------------------------------------------------------------
+struct WarpTop {
+    double W[SCAN_E];
+    unsigned long long key[SCAN_E];
+    double worstW;
+    unsigned long long worstKey;
+    int worstSlot;
+    double gate;          // candidates need W >= gate
+
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int e = 0; e < SCAN_E; ++e) { W[e] = -DBL_MAX; key[e] = SCAN_KEY_NONE; }
+        worstW = -DBL_MAX; worstKey = SCAN_KEY_NONE; worstSlot = 0; gate = -DBL_MAX;
+    }
+    __device__ __forceinline__ void find_worst(int lane) {
+        double w = W[0]; unsigned long long k = key[0]; int s = lane * SCAN_E;
+#pragma unroll
+        for (int e = 1; e < SCAN_E; ++e)
+            if (W[e] < w || (W[e] == w && key[e] > k)) { w = W[e]; k = key[e]; s = lane * SCAN_E + e; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ow = __shfl_xor_sync(0xffffffffu, w, o);
+            unsigned long long ok = __shfl_xor_sync(0xffffffffu, k, o);
+            int os = __shfl_xor_sync(0xffffffffu, s, o);
+            bool take = ow < w || (ow == w && (ok > k || (ok == k && os < s)));
+            if (take) { w = ow; k = ok; s = os; }
+        }
+        worstW = w; worstKey = k; worstSlot = s;
+        if (w > gate) gate = w;
+    }
+    __device__ __forceinline__ void insert(double Wc, unsigned long long kc, int lane) {     // warp-uniform arguments
+        if (Wc > worstW || (Wc == worstW && kc < worstKey)) {
+            if (lane == worstSlot / SCAN_E) {
+#pragma unroll
+                for (int e = 0; e < SCAN_E; ++e)
+                    if (e == worstSlot % SCAN_E) { W[e] = Wc; key[e] = kc; }
+            }
+            find_worst(lane);
+        }
+    }
+    __device__ __forceinline__ void offer(bool cand, double Wc, unsigned long long kc, int lane) {
+        unsigned m = __ballot_sync(0xffffffffu, cand);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            insert(__shfl_sync(0xffffffffu, Wc, src), __shfl_sync(0xffffffffu, kc, src), lane);
+        }
+    }
+    __device__ __forceinline__ void refresh(const unsigned long long *g_thr) {
+        double g = dec_f64(*(volatile const unsigned long long *)g_thr);
+        if (g > gate) gate = g;
+    }
+    __device__ __forceinline__ void publish(unsigned long long *g_thr, int lane) {
+        if (lane == 0 && worstKey != SCAN_KEY_NONE) atomicMax(g_thr, enc_f64(worstW));
+    }
+    __device__ __forceinline__ void store(double *oW, unsigned long long *oK, int lane) {
+#pragma unroll
+        for (int e = 0; e < SCAN_E; ++e) { oW[lane * SCAN_E + e] = W[e]; oK[lane * SCAN_E + e] = key[e]; }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// prep: w+ and the packed {w > 0} mask (one thread per sample), then s_g (one warp per feature)
+// ---------------------------------------------------------------------------
+__global__ void k_scan_prep_w(const double *__restrict__ w, const uint32_t *__restrict__ mask, int S,
+                              double *__restrict__ wpos, uint32_t *__restrict__ pos) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    bool in = false;
+    double v = 0.0;
+    if (s < S) { v = w[s]; in = ((mask[s >> 5] >> (s & 31)) & 1u) && v > 0.0; wpos[s] = in ? v : 0.0; }
+    const uint32_t b = __ballot_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0 && s < S) pos[s >> 5] = b;
+}
+
+__global__ void k_scan_prep_s1(const uint32_t *__restrict__ feat, int fstride, int F, int wprS,
+                               const double *__restrict__ w, const uint32_t *__restrict__ mask, double *__restrict__ s1) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= F) return;
+    double pos = 0, neg = 0;
+    for (int wi = lane; wi < wprS; wi += 32) {
+        uint32_t x = feat[(size_t)g * fstride + wi] & mask[wi];
+        while (x) {
+            const int bp = __ffs(x) - 1;
+            x &= x - 1;
+            const double ws = w[wi * 32 + bp];
+            if (ws > 0) pos += ws;
+            neg += fabs(ws);
+        }
+    }
+    pos = warp_sum_f64(pos); neg = warp_sum_f64(neg);
+    if (lane == 0) s1[g] = 2.0 * pos - neg;
+}
+
+// ---------------------------------------------------------------------------
+// pair table: T[g][h] = -2 sum_{s in g∩h, w_s>0} w_s for h > g.  One CTA per g.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pair_table(const uint32_t *__restrict__ feat, int fstride, int F, int wprS,
+                                                    const uint32_t *__restrict__ pos, const double *__restrict__ wpos,
+                                                    double *__restrict__ T, int Fp) {
+    extern __shared__ uint32_t sm[];
+    uint32_t *gp = sm;                 // wprS: feat[g] & pos
+    int *nz = (int *)(sm + wprS);      // indices of the non-zero words of gp, ascending
+    __shared__ int n_nz;
+    for (int g = blockIdx.x; g < F - 1; g += gridDim.x) {
+        __syncthreads();
+        for (int wi = threadIdx.x; wi < wprS; wi += blockDim.x) gp[wi] = feat[(size_t)g * fstride + wi] & pos[wi];
+        __syncthreads();
+        if (threadIdx.x < 32) {        // ordered compaction by warp 0
+            int base = 0;
+            for (int w0 = 0; w0 < wprS; w0 += 32) {
+                const int wi = w0 + threadIdx.x;
+                const bool nzw = wi < wprS && gp[wi] != 0;
+                const unsigned m = __ballot_sync(0xffffffffu, nzw);
+                if (nzw) nz[base + __popc(m & ((1u << threadIdx.x) - 1u))] = wi;
+                base += __popc(m);
+            }
+            if (threadIdx.x == 0) n_nz = base;
+        }
+        __syncthreads();
+        const int nn = n_nz;
+        for (int h = g + 1 + threadIdx.x; h < F; h += blockDim.x) {
+            double acc = 0.0;
+            const uint32_t *rh = feat + (size_t)h * fstride;
+            for (int q = 0; q < nn; ++q) {
+                const int wi = nz[q];
+                uint32_t x = gp[wi] & rh[wi];
+                while (x) {
+                    const int bp = __ffs(x) - 1;
+                    x &= x - 1;
+                    acc += wpos[wi * 32 + bp];
+                }
+            }
+            T[(size_t)g * Fp + h] = -2.0 * acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+struct ScanArgs {
+    const uint32_t *feat; int fstride;     // F rows over samples
+    const uint32_t *samp; int sstride;     // S rows over features
+    const uint32_t *pos;                   // packed {w > 0}
+    const double *wpos;                    // S
+    const double *s1;                      // F
+    const double *T; int Fp;
+    int F, S, wprS, k;
+    int n_gt, n_hb, n_lc;
+    unsigned int *item_counter;
+    unsigned long long *g_thr;
+    unsigned long long *n_scored;
+    double *outW; unsigned long long *outKey;      // per-warp lists (k_scan12 lists first, then k_scan3)
+};
+
+// singles and pairs: CTA-stride over g, threads over h
+__global__ void __launch_bounds__(SCAN_NT) k_scan12(const __grid_constant__ ScanArgs p) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    WarpTop top;
+    top.init();
+    unsigned long long cnt = 0;
+    const int F = p.F;
+    // singles
+    for (int g0 = blockIdx.x * SCAN_NT; g0 < F; g0 += gridDim.x * SCAN_NT) {
+        const int g = g0 + tid;
+        const bool v = g < F;
+        const double W = v ? p.s1[g] : -INFINITY;
+        cnt += v;
+        top.offer(v && W >= top.gate, W, scan_key(1, v ? g : 0, 0, 0), lane);
+    }
+    if (p.k >= 2) {
+        for (int g = blockIdx.x; g < F - 1; g += gridDim.x) {
+            top.refresh(p.g_thr);
+            const double sg = p.s1[g];
+            const double *Tg = p.T + (size_t)g * p.Fp;
+            for (int h0 = g + 1; h0 < F; h0 += SCAN_NT) {
+                const int h = h0 + tid;
+                const bool v = h < F;
+                const double W = v ? (sg + p.s1[h]) + Tg[h] : -INFINITY;
+                cnt += v;
+                const bool cand = v && W >= top.gate;
+                if (__any_sync(0xffffffffu, cand)) top.offer(cand, W, scan_key(2, g, v ? h : 0, 0), lane);
+            }
+            top.publish(p.g_thr, lane);
+        }
+    }
+    top.publish(p.g_thr, lane);
+    const size_t slot = (size_t)(blockIdx.x * (SCAN_NT / 32) + wid) * SCAN_NL;
+    top.store(p.outW + slot, p.outKey + slot, lane);
+    cnt = __reduce_add_sync(0xffffffffu, (unsigned)cnt);       // per-thread counts are small
+    if (lane == 0 && cnt) atomicAdd(p.n_scored, cnt);
+}
+
+__global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ ScanArgs p) {
+    __shared__ uint32_t sI[SCAN_MAXW];
+    __shared__ unsigned s_item;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int F = p.F, Fp = p.Fp;
+    WarpTop top;
+    top.init();
+    unsigned long long cnt = 0;
+    const unsigned total = (unsigned)p.n_gt * p.n_hb * p.n_lc;
+    const int per_gt = p.n_hb * p.n_lc;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(p.item_counter, 1u);
+        __syncthreads();
+        const unsigned it = s_item;
+        if (it >= total) break;
+        const int gt = it / per_gt, rem = it - gt * per_gt, hb = rem / p.n_lc, lc = rem - hb * p.n_lc;
+        const int g0 = gt * SCAN_GT, l0 = lc * (SCAN_NT * SCAN_NJ);
+        const int hlo = max(hb * SCAN_HB, g0 + 1), hhi = min(hb * SCAN_HB + SCAN_HB, F - 1);
+        if (hlo >= hhi || l0 + SCAN_NT * SCAN_NJ - 1 <= hlo) continue;
+        top.refresh(p.g_thr);
+
+        double c[SCAN_GT][SCAN_NJ];
+#pragma unroll
+        for (int j = 0; j < SCAN_NJ; ++j) {
+            const int l = l0 + tid + j * SCAN_NT;
+            const double sl = l < F ? p.s1[l] : 0.0;
+#pragma unroll
+            for (int gi = 0; gi < SCAN_GT; ++gi) {
+                const int g = g0 + gi;
+                c[gi][j] = (l < F && g < l) ? sl + p.T[(size_t)g * Fp + l] : -INFINITY;
+            }
+        }
+
+        for (int h = hlo; h < hhi; ++h) {
+            double sgh[SCAN_GT];
+            bool slow[SCAN_GT];
+            bool any_slow = false;
+            int nvg = 0;
+            const double sh = p.s1[h];
+#pragma unroll
+            for (int gi = 0; gi < SCAN_GT; ++gi) {
+                const int g = g0 + gi;
+                const bool v = g < h;
+                const double tgh = v ? p.T[(size_t)g * Fp + h] : 0.0;
+                sgh[gi] = v ? (p.s1[g] + sh) + tgh : -INFINITY;
+                slow[gi] = v && tgh != 0.0;
+                any_slow |= slow[gi];
+                nvg += v;
+            }
+            const double *Th = p.T + (size_t)h * Fp;
+            double t[SCAN_NJ];
+#pragma unroll
+            for (int j = 0; j < SCAN_NJ; ++j) {
+                const int l = l0 + tid + j * SCAN_NT;
+                const bool v = l > h && l < F;
+                t[j] = v ? Th[l] : -INFINITY;
+                cnt += v ? nvg : 0;
+            }
+            if (!any_slow) {
+#pragma unroll
+                for (int j = 0; j < SCAN_NJ; ++j) {
+                    double W[SCAN_GT];
+                    bool cand = false;
+#pragma unroll
+                    for (int gi = 0; gi < SCAN_GT; ++gi) {
+                        W[gi] = (sgh[gi] + t[j]) + c[gi][j];
+                        cand |= W[gi] >= top.gate;
+                    }
+                    if (__any_sync(0xffffffffu, cand)) {
+                        const int l = l0 + tid + j * SCAN_NT;
+#pragma unroll
+                        for (int gi = 0; gi < SCAN_GT; ++gi)
+                            top.offer(W[gi] >= top.gate, W[gi], scan_key(3, g0 + gi, h, l), lane);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int gi = 0; gi < SCAN_GT; ++gi) {
+                    if (sgh[gi] == -INFINITY) continue;           // uniform
+                    double p3[SCAN_NJ];
+#pragma unroll
+                    for (int j = 0; j < SCAN_NJ; ++j) p3[j] = 0.0;
+                    if (slow[gi]) {                               // uniform: g∩h∩{w>0} is non-empty
+                        const int g = g0 + gi;
+                        __syncthreads();
+                        for (int wi = tid; wi < p.wprS; wi += SCAN_NT)
+                            sI[wi] = p.feat[(size_t)g * p.fstride + wi] & p.feat[(size_t)h * p.fstride + wi] & p.pos[wi];
+                        __syncthreads();
+                        for (int wi = 0; wi < p.wprS; ++wi) {
+                            uint32_t x = sI[wi];
+                            while (x) {
+                                const int bp = __ffs(x) - 1;
+                                x &= x - 1;
+                                const int s = wi * 32 + bp;
+                                const double wp = p.wpos[s];
+                                const uint32_t *sr = p.samp + (size_t)s * p.sstride;
+#pragma unroll
+                                for (int j = 0; j < SCAN_NJ; ++j) {
+                                    const int l = l0 + tid + j * SCAN_NT;
+                                    if (l < F && ((sr[l >> 5] >> (l & 31)) & 1u)) p3[j] += wp;
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < SCAN_NJ; ++j) {
+                        const double W = ((sgh[gi] + t[j]) + c[gi][j]) + 2.0 * p3[j];
+                        const bool cand = W >= top.gate;
+                        if (__any_sync(0xffffffffu, cand))
+                            top.offer(cand, W, scan_key(3, g0 + gi, h, l0 + tid + j * SCAN_NT), lane);
+                    }
+                }
+            }
+        }
+        top.publish(p.g_thr, lane);
+    }
+    const size_t slot = (size_t)((gridDim.x + blockIdx.x) * (SCAN_NT / 32) + wid) * SCAN_NL;      // after the k_scan12 lists
+    top.store(p.outW + slot, p.outKey + slot, lane);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0 && cnt) atomicAdd(p.n_scored, cnt);
+}
+
+__global__ void k_scan_collect(const double *__restrict__ W, const unsigned long long *__restrict__ key, int n,
+                               const unsigned long long *__restrict__ g_thr, unsigned int *__restrict__ n_out,
+                               double *__restrict__ oW, unsigned long long *__restrict__ oK) {
+    const double thr = dec_f64(*g_thr);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (key[i] != SCAN_KEY_NONE && W[i] >= thr) {
+            const unsigned q = atomicAdd(n_out, 1u);
+            oW[q] = W[i]; oK[q] = key[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int sdx_scan(sdx_ctx *c, int profile, int k, int topn, sdx_hit *hits, int64_t *n_scored) {
+    if (!c) return SDX_ERR_INVALID;
+    SDX_REQUIRE(c, c->d_feat && c->d_w, SDX_ERR_STATE, "matrix and weights must be uploaded first");
+    SDX_REQUIRE(c, profile >= 0 && profile < c->P, SDX_ERR_INVALID, "profile index out of range");
+    SDX_REQUIRE(c, k >= 1 && k <= 3, SDX_ERR_UNSUPPORTED, "the exhaustive scan covers k = 1..3");
+    SDX_REQUIRE(c, topn >= 1 && topn <= SCAN_NL - 16 && hits, SDX_ERR_INVALID, "topn must be in 1..48");
+    SDX_REQUIRE(c, c->wprS <= SCAN_MAXW, SDX_ERR_UNSUPPORTED, "the scan supports at most 8192 samples");
+    SDX_REQUIRE(c, c->F < (1 << 20), SDX_ERR_UNSUPPORTED, "the scan supports fewer than 2^20 features");
+    const int F = c->F, S = c->S, wprS = c->wprS;
+    const int Fp = ((F + 3) / 4) * 4;
+    const int grid12 = c->sm_count * 2, grid3 = c->sm_count * 2;
+    const int n_lists = (grid12 + grid3) * (SCAN_NT / 32);
+    const int n_entries = n_lists * SCAN_NL;
+    int rc;
+    void *p_small, *p_T, *p_lists;
+    // small: wpos[S] | s1[F] | pos[wprS] | counters
+    const size_t off_s1 = sizeof(double) * S, off_pos = off_s1 + sizeof(double) * F;
+    const size_t off_cnt = ((off_pos + sizeof(uint32_t) * wprS + 15) / 16) * 16;
+    if ((rc = sdx_scratch(c, 0, off_cnt + 64, &p_small))) return rc;
+    if ((rc = sdx_scratch(c, 10, sizeof(double) * (size_t)F * Fp + 64, &p_T))) return rc;
+    // lists: W[n_entries] | key[n_entries] | candW[n_entries] | candKey[n_entries] | rescoring buffers
+    const int n_resc = SCAN_NL;
+    const size_t list_bytes = (sizeof(double) + sizeof(unsigned long long)) * 2 * (size_t)n_entries;
+    const size_t resc_bytes = n_resc * (3 * sizeof(int32_t) + sizeof(double) + 3 * sizeof(int32_t));
+    if ((rc = sdx_scratch(c, 11, list_bytes + resc_bytes + 64, &p_lists))) return rc;
+    double *d_wpos = (double *)p_small, *d_s1 = (double *)((char *)p_small + off_s1);
+    uint32_t *d_pos = (uint32_t *)((char *)p_small + off_pos);
+    unsigned long long *d_thr = (unsigned long long *)((char *)p_small + off_cnt);
+    unsigned long long *d_nscored = d_thr + 1;
+    unsigned int *d_item = (unsigned int *)(d_thr + 2), *d_ncand = d_item + 1;
+    double *d_T = (double *)p_T;
+    double *d_lW = (double *)p_lists;
+    unsigned long long *d_lK = (unsigned long long *)(d_lW + n_entries);
+    double *d_cW = (double *)(d_lK + n_entries);
+    unsigned long long *d_cK = (unsigned long long *)(d_cW + n_entries);
+    double *d_rW = (double *)(d_cK + n_entries);
+    int32_t *d_rsets = (int32_t *)(d_rW + n_resc), *d_rcov = d_rsets + 3 * n_resc, *d_rovl = d_rcov + n_resc, *d_ract = d_rovl + n_resc;
+
+    LaunchTimer timer(c);
+    const double *d_w = c->d_w + (size_t)profile * S;
+    const uint32_t *d_mask = c->d_mask + (size_t)profile * wprS;
+    struct { unsigned long long thr, nscored; unsigned int item, ncand; } init = {enc_f64(-DBL_MAX), 0ull, 0u, 0u};
+    SDX_CUDA(c, cudaMemcpyAsync(d_thr, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    cudaEventRecord(c->ev[2], c->stream);
+    k_scan_prep_w<<<ceil_div(wprS * 32, 256), 256, 0, c->stream>>>(d_w, d_mask, S, d_wpos, d_pos);
+    k_scan_prep_s1<<<ceil_div(F, 8), 256, 0, c->stream>>>(c->d_feat, wprS, F, wprS, d_w, d_mask, d_s1);
+    timer.count(2);
+    if (k >= 2 && F >= 2) {
+        k_pair_table<<<std::min(F - 1, c->sm_count * 8), 256, sizeof(uint32_t) * 2 * wprS, c->stream>>>(
+            c->d_feat, wprS, F, wprS, d_pos, d_wpos, d_T, Fp);
+        timer.count();
+    }
+    ScanArgs a{};
+    a.feat = c->d_feat; a.fstride = wprS; a.samp = c->d_samp; a.sstride = c->wprF; a.pos = d_pos; a.wpos = d_wpos;
+    a.s1 = d_s1; a.T = d_T; a.Fp = Fp; a.F = F; a.S = S; a.wprS = wprS; a.k = k;
+    a.n_gt = ceil_div(F, SCAN_GT); a.n_hb = ceil_div(F, SCAN_HB); a.n_lc = ceil_div(F, SCAN_NT * SCAN_NJ);
+    a.item_counter = d_item; a.g_thr = d_thr; a.n_scored = d_nscored; a.outW = d_lW; a.outKey = d_lK;
+    SDX_REQUIRE(c, (int64_t)a.n_gt * a.n_hb * a.n_lc < (1ll << 31), SDX_ERR_UNSUPPORTED, "too many scan work items");
+    k_scan12<<<grid12, SCAN_NT, 0, c->stream>>>(a);
+    timer.count();
+    int used_lists = grid12 * (SCAN_NT / 32);
+    if (k >= 3 && F >= 3) {
+        k_scan3<<<grid3, SCAN_NT, 0, c->stream>>>(a);
+        timer.count();
+        used_lists = n_lists;
+    }
+    k_scan_collect<<<c->sm_count, 256, 0, c->stream>>>(d_lW, d_lK, used_lists * SCAN_NL, d_thr, d_ncand, d_cW, d_cK);
+    timer.count();
+    cudaEventRecord(c->ev[3], c->stream);
+    struct { unsigned long long thr, nscored; unsigned int item, ncand; } fin;
+    SDX_CUDA(c, cudaMemcpyAsync(&fin, d_thr, sizeof fin, cudaMemcpyDeviceToHost, c->stream));
+    SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t nc = fin.ncand;
+    std::vector<double> cW(nc);
+    std::vector<unsigned long long> cK(nc);
+    if (nc) {
+        SDX_CUDA(c, cudaMemcpyAsync(cW.data(), d_cW, sizeof(double) * nc, cudaMemcpyDeviceToHost, c->stream));
+        SDX_CUDA(c, cudaMemcpyAsync(cK.data(), d_cK, sizeof(unsigned long long) * nc, cudaMemcpyDeviceToHost, c->stream));
+        SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    std::vector<int> order(nc);
+    for (size_t i = 0; i < nc; ++i) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return cW[x] > cW[y] || (cW[x] == cW[y] && cK[x] < cK[y]); });
+    const int nr = (int)std::min<size_t>(nc, (size_t)std::min(n_resc, topn + 16));
+    std::vector<int32_t> sets(3 * (size_t)n_resc, -1);
+    std::vector<unsigned long long> rkey(nr);
+    for (int i = 0; i < nr; ++i) {
+        const unsigned long long key = cK[order[i]];
+        rkey[i] = key;
+        const int size = (int)(key >> 60);
+        sets[3 * i] = (int)((key >> 40) & 0xfffff);
+        if (size >= 2) sets[3 * i + 1] = (int)((key >> 20) & 0xfffff);
+        if (size >= 3) sets[3 * i + 2] = (int)(key & 0xfffff);
+    }
+    std::vector<double> rW(nr);
+    std::vector<int32_t> rcov(nr);
+    if (nr) {
+        SDX_CUDA(c, cudaMemcpyAsync(d_rsets, sets.data(), sizeof(int32_t) * 3 * nr, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = sdx_score_sets_device(c, d_rsets, nullptr, profile, nr, 3, d_rW, d_rcov, d_rovl, d_ract))) return rc;
+        timer.count();
+        SDX_CUDA(c, cudaMemcpyAsync(rW.data(), d_rW, sizeof(double) * nr, cudaMemcpyDeviceToHost, c->stream));
+        SDX_CUDA(c, cudaMemcpyAsync(rcov.data(), d_rcov, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, c->stream));
+    }
+    rc = timer.finish();
+    if (rc) return rc;
+    cudaEventElapsedTime(&c->timing.score_ms, c->ev[2], c->ev[3]);
+    std::vector<int> ro(nr);
+    for (int i = 0; i < nr; ++i) ro[i] = i;
+    std::sort(ro.begin(), ro.end(), [&](int x, int y) { return rW[x] > rW[y] || (rW[x] == rW[y] && rkey[x] < rkey[y]); });
+    for (int i = 0; i < topn; ++i) {
+        if (i < nr) {
+            const int q = ro[i];
+            hits[i].W = rW[q]; hits[i].coverage = rcov[q];
+            for (int j = 0; j < 3; ++j) hits[i].features[j] = sets[3 * q + j];
+        } else {
+            hits[i].W = -INFINITY; hits[i].coverage = 0;
+            hits[i].features[0] = hits[i].features[1] = hits[i].features[2] = -1;
+        }
+    }
+    if (n_scored) *n_scored = (int64_t)fin.nscored;
+    return SDX_OK;
+}

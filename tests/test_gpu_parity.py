@@ -1,0 +1,254 @@
+"""Parity of the CUDA path (libsdx.so through the C ABI) against the oracle and
+the golden fixtures made from the reference.  Needs a B200: run with -m gpu."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from superdendrix_b200 import bitpack, synth
+from superdendrix_b200.engine import SDX_STAT_FIXED, Engine, SdxError
+
+from conftest import GOLDEN, curveball_cases, load_npz, rows_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def upload_dense(eng, dense):
+    S, F = dense.shape
+    eng.upload_matrix(bitpack.pack_rows(dense.T), S)
+
+
+# ---------------------------------------------------------------- random streams
+def test_philox_known_answers_on_device(eng):
+    ctr = [(0, 0, 0, 0), (0xffffffff,) * 4, (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344)]
+    key = [(0, 0), (0xffffffff,) * 2, (0xa4093822, 0x299f31d0)]
+    want = [(0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)]
+    out = eng.test_philox(ctr, key)
+    assert [tuple(int(x) for x in r) for r in out] == want
+
+
+@pytest.mark.parametrize("R", [2, 3, 400, 770, 65535])
+def test_trade_pairs_match_oracle(eng, R):
+    a, b = eng.test_trade_pairs(1764, 12345678901, 300, R)
+    for t in range(300):
+        assert (int(a[t]), int(b[t])) == oracle.trade_pair(1764, 12345678901, t, R)
+
+
+# ---------------------------------------------------------------- Curveball: replay of the reference's own schedules
+@pytest.mark.parametrize("name", ["tall_small", "wide_small", "square", "short_run", "c0_shape"])
+def test_replay_reproduces_reference_bit_for_bit(eng, name):
+    cases, _ = curveball_cases()
+    c = cases[name]
+    upload_dense(eng, c["dense"])
+    rows = None
+    for i in range(c["a"].shape[0]):
+        rows, applied = eng.curveball_replay(c["a"][i], c["b"][i], c["to_a"][i], start_rows=rows)
+        assert np.array_equal(rows, c["out"][i]), "null %d differs from the reference output" % i
+        assert applied == int(c["to_a"][i].any(axis=1).sum())
+
+
+# ---------------------------------------------------------------- Curveball: canonical streams vs the oracle
+def _dense_cases():
+    rng = np.random.default_rng(11)
+    cases, _ = curveball_cases()
+    out = {
+        "c0_shape": cases["c0_shape"]["dense"],                        # 770 x ~384: rows = features, G=8
+        "wide": (rng.random((60, 300)) < 0.1).astype(np.uint8),         # rows = samples
+        "tall": (rng.random((300, 41)) < 0.2).astype(np.uint8),
+        "two_rows": (rng.random((2, 90)) < 0.4).astype(np.uint8),
+        "dense_rows": (rng.random((40, 1500)) < 0.5).astype(np.uint8),  # 47 words: G=16; long re-deals
+        "long_rows": (rng.random((50, 3000)) < 0.05).astype(np.uint8),  # 94 words: G=32, V=4
+        "c3_like": (rng.random((64, 5000)) < 0.01).astype(np.uint8),    # 157 words: G=32, V=5
+        "max_rows": (rng.random((30, 8000)) < 0.02).astype(np.uint8),   # 250 words: G=32, V=8
+    }
+    return out
+
+
+@pytest.mark.parametrize("name", list(_dense_cases().keys()))
+def test_curveball_matches_oracle_bit_for_bit(eng, name):
+    dense = _dense_cases()[name]
+    upload_dense(eng, dense)
+    obs = rows_of(dense)
+    R, L, wpr, ras = eng.trade_shape()
+    assert (R, wpr) == obs.shape and ras == (dense.shape[1] >= dense.shape[0])
+    n = 6
+    T = 5 * R
+    want, want_ap = oracle.curveball_nulls(obs, seed=1764, null0=3, n=n, n_trades=T, chain_len=1)
+    got, got_ap = eng.curveball(1764, 3, n, n_trades=-1, chain_len=1)
+    assert np.array_equal(got_ap, want_ap)
+    assert np.array_equal(got, want)
+    # margins (G1)
+    for m in got:
+        assert np.array_equal(bitpack.popcount_rows(m), bitpack.popcount_rows(obs))
+        assert np.array_equal(bitpack.unpack_rows(m, L).sum(0), bitpack.unpack_rows(obs, L).sum(0))
+
+
+@pytest.mark.parametrize("chain_len,null0,n", [(4, 0, 9), (4, 2, 7), (1000, 0, 5), (3, 7, 4)])
+def test_chained_nulls_match_oracle(eng, chain_len, null0, n):
+    cases, _ = curveball_cases()
+    dense = cases["c0_shape"]["dense"]
+    upload_dense(eng, dense)
+    obs = rows_of(dense)
+    want, want_ap = oracle.curveball_nulls(obs, 99, null0, n, 5 * obs.shape[0], chain_len)
+    got, got_ap = eng.curveball(99, null0, n, -1, chain_len)
+    assert np.array_equal(got_ap, want_ap)
+    assert np.array_equal(got, want)
+
+
+def test_long_chain_crosses_segment_boundaries(eng):
+    """chain_len > 256 forces the carry buffer between launches."""
+    rng = np.random.default_rng(5)
+    dense = (rng.random((24, 70)) < 0.3).astype(np.uint8)
+    upload_dense(eng, dense)
+    obs = rows_of(dense)
+    want, _ = oracle.curveball_nulls(obs, 7, 0, 600, 5 * obs.shape[0], 600)
+    got, _ = eng.curveball(7, 0, 600, -1, 600)
+    assert np.array_equal(got, want)
+    want2, _ = oracle.curveball_nulls(obs, 7, 250, 30, 5 * obs.shape[0], 600)
+    got2, _ = eng.curveball(7, 250, 30, -1, 600)
+    assert np.array_equal(got2, want2)
+
+
+def test_results_do_not_depend_on_batching(eng):
+    cases, _ = curveball_cases()
+    upload_dense(eng, cases["c0_shape"]["dense"])
+    whole, _ = eng.curveball(5, 0, 40, -1, 1)
+    parts = [eng.curveball(5, lo, 10, -1, 1)[0] for lo in (0, 10, 20, 30)]
+    assert np.array_equal(whole, np.concatenate(parts))
+
+
+def test_zero_trades_and_zero_nulls(eng):
+    rng = np.random.default_rng(1)
+    dense = (rng.random((10, 33)) < 0.3).astype(np.uint8)
+    upload_dense(eng, dense)
+    got, ap = eng.curveball(1, 0, 2, n_trades=0)
+    assert np.array_equal(got[0], rows_of(dense)) and ap.tolist() == [0, 0]
+    got, ap = eng.curveball(1, 0, 0)
+    assert got.shape[0] == 0
+
+
+# ---------------------------------------------------------------- SuperW
+def test_score_sets_match_reference_superw(eng):
+    z = load_npz("superw.npz")
+    dense = z["dense"]
+    S, F = dense.shape
+    upload_dense(eng, dense)
+    eng.upload_weights(z["weights"])
+    res = eng.score_sets(z["modules"], z["kind"])
+    for i in range(len(z["W"])):
+        w = z["weights"][z["kind"][i]]
+        assert abs(res["W"][i] - z["W"][i]) <= 1e-9 * max(1.0, np.abs(w).sum())
+    assert np.array_equal(res["coverage"], z["cov"])
+    assert np.array_equal(res["overlap"], z["overlap"])
+    assert np.array_equal(res["act_cov"], z["act_cov"])
+
+
+def test_score_sets_with_sample_mask_match_oracle(eng):
+    z = load_npz("superw.npz")
+    dense = z["dense"]
+    S, F = dense.shape
+    rows = bitpack.pack_rows(dense.T)
+    upload_dense(eng, dense)
+    w = z["weights"][:2].copy()
+    keep = np.stack([np.arange(S) % 4 != 0, np.arange(S) % 3 != 1])
+    eng.upload_weights(w, keep)
+    rng = np.random.default_rng(3)
+    sets = np.full((200, 5), -1, dtype=np.int32)
+    for i in range(200):
+        k = rng.integers(1, 6)
+        sets[i, :k] = rng.choice(F, size=k, replace=False)
+    prof = rng.integers(0, 2, size=200).astype(np.int32)
+    res = eng.score_sets(sets, prof)
+    for i in range(200):
+        p = prof[i]
+        feats = sets[i][sets[i] >= 0]
+        W, cov, ov, ac = oracle.score_set(rows, S, feats, np.where(keep[p], w[p], 0.0),
+                                          bitpack.pack_mask(np.nonzero(keep[p])[0], S))
+        assert abs(res["W"][i] - W) <= 1e-9 * np.abs(w[p]).sum()
+        assert (res["coverage"][i], res["overlap"][i], res["act_cov"][i]) == (cov, ov, ac)
+
+
+def test_feature_scores_match_oracle(eng):
+    dense, _, _ = synth.feature_matrix(770, 400)
+    S, F = dense.shape
+    w = synth.weights(S, 2)
+    upload_dense(eng, dense)
+    eng.upload_weights(w)
+    rows = bitpack.pack_rows(dense.T)
+    for p in range(2):
+        sw, W1, cnt, best = oracle.feature_scores(rows, S, w[p])
+        got = eng.feature_scores(p)
+        assert np.allclose(got["sum_w"], sw, rtol=0, atol=1e-9 * np.abs(w[p]).sum())
+        assert np.allclose(got["W1"], W1, rtol=0, atol=1e-9 * np.abs(w[p]).sum())
+        assert np.array_equal(got["count"], cnt)
+        assert got["best_single"] == best
+
+
+# ---------------------------------------------------------------- null loop, fixed statistic
+@pytest.mark.parametrize("shape", [(770, 400), (120, 300)])
+def test_null_pvalue_fixed_matches_oracle(eng, shape):
+    dense, _, _ = synth.feature_matrix(*shape)
+    S, F = dense.shape
+    P = 3
+    w = synth.weights(S, P)
+    keep = np.ones((P, S), bool)
+    keep[1, ::7] = False
+    upload_dense(eng, dense)
+    eng.upload_weights(w, keep)
+    order = np.argsort(-dense.sum(0), kind="stable")
+    modules = np.stack([np.sort(order[1:4]), np.sort(order[0:3]), np.array([order[5], order[9], -1])]).astype(np.int32)
+    n = 24
+    res = eng.null_pvalue(1764, 0, n, modules, chain_len=1, stat=SDX_STAT_FIXED, want_scores=True)
+    obs = rows_of(dense)
+    R, L, wpr, ras = eng.trade_shape()
+    nulls, _ = oracle.curveball_nulls(obs, 1764, 0, n, 5 * R, 1)
+    frows = bitpack.pack_rows(dense.T)
+    for p in range(P):
+        wm = np.where(keep[p], w[p], 0.0)
+        mk = bitpack.pack_mask(np.nonzero(keep[p])[0], S)
+        feats = modules[p][modules[p] >= 0]
+        z, _, _, _ = oracle.score_set(frows, S, feats, wm, mk)
+        assert abs(res["z_obs"][p] - z) <= 1e-9 * np.abs(wm).sum()
+        want = []
+        for i in range(n):
+            d = bitpack.unpack_rows(nulls[i], L)
+            fr = bitpack.pack_rows(d.T) if ras else nulls[i]
+            want.append(oracle.score_set(fr, S, feats, wm, mk)[0])
+        want = np.array(want)
+        assert np.allclose(res["null_scores"][p], want, rtol=0, atol=1e-9 * np.abs(wm).sum())
+        # exceedance count is computed from the device's own scores
+        assert res["n_ge"][p] == int((res["null_scores"][p] >= res["z_obs"][p]).sum())
+    # sharded ranges add up (what the multi-GPU path relies on)
+    parts = [eng.null_pvalue(1764, lo, 8, modules, z_obs=res["z_obs"])["n_ge"] for lo in (0, 8, 16)]
+    assert np.array_equal(np.sum(parts, axis=0), res["n_ge"])
+
+
+# ---------------------------------------------------------------- error behaviour
+def test_errors_are_reported_not_fatal(eng):
+    dense, _, _ = synth.feature_matrix(100, 50)
+    upload_dense(eng, dense)
+    eng.upload_weights(synth.weights(100, 1))
+    with pytest.raises(SdxError):
+        eng.score_sets([[0, 1, 10 ** 6]])
+    with pytest.raises(SdxError):
+        eng.upload_weights(np.zeros((1, 99)))
+    with pytest.raises(SdxError):
+        eng.curveball(1, 0, 1, chain_len=0)
+    bad = bitpack.pack_rows(dense.T).copy()
+    bad[0, -1] |= 0x80000000
+    with pytest.raises(SdxError):
+        eng.upload_matrix(bad, 100)
+    # engine is still usable
+    upload_dense(eng, dense)
+    eng.upload_weights(synth.weights(100, 1))
+    assert eng.score_sets([[0, 1, 2]])["W"].shape == (1,)
