@@ -147,10 +147,20 @@ int sdx_scan(sdx_ctx *ctx, int profile, int k, int topn, sdx_hit *hits, int64_t 
 
 /* conditional_permutation_test (src/superdendrix.py:361-384) for one module of
  * one profile: counts[i] = #{t < n_perm : W(M with g_i := random |g_i|-subset
- * of the profile's samples) >= W(M)}.  real_W: W(M) as used in the comparison.
- * Draws: stream (PERM, id = perm_id0 + i, t). */
+ * of the profile's samples) >= W(M)} (:372-374); the caller applies the
+ * argmax / removal rule of :380-382 and :151-158.  real_W[i] (k values, may be
+ * NULL): W(M) as used in the comparison of slot i.  Empty slots (-1) get
+ * counts[i] = -1.  Draws: stream (PERM, id = perm_id0 + i, t). */
 int sdx_condperm(sdx_ctx *ctx, int profile, const int32_t *module, int k, uint64_t seed,
                  uint64_t perm_id0, int64_t n_perm, int64_t *counts, double *real_W);
+
+/* The same for n_jobs (profile, module) pairs in one call (modules: n_jobs x k,
+ * counts / real_W: n_jobs x k) — the genome-wide screen of BASELINE configs[4].
+ * Every job uses streams perm_id0 .. perm_id0 + k - 1, exactly as n_jobs
+ * separate sdx_condperm calls would. */
+int sdx_condperm_batch(sdx_ctx *ctx, const int32_t *profile_of_job, const int32_t *modules, int64_t n_jobs,
+                       int k, uint64_t seed, uint64_t perm_id0, int64_t n_perm, int64_t *counts,
+                       double *real_W);
 
 /* scipy.stats.ranksums as called at utils/compute_p_value.py:306-318 and
  * utils/compute_ranksum_pval.py:116-128 for n_jobs (profile, module) pairs:

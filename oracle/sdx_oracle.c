@@ -147,15 +147,53 @@ SDXO_API void sdxo_trade_pair(uint64_t seed, uint64_t null_id, uint32_t t, uint3
     *a = x; *b = y;
 }
 
+/* Draw `attempt` of pick i of trade t of null `null_id` (DEAL stream):
+ * word (i & 3) of the Philox block with counter
+ *   ((i >> 2) | (attempt << 16), t, id_lo, (id_hi & 0x3fffffff) | (DEAL << 30)).
+ * Every pick owns its own sub-stream, so the picks of one trade can be drawn
+ * in parallel and a (rare) Lemire rejection of one pick does not shift the
+ * draws of the others. */
+static uint32_t deal_draw(uint64_t seed, uint64_t null_id, uint32_t t, uint32_t i, uint32_t attempt) {
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ctr[4] = {(i >> 2) | (attempt << 16), t, (uint32_t)null_id,
+                       ((uint32_t)(null_id >> 32) & 0x3fffffffu) | ((uint32_t)STREAM_DEAL << 30)};
+    uint32_t out[4];
+    sdxo_philox4x32_10(ctr, key, out);
+    return out[i & 3];
+}
+
+/* exactly uniform integer in [0, m) for pick i (Lemire with rejection) */
+static uint32_t deal_below(uint64_t seed, uint64_t null_id, uint32_t t, uint32_t i, uint32_t m) {
+    uint32_t attempt = 0;
+    uint64_t prod = (uint64_t)deal_draw(seed, null_id, t, i, attempt) * m;
+    uint32_t lo = (uint32_t)prod;
+    if (lo < m) {
+        uint32_t thr = (uint32_t)(-m) % m;
+        while (lo < thr) {
+            prod = (uint64_t)deal_draw(seed, null_id, t, i, ++attempt) * m;
+            lo = (uint32_t)prod;
+        }
+    }
+    return (uint32_t)(prod >> 32);
+}
+
+SDXO_API uint32_t sdxo_deal_draw(uint64_t seed, uint64_t null_id, uint32_t t, uint32_t i, uint32_t attempt) {
+    return deal_draw(seed, null_id, t, i, attempt);
+}
+
 /* One canonical trade on packed rows ra, rb (wpr words each).
  * Restates src/curveball.py:25-35: keep the common part, skip when one row
  * contains the other (:29), re-deal the symmetric difference so that both row
  * sizes are preserved (:30-35).  The uniformly random |a\b|-subset that the
- * reference obtains by shuffle(tot)[:L] (:32-34) is obtained here by drawing
- * k = min(|a\b|, |b\a|) elements without replacement for the smaller side,
- * element order = ascending bit index.  Returns 1 if the trade was applied. */
-static int trade_canonical(uint32_t *ra, uint32_t *rb, int wpr, stream_t *deal,
-                           uint32_t *rem, uint32_t *pick) {
+ * reference obtains by shuffle(tot)[:L] (:32-34) is obtained here as a
+ * uniformly random k-subset, k = min(|a\b|, |b\a|), for the smaller side:
+ * the n symmetric-difference elements are ranked 0..n-1 in ascending bit
+ * order and the ranks are chosen with Floyd's algorithm
+ *     for i in 0..k-1:  j = n-k+i;  r = below_i(j+1);  chosen += (r in chosen ? j : r)
+ * which yields every k-subset with equal probability.
+ * `chosen` is scratch of at least wpr+1 words.  Returns 1 if the trade was applied. */
+static int trade_canonical(uint32_t *ra, uint32_t *rb, int wpr, uint64_t seed, uint64_t null_id, uint32_t t,
+                           uint32_t *chosen) {
     int la = 0, lb = 0;
     for (int i = 0; i < wpr; ++i) {
         la += popc32(ra[i] & ~rb[i]);
@@ -165,23 +203,20 @@ static int trade_canonical(uint32_t *ra, uint32_t *rb, int wpr, stream_t *deal,
     int n = la + lb;
     int small_is_a = la <= lb;
     int k = small_is_a ? la : lb;
-    for (int i = 0; i < wpr; ++i) { rem[i] = ra[i] ^ rb[i]; pick[i] = 0; }
-    for (int j = 0; j < k; ++j) {
-        uint32_t r = stream_below(deal, (uint32_t)(n - j));
-        int i = 0;
-        for (;; ++i) {
-            uint32_t c = (uint32_t)popc32(rem[i]);
-            if (r < c) break;
-            r -= c;
-        }
-        uint32_t bit = 1u << nth_set_bit(rem[i], (int)r);
-        rem[i] ^= bit;
-        pick[i] |= bit;
+    memset(chosen, 0, sizeof(uint32_t) * ((size_t)wpr + 1));
+    for (int i = 0; i < k; ++i) {
+        uint32_t j = (uint32_t)(n - k + i);
+        uint32_t r = deal_below(seed, null_id, t, (uint32_t)i, j + 1);
+        if ((chosen[r >> 5] >> (r & 31)) & 1u) r = j;
+        chosen[r >> 5] |= 1u << (r & 31);
     }
+    uint32_t rank = 0;
     for (int i = 0; i < wpr; ++i) {
-        uint32_t ab = ra[i] & rb[i];
-        if (small_is_a) { ra[i] = ab | pick[i]; rb[i] = ab | rem[i]; }
-        else            { rb[i] = ab | pick[i]; ra[i] = ab | rem[i]; }
+        uint32_t ab = ra[i] & rb[i], sym = ra[i] ^ rb[i], pick = 0;
+        for (uint32_t x = sym; x; x &= x - 1, ++rank)
+            if ((chosen[rank >> 5] >> (rank & 31)) & 1u) pick |= x & (0u - x);
+        if (small_is_a) { ra[i] = ab | pick; rb[i] = ab | (sym ^ pick); }
+        else            { rb[i] = ab | pick; ra[i] = ab | (sym ^ pick); }
     }
     return 1;
 }
@@ -190,17 +225,14 @@ static int trade_canonical(uint32_t *ra, uint32_t *rb, int wpr, stream_t *deal,
  * on the packed form of r_hp (R rows over the longer dimension), in place,
  * for null index `null_id`.  Returns the number of applied trades. */
 SDXO_API int64_t sdxo_curveball(uint32_t *rows, int R, int wpr, uint64_t seed, uint64_t null_id, int64_t n_trades) {
-    uint32_t *rem = (uint32_t *)malloc(sizeof(uint32_t) * 2 * (size_t)wpr);
-    uint32_t *pick = rem + wpr;
+    uint32_t *chosen = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)wpr + 1));
     int64_t applied = 0;
     for (int64_t t = 0; t < n_trades; ++t) {
         uint32_t a, b;
         sdxo_trade_pair(seed, null_id, (uint32_t)t, (uint32_t)R, &a, &b);
-        stream_t deal;
-        stream_init(&deal, seed, STREAM_DEAL, null_id, (uint32_t)t);
-        applied += trade_canonical(rows + (size_t)a * wpr, rows + (size_t)b * wpr, wpr, &deal, rem, pick);
+        applied += trade_canonical(rows + (size_t)a * wpr, rows + (size_t)b * wpr, wpr, seed, null_id, (uint32_t)t, chosen);
     }
-    free(rem);
+    free(chosen);
     return applied;
 }
 

@@ -50,7 +50,7 @@ struct sdx_ctx {
     int *d_nsamp = nullptr;       // P: popcount of the mask
 
     // reusable scratch
-    DevBuf scratch[12];
+    DevBuf scratch[16];
 };
 
 inline int sdx_fail(sdx_ctx *c, int code, const std::string &msg) {

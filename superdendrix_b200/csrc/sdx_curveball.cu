@@ -13,11 +13,14 @@
 //                   earlier trade on those rows is in a lower level, so running
 //                   level by level is identical to the sequential order.
 //   k_plan_sort     one WARP per null: counting sort of the trades by level into
-//                   the plan (a, b, t | END flag on the last trade of a level).
+//                   the plan (a | b << 16, t) plus the level offsets.
 //   k_trade         one CTA per chain segment: matrix resident in shared memory
 //                   (or in L2/global when it does not fit), groups of G lanes
-//                   execute the trades of a level concurrently, __syncthreads
-//                   between levels; then the fused scorer and the outputs.
+//                   execute the trades of a level concurrently (plan entries
+//                   prefetched one round ahead), __syncthreads between levels;
+//                   then the fused scorer and the outputs.
+#include <stdlib.h>
+
 #include "sdx_trade.cuh"
 
 // ---------------------------------------------------------------------------
@@ -69,7 +72,7 @@ __global__ void k_plan_levels(const __grid_constant__ PhiloxKeys keys, NullIndex
 #define SDX_HCAP 2048
 __global__ void k_plan_sort(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T,
                             const uint16_t *__restrict__ lvl, const int *__restrict__ depth,
-                            uint2 *__restrict__ plan) {
+                            uint2 *__restrict__ plan, uint16_t *__restrict__ offs, int offs_stride) {
     __shared__ uint32_t hist_smem[2][SDX_HCAP + 2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n = blockIdx.x * (blockDim.x >> 5) + wid;
@@ -83,9 +86,9 @@ __global__ void k_plan_sort(const __grid_constant__ PhiloxKeys keys, NullIndexin
         for (int t = lane; t < T; t += 32) {
             uint32_t a, b;
             trade_pair(keys, null_id, (uint32_t)t, (uint32_t)R, a, b);
-            out[t] = make_uint2(a | (b << 16), (uint32_t)t | SDX_PLAN_END);
+            out[t] = make_uint2(a | (b << 16), (uint32_t)t);
         }
-        return;
+        return;                 // k_trade runs such a null one trade per level, in order
     }
     for (int l = lane; l <= D + 1; l += 32) hist[l] = 0;
     __syncwarp();
@@ -105,17 +108,15 @@ __global__ void k_plan_sort(const __grid_constant__ PhiloxKeys keys, NullIndexin
         carry += __shfl_sync(0xffffffffu, inc, 31);
     }
     __syncwarp();
+    uint16_t *of = offs + (size_t)n * offs_stride;          // of[l] = first entry of level l+1, of[D] = T
+    for (int l = lane; l < D; l += 32) of[l] = (uint16_t)hist[l + 1];
+    if (lane == 0) of[D] = (uint16_t)T;
+    __syncwarp();
     for (int t = lane; t < T; t += 32) {
         uint32_t a, b;
         trade_pair(keys, null_id, (uint32_t)t, (uint32_t)R, a, b);
         uint32_t pos = atomicAdd(&hist[lv[t]], 1u);
         out[pos] = make_uint2(a | (b << 16), (uint32_t)t);
-    }
-    __syncwarp();
-    __threadfence_block();
-    for (int l = 1 + lane; l <= D; l += 32) {     // hist[l] is now the end offset of level l
-        uint32_t e = hist[l];
-        if (e > 0) out[e - 1].y |= SDX_PLAN_END;
     }
 }
 
@@ -142,6 +143,9 @@ struct TradeArgs {
     uint32_t *work;                   // gridDim.x x R x RS (global-resident variant only)
     uint32_t *carry;                  // n_units x R x RS: chain state between launches (or null)
     const uint2 *plan;                // n_local x T
+    const uint16_t *offs;             // n_local x offs_stride level offsets
+    const int *depth;                 // n_local
+    int offs_stride;
     int n_units;                      // chain segments in this launch
     int R, RS, T, wprL;
     int save_carry;
@@ -150,15 +154,22 @@ struct TradeArgs {
     ScoreArgs sc;
 };
 
-template <int G, int V, bool SMEM>
-__global__ void __launch_bounds__(512) k_trade(const __grid_constant__ TradeArgs p) {
+// out-of-line copy of the scorer for the trade kernel: keeps its registers out of the trade loop's budget
+static __device__ __noinline__ SetScore score_module_call(const uint32_t *rows, int RS, bool rows_are_samples, const int32_t *mod, int k,
+                                                          const double *w, const uint32_t *mask, int S, int lane) {
+    return score_module(rows, RS, rows_are_samples, mod, k, w, mask, S, lane);
+}
+
+// LB selects the launch bounds: 0 = (512, 1), 1 = (128, 5), 2 = (256, 5) — the latter two bound the
+// registers so that five CTAs (five nulls) stay resident per SM when the matrix fits five times in shared memory.
+template <int G, int V, bool SMEM, int LB>
+__global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : 256), LB == 0 ? 1 : 5) k_trade(const __grid_constant__ TradeArgs p) {
     extern __shared__ __align__(16) uint32_t smem_rows[];
     __shared__ unsigned int s_applied;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NW = blockDim.x >> 5;
     constexpr int GPW = 32 / G;                 // groups per warp
-    const int NG = NW * GPW;                    // groups per CTA (<= 32)
+    const int NG = NW * GPW;                    // groups per CTA
     const int sub = lane & (G - 1);
-    const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     const int myg = wid * GPW + (lane / G);
     const int R = p.R, RS = p.RS, T = p.T;
     const int nvec = R * RS / 4;
@@ -179,39 +190,32 @@ __global__ void __launch_bounds__(512) k_trade(const __grid_constant__ TradeArgs
             __syncthreads();
 
             // ---- trades, level by level -------------------------------------
-            const uint2 *pl = p.plan + (size_t)local * T;
             unsigned int my_applied = 0;
-            int wb = 0, wpos = 0;                 // window base (entries), position inside the 64-entry window
-            const uint2 none = make_uint2(0u, SDX_PLAN_END);
-            uint2 e0 = (lane < T) ? pl[lane] : none;
-            uint2 e1 = (32 + lane < T) ? pl[32 + lane] : none;
-            uint32_t f0 = __ballot_sync(0xffffffffu, e0.y & SDX_PLAN_END);
-            uint32_t f1 = __ballot_sync(0xffffffffu, e1.y & SDX_PLAN_END);
-            int pos = 0;
-            while (pos < T) {
-                const uint64_t flags = ((uint64_t)f1 << 32 | f0) >> wpos;
-                int cnt = NG;
-                const uint32_t fl = (uint32_t)flags & ((NG == 32) ? 0xffffffffu : ((1u << NG) - 1u));
-                const bool level_end = fl != 0;
-                if (level_end) cnt = __ffs(fl);
-                if (cnt > T - pos) cnt = T - pos;
-                const int idx = wpos + myg;
-                uint32_t x0 = __shfl_sync(0xffffffffu, e0.x, idx & 31), y0 = __shfl_sync(0xffffffffu, e0.y, idx & 31);
-                uint32_t x1 = __shfl_sync(0xffffffffu, e1.x, idx & 31), y1 = __shfl_sync(0xffffffffu, e1.y, idx & 31);
-                const uint32_t ex = idx < 32 ? x0 : x1, ey = idx < 32 ? y0 : y1;
-                if (myg < cnt) {
-                    bool ap = trade_rows<G, V>(rows, RS, ex & 0xffffu, ex >> 16, ey & ~SDX_PLAN_END, null_id, p.keys, sub, gmask);
+            if (T > 0) {
+                const uint2 *pl = p.plan + (size_t)local * T;
+                const uint16_t *of = p.offs + (size_t)local * p.offs_stride;
+                int D = p.depth[local];
+                const bool seq = D >= SDX_HCAP;          // very deep schedule: one trade per level, in order
+                if (seq) D = T;
+                // level l covers plan entries [OFF(l), OFF(l+1)); e2 = end of level l+1, fetched one level ahead
+                auto OFF = [&](int lv) -> int { return seq ? lv : (int)of[lv]; };
+                int l = 0, base = OFF(0), e = OFF(1);
+                int e2 = (D >= 2) ? OFF(2) : e;
+                const uint2 none = make_uint2(0u, 0u);
+                uint2 ent_n = (base + myg < e) ? pl[base + myg] : none;
+                while (l < D) {
+                    const uint2 ent = ent_n;
+                    const bool act = base + myg < e;
+                    int nbase = base + NG, nl = l, ne = e;
+                    const bool level_end = nbase >= e;
+                    if (level_end) { nl = l + 1; nbase = e; ne = e2; }
+                    ent_n = (nl < D && nbase + myg < ne) ? pl[nbase + myg] : none;
+                    if (level_end) e2 = (nl + 2 <= D) ? OFF(nl + 2) : ne;
+                    const bool ap = trade_rows<G, V>(rows, RS, act, ent.x & 0xffffu, ent.x >> 16, ent.y, null_id, p.keys, sub);
                     my_applied += (ap && sub == 0) ? 1u : 0u;
+                    if (level_end) __syncthreads();
+                    base = nbase; l = nl; e = ne;
                 }
-                __syncwarp();
-                pos += cnt; wpos += cnt;
-                if (wpos >= 32) {
-                    wpos -= 32; wb += 32;
-                    e0 = e1; f0 = f1;
-                    e1 = (wb + 32 + lane < T) ? pl[wb + 32 + lane] : none;
-                    f1 = __ballot_sync(0xffffffffu, e1.y & SDX_PLAN_END);
-                }
-                if (level_end) __syncthreads();
             }
             __syncthreads();
 
@@ -230,9 +234,9 @@ __global__ void __launch_bounds__(512) k_trade(const __grid_constant__ TradeArgs
             }
             if (emit && p.sc.n_profiles > 0) {
                 for (int pr = wid; pr < p.sc.n_profiles; pr += NW) {
-                    SetScore sc = score_module(rows, RS, p.sc.rows_are_samples != 0, p.sc.modules + (size_t)pr * p.sc.k,
-                                               p.sc.k, p.sc.w + (size_t)pr * p.sc.S, p.sc.mask + (size_t)pr * p.sc.wprS,
-                                               p.sc.S, lane);
+                    SetScore sc = score_module_call(rows, RS, p.sc.rows_are_samples != 0, p.sc.modules + (size_t)pr * p.sc.k,
+                                                    p.sc.k, p.sc.w + (size_t)pr * p.sc.S, p.sc.mask + (size_t)pr * p.sc.wprS,
+                                                    p.sc.S, lane);
                     if (lane == 0) {
                         if (sc.W >= p.sc.z_obs[pr]) atomicAdd(&p.sc.n_ge[pr], 1ull);
                         if (p.sc.null_scores) p.sc.null_scores[(size_t)pr * p.sc.n_total + (null_id - p.ix.null_lo)] = sc.W;
@@ -294,7 +298,7 @@ __global__ void k_replay(uint32_t *rows, int RS, int wprL, const int32_t *a, con
 // host side
 // ---------------------------------------------------------------------------
 struct TradeConfig {
-    int G, V;
+    int G, V, LB;
     bool smem;
     int threads;
     size_t smem_bytes;
@@ -303,13 +307,22 @@ struct TradeConfig {
 
 static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
     const int w = c->wprL;
-    if (w <= 32) { cfg->G = 8; cfg->V = 4; }
-    else if (w <= 64) { cfg->G = 16; cfg->V = 4; }
+    if (w <= 32) { cfg->G = 4; cfg->V = 8; }
+    else if (w <= 64) { cfg->G = 8; cfg->V = 8; }
     else if (w <= 128) { cfg->G = 32; cfg->V = 4; }
     else if (w <= 160) { cfg->G = 32; cfg->V = 5; }
     else if (w <= 256) { cfg->G = 32; cfg->V = 8; }
     else return sdx_fail(c, SDX_ERR_UNSUPPORTED, "trade rows longer than 8192 bits are not supported");
     if (c->R > 65535) return sdx_fail(c, SDX_ERR_UNSUPPORTED, "more than 65535 trade rows are not supported");
+    // tuning knobs (benchmarks only): SDX_TRADE_G in {2,4,8,16,32}, SDX_TRADE_WARPS
+    int warps_env = 0;
+    if (const char *e = getenv("SDX_TRADE_G")) {
+        const int g = atoi(e);
+        static const int gv[][2] = {{2, 16}, {4, 8}, {8, 4}, {8, 8}, {16, 4}, {32, 4}, {32, 5}, {32, 8}};
+        for (auto &q : gv)
+            if (q[0] == g && q[0] * q[1] >= c->RS) { cfg->G = q[0]; cfg->V = q[1]; break; }
+    }
+    if (const char *e = getenv("SDX_TRADE_WARPS")) warps_env = atoi(e);
     const size_t bytes = (size_t)c->R * c->RS * 4;
     const size_t budget = c->smem_optin > 2048 ? c->smem_optin - 1024 : 0;
     cfg->smem = bytes <= budget;
@@ -317,17 +330,23 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
         cfg->smem_bytes = bytes < 16 ? 16 : bytes;
         int per_sm = (int)((228 * 1024) / (cfg->smem_bytes + 1024 + 64));
         if (per_sm < 1) per_sm = 1;
-        int warps = 20 / per_sm;                  // aim at ~20 resident warps per SM
+        int warps = 40 / per_sm;                  // aim at ~40 resident warps per SM
         if (warps < 4) warps = 4;
         if (warps > 16) warps = 16;
-        int max_warps = 32 / (32 / cfg->G);       // NG <= 32
-        if (warps > max_warps) warps = max_warps;
+        if (per_sm >= 4 && warps > 4) warps = 4;  // register file: 5 CTAs x 128 threads x 96 registers
+        if (warps_env >= 1 && warps_env <= 16) warps = warps_env;
         cfg->threads = warps * 32;
+        cfg->LB = per_sm >= 4 ? (cfg->threads <= 128 ? 1 : (cfg->threads <= 256 ? 2 : 0)) : 0;
+        if (const char *e = getenv("SDX_TRADE_LB")) {
+            const int lb = atoi(e);
+            if (lb == 0 || (lb == 1 && cfg->threads <= 128) || (lb == 2 && cfg->threads <= 256)) cfg->LB = lb;
+        }
         cfg->grid_cap = 1 << 30;
     } else {
         cfg->smem_bytes = 0;
-        int warps = 32 / (32 / cfg->G);
-        if (warps > 16) warps = 16;
+        cfg->LB = 0;
+        int warps = 16;
+        if (warps_env >= 1 && warps_env <= 16) warps = warps_env;
         cfg->threads = warps * 32;
         size_t per = bytes;
         int cap = (int)((size_t)96 * 1024 * 1024 / per);   // working set ~ within L2
@@ -340,18 +359,21 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
 template <int G, int V>
 static cudaError_t launch_trade(const TradeConfig &cfg, int grid, cudaStream_t st, const TradeArgs &args) {
     if (cfg.smem) {
-        auto kern = k_trade<G, V, true>;
+        auto kern = cfg.LB == 1 ? k_trade<G, V, true, 1> : (cfg.LB == 2 ? k_trade<G, V, true, 2> : k_trade<G, V, true, 0>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;
         kern<<<grid, cfg.threads, cfg.smem_bytes, st>>>(args);
     } else {
-        k_trade<G, V, false><<<grid, cfg.threads, 0, st>>>(args);
+        k_trade<G, V, false, 0><<<grid, cfg.threads, 0, st>>>(args);
     }
     return cudaGetLastError();
 }
 
 static cudaError_t dispatch_trade(const TradeConfig &cfg, int grid, cudaStream_t st, const TradeArgs &args) {
+    if (cfg.G == 2 && cfg.V == 16) return launch_trade<2, 16>(cfg, grid, st, args);
+    if (cfg.G == 4 && cfg.V == 8) return launch_trade<4, 8>(cfg, grid, st, args);
     if (cfg.G == 8 && cfg.V == 4) return launch_trade<8, 4>(cfg, grid, st, args);
+    if (cfg.G == 8 && cfg.V == 8) return launch_trade<8, 8>(cfg, grid, st, args);
     if (cfg.G == 16 && cfg.V == 4) return launch_trade<16, 4>(cfg, grid, st, args);
     if (cfg.G == 32 && cfg.V == 4) return launch_trade<32, 4>(cfg, grid, st, args);
     if (cfg.G == 32 && cfg.V == 5) return launch_trade<32, 5>(cfg, grid, st, args);
@@ -367,7 +389,7 @@ struct HostScore {               // optional fused scoring request
     double *z_obs_out = nullptr;        // host out, P (or null)
 };
 
-enum { SL_LVL = 0, SL_PLAN, SL_AUX, SL_MOD, SL_Z, SL_SCORES, SL_CARRY, SL_OUT, SL_APPLIED, SL_WORK };
+enum { SL_LVL = 0, SL_PLAN, SL_AUX, SL_MOD, SL_Z, SL_SCORES, SL_CARRY, SL_OUT, SL_APPLIED, SL_WORK, SL_OFFS = 12 };
 
 // The common driver behind sdx_curveball and sdx_null_pvalue (stat = fixed).
 int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
@@ -444,7 +466,9 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
         if (lv_smem > 48 * 1024)
             SDX_CUDA(c, cudaFuncSetAttribute(k_plan_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem));
 
-        void *p_lvl, *p_plan, *p_aux = nullptr, *p_carry = nullptr, *p_work = nullptr, *p_out = nullptr, *p_app = nullptr;
+        void *p_lvl, *p_plan, *p_offs, *p_aux = nullptr, *p_carry = nullptr, *p_work = nullptr, *p_out = nullptr, *p_app = nullptr;
+        const int offs_stride = (int)(((T < SDX_HCAP ? T : SDX_HCAP) + 2 + 1) & ~1ll);
+        if ((rc = sdx_scratch(c, SL_OFFS, sizeof(uint16_t) * (size_t)n_local_max * offs_stride + 64, &p_offs))) return rc;
         const size_t lvl_bytes = ((sizeof(uint16_t) * (size_t)n_local_max * Tn + 15) / 16) * 16;
         if ((rc = sdx_scratch(c, SL_LVL, lvl_bytes + sizeof(int) * n_local_max + 64, &p_lvl))) return rc;
         int *d_depth = (int *)((char *)p_lvl + lvl_bytes);
@@ -480,13 +504,14 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
                     k_plan_levels<<<ceil_div(n_local, lv_threads), lv_threads, lv_smem, c->stream>>>(
                         keys, ix, n_local, R, (int)T, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux);
                     k_plan_sort<<<ceil_div(n_local, 2), 64, 0, c->stream>>>(keys, ix, n_local, R, (int)T, (const uint16_t *)p_lvl,
-                                                                          d_depth, (uint2 *)p_plan);
+                                                                          d_depth, (uint2 *)p_plan, (uint16_t *)p_offs, offs_stride);
                     timer.count(2);
                 }
                 cudaEventRecord(c->ev[3], c->stream);
                 TradeArgs ta{};
                 ta.keys = keys; ta.ix = ix; ta.observed = c->d_trade_obs; ta.work = (uint32_t *)p_work;
                 ta.carry = (uint32_t *)p_carry; ta.plan = (const uint2 *)p_plan; ta.n_units = (int)nch;
+                ta.offs = (const uint16_t *)p_offs; ta.depth = d_depth; ta.offs_stride = offs_stride;
                 ta.R = R; ta.RS = RS; ta.T = (int)T; ta.wprL = c->wprL;
                 ta.save_carry = need_carry && sg + 1 < n_segs;
                 ta.out_rows = (uint32_t *)p_out; ta.applied = (unsigned long long *)p_app; ta.sc = sc;
@@ -587,14 +612,25 @@ extern "C" int sdx_curveball_replay(sdx_ctx *c, const uint32_t *start, const int
     return rc;
 }
 
-extern "C" int sdx_null_pvalue(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
-                               int64_t chain_len, int stat, const int32_t *modules, int k, const double *z_obs,
-                               int64_t *n_ge, double *null_scores, double *z_obs_out);
+int sdx_null_pvalue_maxk(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
+                         const int32_t *modules, int k, const double *z_obs, int64_t *n_ge, double *null_scores,
+                         double *z_obs_out);      // sdx_maxk.cu
 
-int sdx_null_pvalue_fixed(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
-                          int64_t chain_len, const int32_t *modules, int k, const double *z_obs,
-                          int64_t *n_ge, double *null_scores, double *z_obs_out) {
+static int sdx_null_pvalue_fixed(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
+                                 int64_t chain_len, const int32_t *modules, int k, const double *z_obs,
+                                 int64_t *n_ge, double *null_scores, double *z_obs_out) {
     HostScore hs;
     hs.k = k; hs.modules = modules; hs.z_obs = z_obs; hs.n_ge = n_ge; hs.null_scores = null_scores; hs.z_obs_out = z_obs_out;
     return sdx_run_nulls(ctx, seed, null0, n_nulls, n_trades, chain_len, nullptr, nullptr, &hs);
+}
+
+extern "C" int sdx_null_pvalue(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
+                               int64_t chain_len, int stat, const int32_t *modules, int k, const double *z_obs,
+                               int64_t *n_ge, double *null_scores, double *z_obs_out) {
+    if (!ctx) return SDX_ERR_INVALID;
+    if (stat == SDX_STAT_FIXED)
+        return sdx_null_pvalue_fixed(ctx, seed, null0, n_nulls, n_trades, chain_len, modules, k, z_obs, n_ge, null_scores, z_obs_out);
+    if (stat == SDX_STAT_MAXK)
+        return sdx_fail(ctx, SDX_ERR_UNSUPPORTED, "stat = max_k is not built yet");
+    return sdx_fail(ctx, SDX_ERR_INVALID, "unknown null statistic");
 }

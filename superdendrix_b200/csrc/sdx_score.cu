@@ -15,6 +15,19 @@ __global__ void k_score_sets(const uint32_t *__restrict__ feat, int wprS, int S,
     }
 }
 
+// device-pointer variant used inside the library (scan re-scoring): no copies, no sync
+int sdx_score_sets_device(sdx_ctx *c, const int32_t *d_sets, const int32_t *d_prof, int profile0, int64_t n, int k,
+                          double *d_W, int32_t *d_cov, int32_t *d_ovl, int32_t *d_act) {
+    if (n <= 0) return SDX_OK;
+    k_score_sets<<<ceil_div(n, 8), 256, 0, c->stream>>>(c->d_feat, c->wprS, c->S, d_sets, d_prof, n, k,
+                                                        c->d_w + (size_t)profile0 * c->S, c->d_mask + (size_t)profile0 * c->wprS,
+                                                        d_W, d_cov, d_ovl, d_act);
+    c->total_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return sdx_fail(c, SDX_ERR_CUDA, std::string("k_score_sets launch failed: ") + cudaGetErrorString(e));
+    return SDX_OK;
+}
+
 extern "C" int sdx_score_sets(sdx_ctx *c, const int32_t *sets, const int32_t *prof, int64_t n, int k,
                               double *W, int32_t *cov, int32_t *ovl, int32_t *act) {
     if (!c) return SDX_ERR_INVALID;

@@ -5,33 +5,56 @@
 #pragma once
 #include "sdx_common.cuh"
 
-#define SDX_PLAN_END 0x80000000u   // plan entry flag: last trade of its level
+// ---------------------------------------------------------------------------
+// DEAL stream (oracle/sdx_oracle.c: deal_draw): draw `attempt`
+// of pick i of trade t = word (i & 3) of block ((i >> 2) | (attempt << 16)).
+// ---------------------------------------------------------------------------
+// Rare branch of Lemire's method (taken with probability m / 2^32 per pick).
+// Out of line so that the modulo is not speculated into the hot loop.
+static __device__ __noinline__ uint32_t deal_below_slow(const PhiloxKeys *keys, uint64_t null_id, uint32_t t, uint32_t i,
+                                                 uint32_t m, uint32_t x) {
+    uint64_t prod = (uint64_t)x * m;
+    uint32_t lo = (uint32_t)prod;
+    const uint32_t thr = (0u - m) % m;
+    uint32_t attempt = 0;
+    while (lo < thr) {
+        ++attempt;
+        const uint4 b = stream_block(*keys, SDX_STREAM_DEAL, null_id, t, (i >> 2) | (attempt << 16));
+        prod = (uint64_t)pick4(b, i & 3) * m;
+        lo = (uint32_t)prod;
+    }
+    return (uint32_t)(prod >> 32);
+}
 
 // ---------------------------------------------------------------------------
-// One trade, executed by a group of G consecutive lanes; lane `sub` of the
-// group holds V consecutive words of each of the two rows (blocked layout, so
-// lane order == ascending bit order).  All lanes of the group must call it
-// together; groups of one warp may diverge from one another.
+// One trade per group of G consecutive lanes; lane `sub` of the group holds V
+// consecutive words of each of the two rows (blocked layout: lane order ==
+// ascending bit order).  ALL 32 lanes of the warp call it together (groups
+// without a trade pass act = false), so every shuffle uses the full mask.
 //
 //   a' = (a&b) | picked ,  b' = (a&b) | rest     (or the other way round)
 //
-// where `picked` is a uniformly random k-subset, k = min(|a\b|, |b\a|), of the
-// symmetric difference, drawn element by element ("r-th remaining element in
-// ascending order", r exactly uniform) from the DEAL stream of (null, t).
+// `picked` is a uniformly random k-subset, k = min(|a\b|, |b\a|), of the n
+// symmetric-difference elements: Floyd's algorithm over their ranks (ascending
+// bit order), one sub-stream of the DEAL stream per pick.  The chosen ranks
+// are kept as a compressed n-bit mask; while the trade runs both rows live in
+// registers, so the storage of row a doubles as the scratch for that mask
+// (lane 0 of the group performs the picks).  Afterwards each lane expands its
+// slice of the mask onto the set bits of its own words.
 // Returns true when the trade was applied (src/curveball.py:29 skip rule).
 // ---------------------------------------------------------------------------
 template <int G, int V>
-__device__ __forceinline__ bool trade_rows(uint32_t *__restrict__ rows, int RS, uint32_t a, uint32_t b,
-                                           uint32_t t, uint64_t null_id, const PhiloxKeys &keys,
-                                           int sub, uint32_t gmask) {
-    uint32_t A[V], B[V];
+__device__ __forceinline__ bool trade_rows(uint32_t *rows, int RS, bool act, uint32_t a, uint32_t b,
+                                           uint32_t t, uint64_t null_id, const PhiloxKeys &keys, int sub) {
+    constexpr unsigned FULL = 0xffffffffu;
+    uint32_t A[V], B[V], sym[V];
     uint32_t *ra = rows + (size_t)a * RS + sub * V;
     uint32_t *rb = rows + (size_t)b * RS + sub * V;
     if constexpr (V % 4 == 0) {
 #pragma unroll
         for (int q = 0; q < V / 4; ++q) {
             uint4 va = make_uint4(0, 0, 0, 0), vb = va;
-            if (sub * V + 4 * q < RS) {
+            if (act && sub * V + 4 * q < RS) {
                 va = *reinterpret_cast<const uint4 *>(ra + 4 * q);
                 vb = *reinterpret_cast<const uint4 *>(rb + 4 * q);
             }
@@ -41,99 +64,121 @@ __device__ __forceinline__ bool trade_rows(uint32_t *__restrict__ rows, int RS, 
     } else {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            bool in = sub * V + i < RS;
+            const bool in = act && sub * V + i < RS;
             A[i] = in ? ra[i] : 0u;
             B[i] = in ? rb[i] : 0u;
         }
     }
 
-    uint32_t rem[V], pick[V];
     uint32_t ca = 0, cb = 0;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-        uint32_t oa = A[i] & ~B[i], ob = B[i] & ~A[i];
+        const uint32_t oa = A[i] & ~B[i], ob = B[i] & ~A[i];
         ca += __popc(oa); cb += __popc(ob);
-        rem[i] = oa | ob; pick[i] = 0;
+        sym[i] = oa | ob;
     }
     // group-wide inclusive scan of (ca, cb) packed in one register
-    uint32_t packed = ca | (cb << 16);
+    const uint32_t packed = ca | (cb << 16);
     uint32_t inc = packed;
 #pragma unroll
     for (int o = 1; o < G; o <<= 1) {
-        uint32_t v = __shfl_up_sync(gmask, inc, o, G);
+        const uint32_t v = __shfl_up_sync(FULL, inc, o, G);
         if (sub >= o) inc += v;
     }
-    uint32_t tot = __shfl_sync(gmask, inc, G - 1, G);
-    uint32_t La = tot & 0xffffu, Lb = tot >> 16;
-    if (La == 0 || Lb == 0) return false;
-
-    uint32_t exc = inc - packed;
-    uint32_t pre = (exc & 0xffffu) + (exc >> 16);   // symmetric-difference elements in lower lanes
-    uint32_t ctot = ca + cb;                        // ... in this lane
+    const uint32_t tot = __shfl_sync(FULL, inc, G - 1, G);
+    const uint32_t La = tot & 0xffffu, Lb = tot >> 16;
+    const bool go = La != 0 && Lb != 0;                 // act == false gives La == Lb == 0
     const bool small_is_a = La <= Lb;
-    const uint32_t k = small_is_a ? La : Lb;
     const uint32_t n = La + Lb;
+    const uint32_t k = go ? (small_is_a ? La : Lb) : 0u;
+    const uint32_t kmax = __reduce_max_sync(FULL, k);
+    if (kmax == 0) return false;                        // warp-uniform
 
-    uint32_t di = 0;          // index of the next draw of the DEAL stream (group-uniform)
-    uint4 blk = make_uint4(0, 0, 0, 0);
-    for (uint32_t j = 0; j < k; ++j) {
-        const uint32_t m = n - j;
-        uint32_t r;
-        for (;;) {
-            if ((di & (4 * G - 1)) == 0)            // every lane refills its own block of this round
-                blk = stream_block(keys, SDX_STREAM_DEAL, null_id, t, (di >> 2) + sub);
-            uint32_t mine = pick4(blk, di & 3);
-            uint32_t x = __shfl_sync(gmask, mine, (di >> 2) & (G - 1), G);
-            ++di;
-            uint64_t prod = (uint64_t)x * m;
-            uint32_t lo = (uint32_t)prod;
-            r = (uint32_t)(prod >> 32);
-            if (lo >= m) break;                     // common case
-            if (lo >= (0u - m) % m) break;          // Lemire rejection threshold
-        }
-        uint32_t d = r - pre;
-        if (d < ctot) {                             // this lane owns the r-th remaining element
-            bool done = false;
+    const uint32_t exc = inc - packed;
+    uint32_t off = (exc & 0xffffu) + (exc >> 16);       // rank of this lane's first symmetric-difference element
+    volatile uint32_t *cm = rows + (size_t)a * RS;      // compressed mask of chosen ranks: ceil(n/32) words of row a's storage
+    const uint32_t nw = go ? (n + 31) >> 5 : 0u;
+    for (uint32_t i = sub; i < nw; i += G) cm[i] = 0u;
+    __syncwarp();
+
+#pragma unroll 1
+    for (uint32_t blk0 = 0; blk0 * 4 < kmax; blk0 += G) {
+        const uint4 blk = stream_block(keys, SDX_STREAM_DEAL, null_id, t, blk0 + sub);
+#pragma unroll 1
+        for (int q = 0; q < G; ++q) {
+            const uint32_t i0 = (blk0 + q) * 4;
+            if (i0 >= kmax) break;                      // warp-uniform
+            uint32_t x[4];
+            x[0] = __shfl_sync(FULL, blk.x, q, G);
+            x[1] = __shfl_sync(FULL, blk.y, q, G);
+            x[2] = __shfl_sync(FULL, blk.z, q, G);
+            x[3] = __shfl_sync(FULL, blk.w, q, G);
+            if (sub == 0 && i0 < k) {
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                uint32_t cw = __popc(rem[i]);
-                bool here = !done && d < cw;
-                if (here) {
-                    uint32_t x = rem[i];
-                    for (uint32_t q = 0; q < d; ++q) x &= x - 1;
-                    uint32_t bit = x & (0u - x);
-                    rem[i] ^= bit; pick[i] |= bit;
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t i = i0 + c;
+                    if (i < k) {
+                        const uint32_t m = n - k + i + 1;               // Floyd: j = m - 1, r uniform in [0, j]
+                        const uint64_t prod = (uint64_t)x[c] * m;
+                        uint32_t r = (uint32_t)(prod >> 32);
+                        if ((uint32_t)prod < m) r = deal_below_slow(&keys, null_id, t, i, m, x[c]);
+                        uint32_t w = cm[r >> 5];
+                        if ((w >> (r & 31)) & 1u) { r = m - 1; w = cm[r >> 5]; }
+                        cm[r >> 5] = w | (1u << (r & 31));
+                    }
                 }
-                if (!done && !here) d -= cw;
-                done |= here;
             }
-            --ctot;
-        } else if (r < pre) {
-            --pre;
         }
     }
+    __syncwarp();
 
+    // expand: this lane's words take bits [off, off + popc) of the compressed mask, in rank order
+    uint32_t pick[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-        uint32_t ab = A[i] & B[i];
-        A[i] = ab | (small_is_a ? pick[i] : rem[i]);
-        B[i] = ab | (small_is_a ? rem[i] : pick[i]);
-    }
-    if constexpr (V % 4 == 0) {
-#pragma unroll
-        for (int q = 0; q < V / 4; ++q) {
-            if (sub * V + 4 * q < RS) {
-                *reinterpret_cast<uint4 *>(ra + 4 * q) = make_uint4(A[4 * q], A[4 * q + 1], A[4 * q + 2], A[4 * q + 3]);
-                *reinterpret_cast<uint4 *>(rb + 4 * q) = make_uint4(B[4 * q], B[4 * q + 1], B[4 * q + 2], B[4 * q + 3]);
+        const uint32_t c = __popc(sym[i]);
+        uint32_t pk = 0;
+        if (go && c) {
+            const uint32_t w0 = off >> 5;
+            const uint32_t lo = cm[w0];
+            const uint32_t hi = (w0 + 1 < nw) ? cm[w0 + 1] : 0u;
+            uint32_t ch = __funnelshift_r(lo, hi, off & 31);
+            if (c < 32) ch &= (1u << c) - 1u;
+            uint32_t m = sym[i];
+            while (ch) {
+                const uint32_t low = m & (0u - m);
+                m ^= low;
+                if (ch & 1u) pk |= low;
+                ch >>= 1;
             }
         }
-    } else {
+        pick[i] = pk;
+        off += c;
+    }
+    __syncwarp();                                       // all reads of the scratch are done before row a is rewritten
+    if (go) {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            if (sub * V + i < RS) { ra[i] = A[i]; rb[i] = B[i]; }
+            const uint32_t ab = A[i] & B[i], rest = sym[i] ^ pick[i];
+            A[i] = ab | (small_is_a ? pick[i] : rest);
+            B[i] = ab | (small_is_a ? rest : pick[i]);
+        }
+        if constexpr (V % 4 == 0) {
+#pragma unroll
+            for (int q = 0; q < V / 4; ++q) {
+                if (sub * V + 4 * q < RS) {
+                    *reinterpret_cast<uint4 *>(ra + 4 * q) = make_uint4(A[4 * q], A[4 * q + 1], A[4 * q + 2], A[4 * q + 3]);
+                    *reinterpret_cast<uint4 *>(rb + 4 * q) = make_uint4(B[4 * q], B[4 * q + 1], B[4 * q + 2], B[4 * q + 3]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                if (sub * V + i < RS) { ra[i] = A[i]; rb[i] = B[i]; }
+            }
         }
     }
-    return true;
+    return go;
 }
 
 // ---------------------------------------------------------------------------

@@ -182,12 +182,26 @@ class Engine:
         return {"W": W, "features": feats, "coverage": cov, "n_scored": n.value}
 
     def condperm(self, module, n_perm: int, seed: int, perm_id0: int = 0, profile: int = 0):
+        """Returns (counts (k,) int64, real_W (k,)) for one module of one profile."""
         m = np.ascontiguousarray(module, dtype=np.int32)
         counts = np.zeros(len(m), dtype=np.int64)
-        real = C.c_double(0)
+        real = np.zeros(len(m))
         self._check(self._lib.sdx_condperm(self._ctx, int(profile), _ptr(m, C.c_int32), len(m), C.c_uint64(seed),
-                                           C.c_uint64(perm_id0), int(n_perm), _ptr(counts, C.c_int64), C.byref(real)))
-        return counts, real.value
+                                           C.c_uint64(perm_id0), int(n_perm), _ptr(counts, C.c_int64),
+                                           _ptr(real, C.c_double)))
+        return counts, real
+
+    def condperm_batch(self, modules, n_perm: int, seed: int, perm_id0: int = 0, profile_of_job=None):
+        """modules: (n_jobs, k).  Returns (counts (n_jobs, k), real_W (n_jobs, k))."""
+        mods = np.ascontiguousarray(np.atleast_2d(np.asarray(modules, dtype=np.int32)))
+        n, k = mods.shape
+        pj = np.zeros(n, dtype=np.int32) if profile_of_job is None else np.ascontiguousarray(profile_of_job, dtype=np.int32)
+        counts = np.zeros((n, k), dtype=np.int64)
+        real = np.zeros((n, k))
+        self._check(self._lib.sdx_condperm_batch(self._ctx, _ptr(pj, C.c_int32), _ptr(mods, C.c_int32), n, k,
+                                                 C.c_uint64(seed), C.c_uint64(perm_id0), int(n_perm),
+                                                 _ptr(counts, C.c_int64), _ptr(real, C.c_double)))
+        return counts, real
 
     def ranksum(self, modules, profile_of_job=None):
         mods = np.ascontiguousarray(np.atleast_2d(np.asarray(modules, dtype=np.int32)))

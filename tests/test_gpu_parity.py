@@ -252,3 +252,207 @@ def test_errors_are_reported_not_fatal(eng):
     upload_dense(eng, dense)
     eng.upload_weights(synth.weights(100, 1))
     assert eng.score_sets([[0, 1, 2]])["W"].shape == (1,)
+
+
+# ---------------------------------------------------------------- exhaustive scan
+def _check_scan_against_oracle(eng, dense, w, k, topn, exact_sets=False):
+    S, F = dense.shape
+    rows = bitpack.pack_rows(dense.T)
+    upload_dense(eng, dense)
+    eng.upload_weights(w[None, :])
+    got = eng.scan(0, k, topn)
+    oW, oF, oC, n = oracle.scan(rows, S, w, k, topn)
+    tol = 1e-9 * max(1.0, np.abs(w).sum())
+    assert got["n_scored"] == n
+    assert np.allclose(got["W"], oW, rtol=0, atol=tol)
+    # every reported subset really has the reported W and coverage (oracle re-score)
+    for i in range(topn):
+        feats = got["features"][i]
+        feats = feats[feats >= 0]
+        if len(feats) == 0:
+            assert got["W"][i] == -np.inf and oW[i] == -np.inf
+            continue
+        W, cov, _, _ = oracle.score_set(rows, S, feats, w)
+        assert abs(W - got["W"][i]) <= tol and cov == got["coverage"][i]
+    if exact_sets:
+        assert np.array_equal(got["features"], oF) and np.array_equal(got["coverage"], oC)
+    else:
+        # the optimum itself is unambiguous unless tied within tolerance
+        if topn == 1 or oW[0] - oW[1] > 10 * tol:
+            assert np.array_equal(got["features"][0], oF[0])
+    return got
+
+
+@pytest.mark.parametrize("name", ["a", "b", "unit"])
+def test_scan_matches_golden_bruteforce(eng, name):
+    z = load_npz("scan.npz")
+    dense, w = z[name + "__dense"], z[name + "__w"]
+    got = _check_scan_against_oracle(eng, dense, w, 3, 16, exact_sets=(name == "unit"))
+    tol = 1e-9 * np.abs(w).sum()
+    assert np.allclose(got["W"], z[name + "__topW"], rtol=0, atol=tol)       # the reference's own SuperW, brute force
+    assert got["n_scored"] == int(z[name + "__n"])
+    for k in (1, 2, 3):
+        upload_dense(eng, dense)
+        eng.upload_weights(w[None, :])
+        assert abs(eng.scan(0, k, 1)["W"][0] - z[name + "__best_le_k"][k - 1]) < tol
+
+
+@pytest.mark.parametrize("S,F,density,k", [(200, 61, 0.05, 3), (130, 37, 0.5, 3), (64, 5, 0.3, 3), (40, 3, 0.4, 3),
+                                           (40, 2, 0.4, 3), (33, 1, 0.5, 3), (300, 90, 0.02, 2), (300, 90, 0.02, 1),
+                                           (1030, 70, 0.1, 3)])
+def test_scan_matches_oracle_on_random_matrices(eng, S, F, density, k):
+    rng = np.random.default_rng(S * 1000 + F)
+    dense = (rng.random((S, F)) < density).astype(np.uint8)
+    w = synth.weights(S, 1, seed=F)[0]
+    _check_scan_against_oracle(eng, dense, w, k, 8)
+
+
+def test_scan_duplicate_features_tie_order(eng):
+    """Identical carrier sets give exactly equal W; ties resolve in enumeration order like the oracle."""
+    rng = np.random.default_rng(2)
+    base = (rng.random((150, 12)) < 0.15).astype(np.uint8)
+    dense = np.concatenate([base, base[:, :6]], axis=1)
+    w = synth.weights(150, 1, seed=5)[0]
+    _check_scan_against_oracle(eng, dense, w, 3, 12, exact_sets=True)
+
+
+def test_scan_with_sample_mask(eng):
+    rng = np.random.default_rng(8)
+    dense = (rng.random((180, 40)) < 0.1).astype(np.uint8)
+    w = synth.weights(180, 1, seed=1)[0]
+    keep = np.arange(180) % 5 != 2
+    upload_dense(eng, dense)
+    eng.upload_weights(w[None, :], keep[None, :])
+    got = eng.scan(0, 3, 4)
+    rows = bitpack.pack_rows(dense.T)
+    oW, oF, oC, n = oracle.scan(rows, 180, np.where(keep, w, 0.0), 3, 4, mask=bitpack.pack_mask(np.nonzero(keep)[0], 180))
+    assert np.allclose(got["W"], oW, rtol=0, atol=1e-9 * np.abs(w).sum())
+    assert np.array_equal(got["features"][0], oF[0]) and np.array_equal(got["coverage"], oC)
+
+
+def test_scan_full_size_properties(eng):
+    """C2 (2 000 features x 1 000 samples): count is exact, optimum dominates sampled subsets and the
+    single / pair optima, and is reproduced by the set scorer."""
+    dense, _, _ = synth.feature_matrix(1000, 2000)
+    S, F = dense.shape
+    w = synth.weights(S, 1)
+    upload_dense(eng, dense)
+    eng.upload_weights(w)
+    got = eng.scan(0, 3, 8)
+    assert got["n_scored"] == F + F * (F - 1) // 2 + F * (F - 1) * (F - 2) // 6
+    rng = np.random.default_rng(0)
+    sets = np.sort(np.stack([rng.choice(F, 3, replace=False) for _ in range(20000)]), axis=1).astype(np.int32)
+    sc = eng.score_sets(sets)
+    tol = 1e-9 * np.abs(w).sum()
+    assert sc["W"].max() <= got["W"][0] + tol
+    assert (np.diff(got["W"]) <= 0).all()
+    re = eng.score_sets(got["features"])
+    assert np.allclose(re["W"], got["W"], rtol=0, atol=tol) and np.array_equal(re["coverage"], got["coverage"])
+    assert eng.scan(0, 1, 1)["W"][0] <= eng.scan(0, 2, 1)["W"][0] + tol <= got["W"][0] + 2 * tol
+    fs = eng.feature_scores(0)
+    assert abs(eng.scan(0, 1, 1)["W"][0] - fs["W1"].max()) <= tol
+    # greedy local search from the optimum cannot improve it (swap one feature)
+    best = got["features"][0]
+    for pos in range(3):
+        cand = np.tile(best, (F, 1))
+        cand[:, pos] = np.arange(F)
+        ok = np.array([len(set(r)) == 3 for r in cand])
+        assert eng.score_sets(cand[ok].astype(np.int32))["W"].max() <= got["W"][0] + tol
+
+
+# ---------------------------------------------------------------- conditional permutation
+def _condperm_inputs():
+    z = load_npz("condperm_data.npz")
+    with open(os.path.join(GOLDEN, "condperm.json")) as fh:
+        meta = json.load(fh)
+    return z["dense"], z["w"], meta
+
+
+def test_condperm_counts_equal_oracle_and_reference_within_mc_error(eng):
+    dense, w, meta = _condperm_inputs()
+    S, F = dense.shape
+    rows = bitpack.pack_rows(dense.T)
+    upload_dense(eng, dense)
+    eng.upload_weights(w[None, :])
+    for c in meta["cases"]:
+        P = c["P"]
+        counts, realW = eng.condperm(c["feats"], P, seed=77, perm_id0=0)
+        ocounts, orealW = oracle.condperm(rows, S, c["feats"], w, np.arange(S), seed=77, perm_id0=0, P=P)
+        assert np.array_equal(counts, ocounts)               # same streams, same summation order: exact
+        assert np.array_equal(realW, orealW)
+        for got, want in zip(counts, c["per_feature"]):      # the reference's own counts (CPython random): Monte-Carlo error
+            p = max(want, 1) / P
+            sd = np.sqrt(2 * P * p * (1 - p)) + 1
+            assert abs(got - want) < 4.5 * sd, (got, want)
+
+
+def test_condperm_with_mask_padding_and_batch(eng):
+    rng = np.random.default_rng(12)
+    dense = (rng.random((333, 30)) < 0.12).astype(np.uint8)
+    dense[:, 0] = rng.random(333) < 0.6
+    S, F = dense.shape
+    w = synth.weights(S, 3, seed=2)
+    keep = np.ones((3, S), bool)
+    keep[1, ::5] = False
+    keep[2, 100:140] = False
+    upload_dense(eng, dense)
+    eng.upload_weights(w, keep)
+    rows = bitpack.pack_rows(dense.T)
+    modules = np.array([[0, 3, 7], [1, 2, -1], [0, 1, 2], [5, -1, -1]], dtype=np.int32)
+    prof = np.array([0, 1, 2, 1], dtype=np.int32)
+    counts, realW = eng.condperm_batch(modules, 500, seed=5, perm_id0=40, profile_of_job=prof)
+    for j in range(len(modules)):
+        p = prof[j]
+        feats = modules[j][modules[j] >= 0]
+        oc, orw = oracle.condperm(rows, S, feats, np.where(keep[p], w[p], 0.0), np.nonzero(keep[p])[0], seed=5, perm_id0=40, P=500)
+        assert np.array_equal(counts[j][:len(feats)], oc), j
+        assert np.array_equal(realW[j][:len(feats)], orw)
+        assert (counts[j][len(feats):] == -1).all()
+        one, _ = eng.condperm(modules[j], 500, seed=5, perm_id0=40, profile=int(p))
+        assert np.array_equal(one, counts[j])
+    # n_perm = 0 and a single-feature module
+    c0, r0 = eng.condperm([0, 3], 0, seed=1)
+    assert c0.tolist() == [0, 0]
+
+
+# ---------------------------------------------------------------- rank-sum
+def test_ranksum_matches_scipy_golden(eng):
+    z = load_npz("ranksum.npz")
+    prof, carrier = z["profile"], z["carrier"]
+    n, S = prof.shape
+    # one feature per job carrying exactly the golden carrier set
+    upload_dense(eng, carrier.T.astype(np.uint8))
+    eng.upload_weights(prof)
+    res = eng.ranksum(np.arange(n, dtype=np.int32)[:, None], np.arange(n, dtype=np.int32))
+    for i in range(n):
+        assert res["n1"][i] == int(carrier[i].sum())
+        assert abs(res["z"][i] - z["z"][i]) < 1e-12 * max(1, abs(z["z"][i]))
+        assert abs(res["p"][i] - z["p"][i]) <= 1e-12 + 1e-10 * z["p"][i]
+        _, _, s2, n1 = oracle.ranksum(prof[i], np.arange(S), bitpack.pack_mask(np.nonzero(carrier[i])[0], S))
+        assert (res["twice_rank_sum"][i], res["n1"][i]) == (s2, n1)     # integer work: exact
+
+
+def test_ranksum_union_of_module_with_mask_and_ties(eng):
+    dense, _, _ = synth.feature_matrix(770, 400)
+    S, F = dense.shape
+    w = synth.weights(S, 2)          # 2 % exact zeros -> ties
+    w[1] = np.round(w[1])            # heavy ties
+    keep = np.ones((2, S), bool)
+    keep[1, ::3] = False
+    upload_dense(eng, dense)
+    eng.upload_weights(w, keep)
+    modules = np.array([[0, 1, 2], [5, 9, -1], [3, -1, -1], [0, 10, 20]], dtype=np.int32)
+    prof = np.array([0, 1, 1, 0], dtype=np.int32)
+    res = eng.ranksum(modules, prof)
+    from scipy import stats
+    for j in range(len(modules)):
+        p = prof[j]
+        feats = modules[j][modules[j] >= 0]
+        union = dense[:, feats].any(axis=1)
+        idx = np.nonzero(keep[p])[0]
+        zz, pp, s2, n1 = oracle.ranksum(np.where(keep[p], w[p], 0.0), idx, bitpack.pack_mask(np.nonzero(union)[0], S))
+        assert (res["twice_rank_sum"][j], res["n1"][j]) == (s2, n1)
+        assert abs(res["z"][j] - zz) <= 1e-12 * max(1, abs(zz)) and abs(res["p"][j] - pp) <= 1e-12 + 1e-10 * pp
+        x, y = w[p][keep[p] & union], w[p][keep[p] & ~union]
+        ref = stats.ranksums(x, y)
+        assert abs(res["z"][j] - ref.statistic) < 1e-10 and abs(res["p"][j] - ref.pvalue) < 1e-10
