@@ -59,7 +59,9 @@ static void free_matrix(sdx_ctx *c) {
     if (c->d_feat) cudaFree(c->d_feat);
     if (c->d_samp) cudaFree(c->d_samp);
     if (c->d_trade_obs) cudaFree(c->d_trade_obs);
+    if (c->d_rowsize) cudaFree(c->d_rowsize);
     c->d_feat = c->d_samp = c->d_trade_obs = nullptr;
+    c->d_rowsize = nullptr;
 }
 
 static void free_weights(sdx_ctx *c) {
@@ -123,6 +125,17 @@ __global__ void k_transpose_bits(const uint32_t *__restrict__ in, int n_rows, in
     }
 }
 
+// popcount of every trade row: one warp per row
+__global__ void k_row_sizes(const uint32_t *__restrict__ rows, int R, int RS, int *__restrict__ size) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R) return;
+    int c = 0;
+    for (int i = lane; i < RS; i += 32) c += __popc(rows[(size_t)r * RS + i]);
+    c = warp_sum_i32(c);
+    if (lane == 0) size[r] = c;
+}
+
 extern "C" int sdx_upload_matrix(sdx_ctx *c, const uint32_t *rows, int F, int S, int wpr) {
     if (!c) return SDX_ERR_INVALID;
     SDX_REQUIRE(c, rows && F >= 1 && S >= 1, SDX_ERR_INVALID, "matrix pointer / shape invalid");
@@ -152,6 +165,9 @@ extern "C" int sdx_upload_matrix(sdx_ctx *c, const uint32_t *rows, int F, int S,
     SDX_CUDA(c, cudaMemsetAsync(c->d_trade_obs, 0, sizeof(uint32_t) * (size_t)c->R * c->RS, c->stream));
     SDX_CUDA(c, cudaMemcpy2DAsync(c->d_trade_obs, (size_t)c->RS * 4, c->rows_are_samples ? c->d_samp : c->d_feat,
                                   (size_t)c->wprL * 4, (size_t)c->wprL * 4, c->R, cudaMemcpyDeviceToDevice, c->stream));
+    SDX_CUDA(c, cudaMalloc(&c->d_rowsize, sizeof(int) * (size_t)c->R));
+    k_row_sizes<<<ceil_div(c->R, 8), 256, 0, c->stream>>>(c->d_trade_obs, c->R, c->RS, c->d_rowsize);
+    c->total_launches++;
     SDX_CUDA(c, cudaStreamSynchronize(c->stream));
     SDX_CUDA(c, cudaGetLastError());
     return SDX_OK;

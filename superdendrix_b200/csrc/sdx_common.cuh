@@ -42,6 +42,7 @@ struct sdx_ctx {
     int R = 0, L = 0, wprL = 0, RS = 0;   // RS: padded row stride (words, multiple of 4)
     int rows_are_samples = 0;
     uint32_t *d_trade_obs = nullptr;      // R x RS, observed matrix in trade orientation
+    int *d_rowsize = nullptr;             // R: popcount of each trade row (invariant under Curveball)
 
     // weights
     int P = 0;

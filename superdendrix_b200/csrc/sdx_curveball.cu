@@ -69,11 +69,23 @@ __global__ void k_plan_levels(const __grid_constant__ PhiloxKeys keys, NullIndex
 // ---------------------------------------------------------------------------
 // plan: counting sort by level (one warp per null)
 // ---------------------------------------------------------------------------
-#define SDX_HCAP 2048
+#define SDX_HCAP 1024          // deepest level schedule the plan kernels sort; deeper nulls run in sequential order
+#define SDX_NCLS 4             // trade size classes inside a level (largest first)
+
+// Row sizes never change (Curveball preserves them), so min(|a|, |b|) bounds the number of picks of a
+// trade and |a| + |b| bounds its symmetric difference.  Inside a level the plan lists the large
+// trades first and groups similar sizes, so the groups of one warp run loops of similar length and
+// the register fast path of trade_rows (n <= 64) is taken by whole warps.
+__device__ __forceinline__ int trade_class(int sa, int sb) {
+    const int kb = sa < sb ? sa : sb;
+    if (sa + sb > 64) return 0;
+    return kb > 8 ? 1 : (kb > 3 ? 2 : 3);
+}
+
 __global__ void k_plan_sort(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T,
-                            const uint16_t *__restrict__ lvl, const int *__restrict__ depth,
+                            const uint16_t *__restrict__ lvl, const int *__restrict__ depth, const int *__restrict__ rowsize,
                             uint2 *__restrict__ plan, uint16_t *__restrict__ offs, int offs_stride) {
-    __shared__ uint32_t hist_smem[2][SDX_HCAP + 2];
+    __shared__ uint32_t hist_smem[2][SDX_HCAP * SDX_NCLS + 2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n = blockIdx.x * (blockDim.x >> 5) + wid;
     if (n >= n_local) return;
@@ -90,32 +102,38 @@ __global__ void k_plan_sort(const __grid_constant__ PhiloxKeys keys, NullIndexin
         }
         return;                 // k_trade runs such a null one trade per level, in order
     }
-    for (int l = lane; l <= D + 1; l += 32) hist[l] = 0;
+    const int NB = D * SDX_NCLS;                       // bin = (level - 1) * NCLS + class
+    for (int i = lane; i <= NB; i += 32) hist[i] = 0;
     __syncwarp();
-    for (int t = lane; t < T; t += 32) atomicAdd(&hist[lv[t]], 1u);
+    for (int t = lane; t < T; t += 32) {
+        uint32_t a, b;
+        trade_pair(keys, null_id, (uint32_t)t, (uint32_t)R, a, b);
+        atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[a], rowsize[b])], 1u);
+    }
     __syncwarp();
-    // exclusive scan of hist[1..D] -> start offsets
+    // exclusive scan of the bins -> start offsets
     uint32_t carry = 0;
-    for (int base = 1; base <= D; base += 32) {
-        int l = base + lane;
-        uint32_t c = (l <= D) ? hist[l] : 0u, inc = c;
+    for (int base = 0; base < NB; base += 32) {
+        const int i = base + lane;
+        const uint32_t c = (i < NB) ? hist[i] : 0u;
+        uint32_t inc = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += v;
         }
-        if (l <= D) hist[l] = carry + inc - c;
+        if (i < NB) hist[i] = carry + inc - c;
         carry += __shfl_sync(0xffffffffu, inc, 31);
     }
     __syncwarp();
     uint16_t *of = offs + (size_t)n * offs_stride;          // of[l] = first entry of level l+1, of[D] = T
-    for (int l = lane; l < D; l += 32) of[l] = (uint16_t)hist[l + 1];
+    for (int l = lane; l < D; l += 32) of[l] = (uint16_t)hist[l * SDX_NCLS];
     if (lane == 0) of[D] = (uint16_t)T;
     __syncwarp();
     for (int t = lane; t < T; t += 32) {
         uint32_t a, b;
         trade_pair(keys, null_id, (uint32_t)t, (uint32_t)R, a, b);
-        uint32_t pos = atomicAdd(&hist[lv[t]], 1u);
+        uint32_t pos = atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[a], rowsize[b])], 1u);
         out[pos] = make_uint2(a | (b << 16), (uint32_t)t);
     }
 }
@@ -160,10 +178,10 @@ static __device__ __noinline__ SetScore score_module_call(const uint32_t *rows, 
     return score_module(rows, RS, rows_are_samples, mod, k, w, mask, S, lane);
 }
 
-// LB selects the launch bounds: 0 = (512, 1), 1 = (128, 5), 2 = (256, 5) — the latter two bound the
+// LB selects the launch bounds: 0 = (512, 1), 1 = (128, 5), 2 = (256, 5), 3 = (256, 4) — the latter three bound the
 // registers so that five CTAs (five nulls) stay resident per SM when the matrix fits five times in shared memory.
 template <int G, int V, bool SMEM, int LB>
-__global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : 256), LB == 0 ? 1 : 5) k_trade(const __grid_constant__ TradeArgs p) {
+__global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : 256), LB == 0 ? 1 : (LB == 3 ? 4 : 5)) k_trade(const __grid_constant__ TradeArgs p) {
     extern __shared__ __align__(16) uint32_t smem_rows[];
     __shared__ unsigned int s_applied;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NW = blockDim.x >> 5;
@@ -339,7 +357,7 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
         cfg->LB = per_sm >= 4 ? (cfg->threads <= 128 ? 1 : (cfg->threads <= 256 ? 2 : 0)) : 0;
         if (const char *e = getenv("SDX_TRADE_LB")) {
             const int lb = atoi(e);
-            if (lb == 0 || (lb == 1 && cfg->threads <= 128) || (lb == 2 && cfg->threads <= 256)) cfg->LB = lb;
+            if (lb == 0 || (lb == 1 && cfg->threads <= 128) || ((lb == 2 || lb == 3) && cfg->threads <= 256)) cfg->LB = lb;
         }
         cfg->grid_cap = 1 << 30;
     } else {
@@ -359,7 +377,7 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
 template <int G, int V>
 static cudaError_t launch_trade(const TradeConfig &cfg, int grid, cudaStream_t st, const TradeArgs &args) {
     if (cfg.smem) {
-        auto kern = cfg.LB == 1 ? k_trade<G, V, true, 1> : (cfg.LB == 2 ? k_trade<G, V, true, 2> : k_trade<G, V, true, 0>);
+        auto kern = cfg.LB == 1 ? k_trade<G, V, true, 1> : (cfg.LB == 2 ? k_trade<G, V, true, 2> : (cfg.LB == 3 ? k_trade<G, V, true, 3> : k_trade<G, V, true, 0>));
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;
         kern<<<grid, cfg.threads, cfg.smem_bytes, st>>>(args);
@@ -504,7 +522,7 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
                     k_plan_levels<<<ceil_div(n_local, lv_threads), lv_threads, lv_smem, c->stream>>>(
                         keys, ix, n_local, R, (int)T, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux);
                     k_plan_sort<<<ceil_div(n_local, 2), 64, 0, c->stream>>>(keys, ix, n_local, R, (int)T, (const uint16_t *)p_lvl,
-                                                                          d_depth, (uint2 *)p_plan, (uint16_t *)p_offs, offs_stride);
+                                                                          d_depth, c->d_rowsize, (uint2 *)p_plan, (uint16_t *)p_offs, offs_stride);
                     timer.count(2);
                 }
                 cudaEventRecord(c->ev[3], c->stream);

@@ -70,15 +70,15 @@ __device__ __forceinline__ bool trade_rows(uint32_t *rows, int RS, bool act, uin
         }
     }
 
-    uint32_t ca = 0, cb = 0;
+    uint32_t ca = 0, cs = 0;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-        const uint32_t oa = A[i] & ~B[i], ob = B[i] & ~A[i];
-        ca += __popc(oa); cb += __popc(ob);
-        sym[i] = oa | ob;
+        sym[i] = A[i] ^ B[i];
+        ca += __popc(A[i] & ~B[i]);
+        cs += __popc(sym[i]);
     }
-    // group-wide inclusive scan of (ca, cb) packed in one register
-    const uint32_t packed = ca | (cb << 16);
+    // group-wide inclusive scan of (|a\b|, |a^b|) packed in one register
+    const uint32_t packed = ca | (cs << 16);
     uint32_t inc = packed;
 #pragma unroll
     for (int o = 1; o < G; o <<= 1) {
@@ -86,74 +86,129 @@ __device__ __forceinline__ bool trade_rows(uint32_t *rows, int RS, bool act, uin
         if (sub >= o) inc += v;
     }
     const uint32_t tot = __shfl_sync(FULL, inc, G - 1, G);
-    const uint32_t La = tot & 0xffffu, Lb = tot >> 16;
+    const uint32_t La = tot & 0xffffu, n = tot >> 16, Lb = n - La;
     const bool go = La != 0 && Lb != 0;                 // act == false gives La == Lb == 0
     const bool small_is_a = La <= Lb;
-    const uint32_t n = La + Lb;
     const uint32_t k = go ? (small_is_a ? La : Lb) : 0u;
+    // one reduction for both maxima: k <= n / 2 and n < 2^15, and the group with the largest n that trades has k > 0
     const uint32_t kmax = __reduce_max_sync(FULL, k);
     if (kmax == 0) return false;                        // warp-uniform
+    const uint32_t nmax = __reduce_max_sync(FULL, go ? n : 0u);
+    uint32_t off = (inc - packed) >> 16;                // rank of this lane's first symmetric-difference element
+    uint32_t pick[V];
 
-    const uint32_t exc = inc - packed;
-    uint32_t off = (exc & 0xffffu) + (exc >> 16);       // rank of this lane's first symmetric-difference element
-    volatile uint32_t *cm = rows + (size_t)a * RS;      // compressed mask of chosen ranks: ceil(n/32) words of row a's storage
-    const uint32_t nw = go ? (n + 31) >> 5 : 0u;
-    for (uint32_t i = sub; i < nw; i += G) cm[i] = 0u;
-    __syncwarp();
-
+    if (nmax <= 64) {
+        // ---- fast path: the compressed mask of chosen ranks fits a register pair of lane 0 ----------
+        uint32_t c0 = 0, c1 = 0;
 #pragma unroll 1
-    for (uint32_t blk0 = 0; blk0 * 4 < kmax; blk0 += G) {
-        const uint4 blk = stream_block(keys, SDX_STREAM_DEAL, null_id, t, blk0 + sub);
+        for (uint32_t blk0 = 0; blk0 * 4 < kmax; blk0 += G) {
+            const uint4 blk = stream_block(keys, SDX_STREAM_DEAL, null_id, t, blk0 + sub);
 #pragma unroll 1
-        for (int q = 0; q < G; ++q) {
-            const uint32_t i0 = (blk0 + q) * 4;
-            if (i0 >= kmax) break;                      // warp-uniform
-            uint32_t x[4];
-            x[0] = __shfl_sync(FULL, blk.x, q, G);
-            x[1] = __shfl_sync(FULL, blk.y, q, G);
-            x[2] = __shfl_sync(FULL, blk.z, q, G);
-            x[3] = __shfl_sync(FULL, blk.w, q, G);
-            if (sub == 0 && i0 < k) {
+            for (int q = 0; q < G; ++q) {
+                const uint32_t i0 = (blk0 + q) * 4;
+                if (i0 >= kmax) break;                  // warp-uniform
+                uint32_t x[4];
+                x[0] = __shfl_sync(FULL, blk.x, q, G);
+                x[1] = __shfl_sync(FULL, blk.y, q, G);
+                x[2] = __shfl_sync(FULL, blk.z, q, G);
+                x[3] = __shfl_sync(FULL, blk.w, q, G);
+                if (sub == 0 && i0 < k) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t i = i0 + c;
-                    if (i < k) {
-                        const uint32_t m = n - k + i + 1;               // Floyd: j = m - 1, r uniform in [0, j]
-                        const uint64_t prod = (uint64_t)x[c] * m;
-                        uint32_t r = (uint32_t)(prod >> 32);
-                        if ((uint32_t)prod < m) r = deal_below_slow(&keys, null_id, t, i, m, x[c]);
-                        uint32_t w = cm[r >> 5];
-                        if ((w >> (r & 31)) & 1u) { r = m - 1; w = cm[r >> 5]; }
-                        cm[r >> 5] = w | (1u << (r & 31));
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t i = i0 + c;
+                        if (i < k) {
+                            const uint32_t m = n - k + i + 1;           // Floyd: j = m - 1, r uniform in [0, j]
+                            const uint64_t prod = (uint64_t)x[c] * m;
+                            uint32_t r = (uint32_t)(prod >> 32);
+                            if ((uint32_t)prod < m) r = deal_below_slow(&keys, null_id, t, i, m, x[c]);
+                            const uint32_t w = (r & 32u) ? c1 : c0;
+                            if ((w >> (r & 31)) & 1u) r = m - 1;
+                            const uint32_t bit = 1u << (r & 31);
+                            if (r & 32u) c1 |= bit; else c0 |= bit;
+                        }
                     }
                 }
             }
         }
-    }
-    __syncwarp();
-
-    // expand: this lane's words take bits [off, off + popc) of the compressed mask, in rank order
-    uint32_t pick[V];
+        c0 = __shfl_sync(FULL, c0, 0, G);
+        c1 = __shfl_sync(FULL, c1, 0, G);
+        // drop the ranks below this lane's first element, then peel popc(sym) bits per word
+        if (off & 32u) { c0 = c1; c1 = 0u; }
+        c0 = __funnelshift_r(c0, c1, off & 31u);
+        c1 >>= (off & 31u);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-        const uint32_t c = __popc(sym[i]);
-        uint32_t pk = 0;
-        if (go && c) {
-            const uint32_t w0 = off >> 5;
-            const uint32_t lo = cm[w0];
-            const uint32_t hi = (w0 + 1 < nw) ? cm[w0 + 1] : 0u;
-            uint32_t ch = __funnelshift_r(lo, hi, off & 31);
-            if (c < 32) ch &= (1u << c) - 1u;
-            uint32_t m = sym[i];
+        for (int i = 0; i < V; ++i) {
+            const uint32_t c = __popc(sym[i]);
+            uint32_t ch = c0 & __funnelshift_rc(0xffffffffu, 0u, 32u - c);
+            c0 = __funnelshift_rc(c0, c1, c);
+            c1 = (c & 32u) ? 0u : (c1 >> c);
+            uint32_t m = sym[i], pk = 0;
             while (ch) {
                 const uint32_t low = m & (0u - m);
                 m ^= low;
                 if (ch & 1u) pk |= low;
                 ch >>= 1;
             }
+            pick[i] = pk;
         }
-        pick[i] = pk;
-        off += c;
+    } else {
+        // ---- general path: the mask lives in the storage of row a (both rows are in registers) ------
+        volatile uint32_t *cm = rows + (size_t)a * RS;
+        const uint32_t nw = go ? (n + 31) >> 5 : 0u;
+        for (uint32_t i = sub; i < nw; i += G) cm[i] = 0u;
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t blk0 = 0; blk0 * 4 < kmax; blk0 += G) {
+            const uint4 blk = stream_block(keys, SDX_STREAM_DEAL, null_id, t, blk0 + sub);
+#pragma unroll 1
+            for (int q = 0; q < G; ++q) {
+                const uint32_t i0 = (blk0 + q) * 4;
+                if (i0 >= kmax) break;                  // warp-uniform
+                uint32_t x[4];
+                x[0] = __shfl_sync(FULL, blk.x, q, G);
+                x[1] = __shfl_sync(FULL, blk.y, q, G);
+                x[2] = __shfl_sync(FULL, blk.z, q, G);
+                x[3] = __shfl_sync(FULL, blk.w, q, G);
+                if (sub == 0 && i0 < k) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t i = i0 + c;
+                        if (i < k) {
+                            const uint32_t m = n - k + i + 1;
+                            const uint64_t prod = (uint64_t)x[c] * m;
+                            uint32_t r = (uint32_t)(prod >> 32);
+                            if ((uint32_t)prod < m) r = deal_below_slow(&keys, null_id, t, i, m, x[c]);
+                            uint32_t w = cm[r >> 5];
+                            if ((w >> (r & 31)) & 1u) { r = m - 1; w = cm[r >> 5]; }
+                            cm[r >> 5] = w | (1u << (r & 31));
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // expand: this lane's words take bits [off, off + popc) of the compressed mask, in rank order
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const uint32_t c = __popc(sym[i]);
+            uint32_t pk = 0;
+            if (go && c) {
+                const uint32_t w0 = off >> 5;
+                const uint32_t lo = cm[w0];
+                const uint32_t hi = (w0 + 1 < nw) ? cm[w0 + 1] : 0u;
+                uint32_t ch = __funnelshift_r(lo, hi, off & 31);
+                if (c < 32) ch &= (1u << c) - 1u;
+                uint32_t m = sym[i];
+                while (ch) {
+                    const uint32_t low = m & (0u - m);
+                    m ^= low;
+                    if (ch & 1u) pk |= low;
+                    ch >>= 1;
+                }
+            }
+            pick[i] = pk;
+            off += c;
+        }
     }
     __syncwarp();                                       // all reads of the scratch are done before row a is rewritten
     if (go) {

@@ -1,6 +1,6 @@
 #!/bin/bash
 # sweep of the k_trade launch configuration on the C1 workload (benchmarks only)
-for cfg in "8 4 1" "8 8 2" "8 8 0" "4 4 1" "4 8 2" "4 8 0" "2 4 1" "2 8 2" "16 4 1" "16 8 2"; do
+for cfg in "8 4 1" "4 4 1" "4 8 2" "4 8 3" "4 6 3" "2 4 1" "2 8 3" "8 8 3"; do
   set -- $cfg
   v=$(SDX_TRADE_G=$1 SDX_TRADE_WARPS=$2 SDX_TRADE_LB=$3 python bench.py --steps 3 --warmup 2 --no-extra --nulls 100000 2>&1 | python -c "
 import sys,json
