@@ -145,6 +145,12 @@ int sdx_null_pvalue(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls
  * order, size-major then lexicographic).  n_scored: number of subsets scored. */
 int sdx_scan(sdx_ctx *ctx, int profile, int k, int topn, sdx_hit *hits, int64_t *n_scored);
 
+/* The same restricted to subsets whose smallest feature index lies in
+ * [g_lo, g_hi): the unit of multi-GPU sharding (ranks take disjoint ranges and
+ * merge their top lists; the counts add up to sdx_scan's). */
+int sdx_scan_range(sdx_ctx *ctx, int profile, int k, int topn, int g_lo, int g_hi, sdx_hit *hits,
+                   int64_t *n_scored);
+
 /* conditional_permutation_test (src/superdendrix.py:361-384) for one module of
  * one profile: counts[i] = #{t < n_perm : W(M with g_i := random |g_i|-subset
  * of the profile's samples) >= W(M)} (:372-374); the caller applies the

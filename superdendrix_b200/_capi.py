@@ -63,6 +63,7 @@ PROTOTYPES = {
     "sdx_null_pvalue": (C.c_int, [_ctx, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _i32p,
                                   C.c_int, _f64p, _i64p, _f64p, _f64p]),
     "sdx_scan": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.POINTER(Hit), _i64p]),
+    "sdx_scan_range": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Hit), _i64p]),
     "sdx_condperm": (C.c_int, [_ctx, C.c_int, _i32p, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _i64p, _f64p]),
     "sdx_condperm_batch": (C.c_int, [_ctx, _i32p, _i32p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _i64p, _f64p]),
     "sdx_ranksum": (C.c_int, [_ctx, _i32p, _i32p, C.c_int64, C.c_int, _f64p, _f64p, _i64p, _i32p]),

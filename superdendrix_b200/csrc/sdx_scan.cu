@@ -208,7 +208,8 @@ struct ScanArgs {
     const double *s1;                      // F
     const double *T; int Fp;
     int F, S, wprS, k;
-    int n_gt, n_hb, n_lc;
+    int g_lo, g_hi;                        // only subsets whose smallest feature index is in [g_lo, g_hi)
+    int gt0, n_gt, n_hb, n_lc;             // g-tiles gt0 .. gt0 + n_gt - 1
     unsigned int *item_counter;
     unsigned long long *g_thr;
     unsigned long long *n_scored;
@@ -225,13 +226,13 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan12(const __grid_constant__ Scan
     // singles
     for (int g0 = blockIdx.x * SCAN_NT; g0 < F; g0 += gridDim.x * SCAN_NT) {
         const int g = g0 + tid;
-        const bool v = g < F;
+        const bool v = g < F && g >= p.g_lo && g < p.g_hi;
         const double W = v ? p.s1[g] : -INFINITY;
         cnt += v;
         top.offer(v && W >= top.gate, W, scan_key(1, v ? g : 0, 0, 0), lane);
     }
     if (p.k >= 2) {
-        for (int g = blockIdx.x; g < F - 1; g += gridDim.x) {
+        for (int g = p.g_lo + blockIdx.x; g < min(p.g_hi, F - 1); g += gridDim.x) {
             top.refresh(p.g_thr);
             const double sg = p.s1[g];
             const double *Tg = p.T + (size_t)g * p.Fp;
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
         __syncthreads();
         const unsigned it = s_item;
         if (it >= total) break;
-        const int gt = it / per_gt, rem = it - gt * per_gt, hb = rem / p.n_lc, lc = rem - hb * p.n_lc;
+        const int gt = p.gt0 + it / per_gt, rem = it % per_gt, hb = rem / p.n_lc, lc = rem - hb * p.n_lc;
         const int g0 = gt * SCAN_GT, l0 = lc * (SCAN_NT * SCAN_NJ);
         const int hlo = max(hb * SCAN_HB, g0 + 1), hhi = min(hb * SCAN_HB + SCAN_HB, F - 1);
         if (hlo >= hhi || l0 + SCAN_NT * SCAN_NJ - 1 <= hlo) continue;
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
 #pragma unroll
             for (int gi = 0; gi < SCAN_GT; ++gi) {
                 const int g = g0 + gi;
-                c[gi][j] = (l < F && g < l) ? sl + p.T[(size_t)g * Fp + l] : -INFINITY;
+                c[gi][j] = (l < F && g < l && g >= p.g_lo && g < p.g_hi) ? sl + p.T[(size_t)g * Fp + l] : -INFINITY;
             }
         }
 
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
 #pragma unroll
             for (int gi = 0; gi < SCAN_GT; ++gi) {
                 const int g = g0 + gi;
-                const bool v = g < h;
+                const bool v = g < h && g >= p.g_lo && g < p.g_hi;
                 const double tgh = v ? p.T[(size_t)g * Fp + h] : 0.0;
                 sgh[gi] = v ? (p.s1[g] + sh) + tgh : -INFINITY;
                 slow[gi] = v && tgh != 0.0;
@@ -390,7 +391,14 @@ __global__ void k_scan_collect(const double *__restrict__ W, const unsigned long
 }
 
 // ---------------------------------------------------------------------------
+extern "C" int sdx_scan_range(sdx_ctx *c, int profile, int k, int topn, int g_lo, int g_hi, sdx_hit *hits, int64_t *n_scored);
+
 extern "C" int sdx_scan(sdx_ctx *c, int profile, int k, int topn, sdx_hit *hits, int64_t *n_scored) {
+    if (!c) return SDX_ERR_INVALID;
+    return sdx_scan_range(c, profile, k, topn, 0, c->F, hits, n_scored);
+}
+
+extern "C" int sdx_scan_range(sdx_ctx *c, int profile, int k, int topn, int g_lo, int g_hi, sdx_hit *hits, int64_t *n_scored) {
     if (!c) return SDX_ERR_INVALID;
     SDX_REQUIRE(c, c->d_feat && c->d_w, SDX_ERR_STATE, "matrix and weights must be uploaded first");
     SDX_REQUIRE(c, profile >= 0 && profile < c->P, SDX_ERR_INVALID, "profile index out of range");
@@ -398,6 +406,7 @@ extern "C" int sdx_scan(sdx_ctx *c, int profile, int k, int topn, sdx_hit *hits,
     SDX_REQUIRE(c, topn >= 1 && topn <= SCAN_NL - 16 && hits, SDX_ERR_INVALID, "topn must be in 1..48");
     SDX_REQUIRE(c, c->wprS <= SCAN_MAXW, SDX_ERR_UNSUPPORTED, "the scan supports at most 8192 samples");
     SDX_REQUIRE(c, c->F < (1 << 20), SDX_ERR_UNSUPPORTED, "the scan supports fewer than 2^20 features");
+    SDX_REQUIRE(c, g_lo >= 0 && g_lo <= g_hi && g_hi <= c->F, SDX_ERR_INVALID, "feature range must satisfy 0 <= g_lo <= g_hi <= n_features");
     const int F = c->F, S = c->S, wprS = c->wprS;
     const int Fp = ((F + 3) / 4) * 4;
     const int grid12 = c->sm_count * 2, grid3 = c->sm_count * 2;
@@ -445,7 +454,8 @@ extern "C" int sdx_scan(sdx_ctx *c, int profile, int k, int topn, sdx_hit *hits,
     ScanArgs a{};
     a.feat = c->d_feat; a.fstride = wprS; a.samp = c->d_samp; a.sstride = c->wprF; a.pos = d_pos; a.wpos = d_wpos;
     a.s1 = d_s1; a.T = d_T; a.Fp = Fp; a.F = F; a.S = S; a.wprS = wprS; a.k = k;
-    a.n_gt = ceil_div(F, SCAN_GT); a.n_hb = ceil_div(F, SCAN_HB); a.n_lc = ceil_div(F, SCAN_NT * SCAN_NJ);
+    a.g_lo = g_lo; a.g_hi = g_hi; a.gt0 = g_lo / SCAN_GT; a.n_gt = g_hi > g_lo ? ceil_div(g_hi, SCAN_GT) - a.gt0 : 0;
+    a.n_hb = ceil_div(F, SCAN_HB); a.n_lc = ceil_div(F, SCAN_NT * SCAN_NJ);
     a.item_counter = d_item; a.g_thr = d_thr; a.n_scored = d_nscored; a.outW = d_lW; a.outKey = d_lK;
     SDX_REQUIRE(c, (int64_t)a.n_gt * a.n_hb * a.n_lc < (1ll << 31), SDX_ERR_UNSUPPORTED, "too many scan work items");
     k_scan12<<<grid12, SCAN_NT, 0, c->stream>>>(a);

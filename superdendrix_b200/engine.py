@@ -172,10 +172,12 @@ class Engine:
         return {"n_ge": n_ge, "z_obs": zout, "null_scores": scores}
 
     # -- scan / model selection / rank-sum -------------------------------------
-    def scan(self, profile: int = 0, k: int = 3, topn: int = 8):
+    def scan(self, profile: int = 0, k: int = 3, topn: int = 8, g_lo: int = 0, g_hi: int | None = None):
+        """Exhaustive scan over subsets of size <= k whose smallest feature index is in [g_lo, g_hi)."""
         hits = (_capi.Hit * topn)()
         n = C.c_int64(0)
-        self._check(self._lib.sdx_scan(self._ctx, int(profile), int(k), int(topn), hits, C.byref(n)))
+        self._check(self._lib.sdx_scan_range(self._ctx, int(profile), int(k), int(topn), int(g_lo),
+                                             int(self.F if g_hi is None else g_hi), hits, C.byref(n)))
         W = np.array([h.W for h in hits])
         feats = np.array([[h.features[0], h.features[1], h.features[2]] for h in hits], dtype=np.int32)
         cov = np.array([h.coverage for h in hits], dtype=np.int32)

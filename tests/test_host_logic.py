@@ -1,0 +1,131 @@
+"""Host-side logic: loaders (against the fixtures made from the reference), the TSV writer,
+profile parsing, bit packing and the sharding / merging helpers.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from superdendrix_b200 import bitpack, dist, i_o, synth
+from superdendrix_b200 import superdendrix as sd
+
+from conftest import GOLDEN
+
+
+def test_loader_matches_reference_fixtures():
+    with open(os.path.join(GOLDEN, "loader.json")) as fh:
+        cases = json.load(fh)
+    d = os.path.join(GOLDEN, "loader")
+    for name, c in cases.items():
+        kw = dict(c["kwargs"])
+        m, n, genes, patients, g2c, p2g = i_o.load_mutation_data(
+            os.path.join(d, "features.tsv"), kw.get("patients"),
+            os.path.join(d, kw["geneFile"]) if "geneFile" in kw else None,
+            kw.get("mut_only", False), kw.get("min_freq", 0), kw.get("max_freq", float("inf")))
+        assert (m, n) == (c["m"], c["n"]), name
+        assert sorted(genes) == c["genes"] and list(patients) == c["patients"]
+        assert {g: sorted(v) for g, v in g2c.items()} == c["geneToCases"]
+        assert {p: sorted(v) for p, v in p2g.items()} == c["patientToGenes"]
+
+
+def test_reference_null_files_round_trip(tmp_path):
+    """Files written by the reference generator parse, pack, unpack and re-write to the same content."""
+    gdir = os.path.join(GOLDEN, "generator")
+    m, n, genes, samples, g2c, p2g = i_o.load_mutation_data(os.path.join(gdir, "features.tsv"))
+    dense = i_o.dense_matrix(genes, samples, p2g)
+    rows = i_o.pack_features(genes, samples, g2c)
+    assert np.array_equal(bitpack.unpack_rows(rows, len(samples)), dense.T)
+    for f in sorted(os.listdir(gdir)):
+        if not f.startswith("ref_null_"):
+            continue
+        pm, pn, pgenes, psamples, pg2c, pp2g = i_o.load_mutation_data(os.path.join(gdir, f))
+        nd = i_o.dense_matrix(genes, samples, pp2g)
+        assert np.array_equal(nd.sum(0), dense.sum(0)) and np.array_equal(nd.sum(1), dense.sum(1))   # Curveball margins
+        out = tmp_path / f
+        i_o.write_sample_events(str(out), samples, genes, nd)
+        again = i_o.load_mutation_data(str(out))
+        assert {g: sorted(v) for g, v in again[4].items()} == {g: sorted(v) for g, v in pg2c.items()}
+        assert again[3] == psamples                      # samples with no events are kept, in order
+        assert open(out).readline() == "#Samples\tEvents\n"
+
+
+def test_parse_profile_semantics(tmp_path):
+    p = tmp_path / "t.tsv"
+    p.write_text("id\tA\tB\ns1\t1.5\t2\ns2\tnan\t3\ns3\tinf\t4\ns4\t\t5\ns5\t-2\tx\n# c\ts\ns6\t0\t6\n")
+    w, bad, rows = sd.parse_profile(str(p), "A")                      # increased_dependency: sign flip
+    assert w == {"s1": -1.5, "s3": -100.0, "s5": 2.0, "s6": -0.0} and bad == 3 and rows == 6
+    w, bad, _ = sd.parse_profile(str(p), "A", direction="positive", offset=0.5)
+    assert w == {"s1": 2.0, "s3": 100.0, "s5": -1.5, "s6": 0.5}
+    w, _, _ = sd.parse_profile(str(p), "A", direction="positive", unit_weights=True)
+    assert w == {"s1": 1, "s3": 100.0, "s5": -1, "s6": -1}
+    w, bad, _ = sd.parse_profile(str(p), "B", direction="positive")
+    assert bad == 1 and "s5" not in w and w["s6"] == 6.0
+
+
+def test_profile_loaders(tmp_path):
+    p = tmp_path / "prof.csv"
+    p.write_text("id,G1_x,G2_y\na,1,NA\nb,,2.5\n")
+    profs, samples = i_o.load_profiles(str(p))
+    assert samples == ["a", "b"] and np.isnan(profs["G1_x"][1]) and np.isnan(profs["G2_y"][0]) and profs["G2_y"][1] == 2.5
+    profs, samples = i_o.load_profiles(str(p), sample_whitelist={"b"})
+    assert samples == ["b"] and profs["G2_y"].tolist() == [2.5]
+    assert i_o.load_single_profile(str(p), "G1") == {"a": 1.0, "b": 0.0}
+    ev, ms = i_o.load_events(os.path.join(GOLDEN, "loader", "features.tsv"))
+    assert ms and all(isinstance(v, set) for v in ev.values())
+
+
+def test_bitpack_round_trip_and_padding():
+    rng = np.random.default_rng(0)
+    for L in (1, 31, 32, 33, 770):
+        d = rng.random((5, L)) < 0.3
+        p = bitpack.pack_rows(d)
+        assert p.shape == (5, bitpack.words_for(L)) and p.dtype == np.uint32
+        assert np.array_equal(bitpack.unpack_rows(p, L), d.astype(np.uint8))
+        assert np.array_equal(bitpack.popcount_rows(p), d.sum(1))
+        if L % 32:
+            assert (p[:, -1] >> (L % 32) == 0).all()
+    assert bitpack.pack_mask([0, 33], 40).tolist() == [1, 2]
+
+
+def test_shard_ranges_cover_and_balance():
+    for n in (0, 1, 7, 100000, 100003):
+        for world in (1, 2, 3, 8):
+            r = [dist.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_scan_feature_ranges_balance_work():
+    F = 2000
+    for world in (1, 2, 4, 8):
+        r = dist.scan_feature_ranges(F, 3, world)
+        assert r[0][0] == 0 and r[-1][1] == F and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+
+        def work(lo, hi):
+            g = np.arange(lo, hi, dtype=np.float64)
+            q = F - 1 - g
+            return (1 + q + q * (q - 1) / 2).sum()
+        w = [work(*x) for x in r]
+        assert sum(w) == F + F * (F - 1) // 2 + F * (F - 1) * (F - 2) // 6
+        assert max(w) / (sum(w) / world) < 1.02
+    assert dist.scan_feature_ranges(3, 3, 8)[-1][1] == 3
+
+
+def test_merge_hits_orders_like_a_single_scan():
+    a = {"W": np.array([5.0, 3.0, -np.inf]), "features": np.array([[1, 2, 3], [4, -1, -1], [-1, -1, -1]]), "coverage": np.array([9, 2, 0])}
+    b = {"W": np.array([5.0, 4.0, 3.0]), "features": np.array([[0, 9, -1], [7, 8, 9], [2, -1, -1]]), "coverage": np.array([7, 5, 1])}
+    m = dist.merge_hits([a, b], 4)
+    assert m["W"].tolist() == [5.0, 5.0, 4.0, 3.0]
+    assert m["features"].tolist() == [[0, 9, -1], [1, 2, 3], [7, 8, 9], [2, -1, -1]]      # equal W: pairs before triples
+    assert m["coverage"].tolist() == [7, 9, 5, 1]
+    assert dist.merge_hits([a], 5)["features"][2:].tolist() == [[-1, -1, -1]] * 3
+
+
+def test_synthetic_shapes_are_stable():
+    dense, samples, feats = synth.feature_matrix(770, 400)
+    assert dense.shape[0] == 770 and 380 <= dense.shape[1] <= 400 and dense.sum(0).min() >= 1
+    assert dense.sum() == synth.feature_matrix(770, 400)[0].sum()
+    w = synth.weights(770, 2)
+    assert w.shape == (2, 770) and (w == 0).mean() > 0.005 and np.abs(w).max() <= 20
