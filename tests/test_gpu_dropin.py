@@ -1,0 +1,238 @@
+"""The reference-named Python entry points (drop-in layer) running on the GPU, checked against the oracle,
+the golden fixtures made from the reference and the reference's file formats.  Needs a B200: -m gpu."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import refport
+from superdendrix_b200 import bitpack, curveball, dist, generate_null_matrices as gnm, i_o, synth
+from superdendrix_b200 import superdendrix as sd
+from superdendrix_b200.engine import Engine
+
+from conftest import GOLDEN, load_npz, rows_of
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------- src/curveball.py
+@pytest.mark.parametrize("shape", [(40, 17), (17, 40), (25, 25)])
+def test_curveball_shim_keeps_reference_semantics(shape):
+    rng = np.random.default_rng(shape[0])
+    mat = (rng.random(shape) < 0.3).astype(np.float64)
+    hp = curveball.find_presences(mat)
+    assert [list(map(int, r)) for r in hp] == [list(map(int, r)) for r in refport.presences(mat)]
+    curveball.seed(1764)
+    obs = rows_of(mat.astype(np.uint8))
+    want, _ = oracle.curveball_nulls(obs, 1764, 0, 3, 5 * min(shape), chain_len=3)     # one chain, nulls 0..2
+    L = max(shape)
+    for i in range(3):
+        out = curveball.curve_ball(mat, hp)
+        assert out.dtype == np.int8 and out.shape == mat.shape
+        assert np.array_equal(out.sum(0), mat.sum(0)) and np.array_equal(out.sum(1), mat.sum(1))
+        state = out if shape[1] >= shape[0] else out.T
+        assert np.array_equal(bitpack.pack_rows(state), want[i])
+        # r_hp holds the new state (the reference mutates it in place, src/curveball.py:34-35)
+        assert [sorted(map(int, r)) for r in hp] == [list(np.flatnonzero(state[r])) for r in range(len(hp))]
+    out = curveball.curve_ball(mat, hp, num_iterations=0)
+    assert np.array_equal(out if shape[1] >= shape[0] else out.T, bitpack.unpack_rows(want[2], L))
+
+
+# ---------------------------------------------------------------- SuperW / conditional permutation under the reference names
+def test_superw_shim_matches_reference_values():
+    z = load_npz("superw.npz")
+    dense = z["dense"]
+    S, F = dense.shape
+    samples = ["s%d" % i for i in range(S)]
+    for i in range(0, len(z["W"]), 7):
+        w = z["weights"][z["kind"][i]]
+        profile = {samples[j]: float(w[j]) for j in range(S)}
+        feats = z["modules"][i][z["modules"][i] >= 0]
+        cases = [set(samples[j] for j in np.flatnonzero(dense[:, g])) for g in feats]
+        assert abs(sd.SuperW(cases, profile, samples) - z["W"][i]) <= 1e-9 * max(1.0, np.abs(w).sum())
+    assert sd.SuperW([], {"a": 1.0}, ["a"]) == 0.0
+
+
+def test_conditional_permutation_shim_agrees_with_reference_decisions():
+    zd = load_npz("condperm_data.npz")
+    with open(os.path.join(GOLDEN, "condperm.json")) as fh:
+        meta = json.load(fh)
+    dense, w = zd["dense"], zd["w"]
+    S, F = dense.shape
+    samples = ["s%d" % i for i in range(S)]
+    profile = {samples[i]: float(w[i]) for i in range(S)}
+    e2c = {"f%d" % g: set(samples[i] for i in np.flatnonzero(dense[:, g])) for g in range(F)}
+    sd.seed(11)
+    for c in meta["cases"]:
+        P = c["P"]
+        ev, cnt = sd.conditional_permutation_test(["f%d" % g for g in c["feats"]], e2c, profile, samples, P)
+        want_counts = c["per_feature"]
+        top = max(want_counts)
+        p = max(top, 1) / P
+        assert abs(cnt - top) < 4.5 * (np.sqrt(2 * P * p * (1 - p)) + 1)
+        srt = sorted(want_counts, reverse=True)
+        if top == 0:
+            assert ev is None or cnt <= 3
+        elif len(srt) == 1 or srt[0] - srt[1] > 6 * np.sqrt(P * p * (1 - p)) + 3:      # decision only checked when unambiguous
+            assert ev == c["worst"]
+
+
+# ---------------------------------------------------------------- generator CLI and file formats
+def test_generate_null_matrices_cli_writes_reference_format(tmp_path):
+    gdir = os.path.join(GOLDEN, "generator")
+    out = tmp_path / "nulls"
+    out.mkdir()
+    rc = gnm.main(["-m", os.path.join(gdir, "features.tsv"), "-p", "6", "-o", str(out) + "/", "-rs", "5", "--mode", "restart",
+                   "--packed", str(tmp_path / "nulls.npz")])
+    assert rc == 0
+    m, n, genes, samples, g2c, p2g = i_o.load_mutation_data(os.path.join(gdir, "features.tsv"))
+    dense = i_o.dense_matrix(genes, samples, p2g)
+    with Engine(0) as eng:
+        eng.upload_dense(dense)
+        R, L, wpr, ras = eng.trade_shape()
+        rows, _ = eng.curveball(5, 0, 6, chain_len=1)
+    pk = np.load(tmp_path / "nulls.npz")
+    for i in range(6):
+        path = out / ("%d.tsv" % i)
+        assert open(path).readline() == "#Samples\tEvents\n"
+        pm, pn, pgenes, psamples, pg2c, pp2g = i_o.load_mutation_data(str(path))
+        assert psamples == samples                                    # every sample listed, file order kept
+        nd = i_o.dense_matrix(genes, samples, pp2g)
+        assert np.array_equal(nd.sum(0), dense.sum(0)) and np.array_equal(nd.sum(1), dense.sum(1))
+        bits = bitpack.unpack_rows(rows[i], L)
+        assert np.array_equal(nd, bits if ras else bits.T)
+        assert np.array_equal(pk["feature_rows"][i], bitpack.pack_rows(nd.T))
+        # events in a row follow the order of `genes`, as src/generate_null_matrices.py:78 does
+        for line in open(path).read().splitlines()[1:4]:
+            ev = line.split("\t")[1:]
+            assert ev == [g for g in genes if g in set(ev)]
+    # sharding by -pre: nulls 4..5 of a second process equal nulls 4..5 above
+    out2 = tmp_path / "shard"
+    out2.mkdir()
+    gnm.main(["-m", os.path.join(gdir, "features.tsv"), "-p", "2", "-pre", "4", "-o", str(out2) + "/", "-rs", "5", "--mode", "restart"])
+    for i in (4, 5):
+        assert open(out2 / ("%d.tsv" % i)).read() == open(out / ("%d.tsv" % i)).read()
+    # chained mode: one Markov chain, like the reference driver
+    out3 = tmp_path / "chain"
+    out3.mkdir()
+    gnm.main(["-m", os.path.join(gdir, "features.tsv"), "-p", "3", "-o", str(out3) + "/", "-rs", "5"])
+    want, _ = oracle.curveball_nulls(rows_of(dense), 5, 0, 3, 5 * R, chain_len=3)
+    pp2g = i_o.load_mutation_data(str(out3 / "2.tsv"))[5]
+    nd = i_o.dense_matrix(genes, samples, pp2g)
+    assert np.array_equal(bitpack.pack_rows(nd if ras else nd.T), want[2])
+
+
+# ---------------------------------------------------------------- the driver end to end
+def _write_case(tmp_path, S=120, F=40, seed=3):
+    dense, samples, features = synth.feature_matrix(S, F, seed=seed)
+    w = synth.weights(S, 2, seed=seed + 1)
+    w[0, 5] = np.nan
+    mut = tmp_path / "features.tsv"
+    synth.write_features_tsv(str(mut), dense, samples, features)
+    prof = tmp_path / "profiles.tsv"
+    synth.write_profile_tsv(str(prof), samples, w, ["GENE1", "GENE2"])
+    return dense, samples, features, w, mut, prof
+
+
+@pytest.mark.parametrize("stat", ["fixed"])
+def test_driver_end_to_end_against_oracle(tmp_path, stat):
+    dense, samples, features, w, mut, prof = _write_case(tmp_path)
+    out = tmp_path / "res.tsv"
+    args = sd.get_parser().parse_args(["-m", str(mut), "-T", str(prof), "-Tc", "GENE1", "-k", "3", "-cp", "200", "-p", "64",
+                                       "-o", str(out), "-d", "positive", "--null-stat", stat, "-rs", "9"])
+    module = sd.run(args)
+    keep = ~np.isnan(w[0])
+    kept = {s for s, k_ in zip(samples, keep) if k_}
+    # the matrix as the driver sees it: profiled samples only; features without a carrier among them vanish
+    # (src/i_o.py:57,62-67); feature order = the loader's
+    _, _, names, smp, _, s2g = i_o.load_mutation_data(str(mut), kept)
+    d = i_o.dense_matrix(names, smp, s2g)
+    assert smp == [s for s in samples if s in kept] and d.shape[1] == int((dense[keep].sum(0) > 0).sum())
+    rows = bitpack.pack_rows(d.T)
+    wv = w[0][keep]
+    oW, oF, oC, _ = oracle.scan(rows, d.shape[0], wv, 3, 1)
+    last = sd.run.last
+    assert abs(last["z"] - max(oW[0], 0.0)) <= 1e-9 * np.abs(wv).sum()
+    # model selection can only remove features from the scan optimum
+    assert set(module) <= {names[f] for f in oF[0] if f >= 0}
+    feats = sorted(names.index(g) for g in module)
+    zP, cov, _, _ = oracle.score_set(rows, d.shape[0], feats, wv)
+    assert abs(last["zP"] - zP) <= 1e-9 * np.abs(wv).sum()
+    # null loop: same nulls through the oracle
+    obs = rows_of(d)
+    nulls, _ = oracle.curveball_nulls(obs, 9, 0, 64, 5 * obs.shape[0], 1)
+    ras = d.shape[1] >= d.shape[0]
+    sc = []
+    for m in nulls:
+        fr = bitpack.pack_rows(bitpack.unpack_rows(m, max(d.shape)).T) if ras else m
+        sc.append(oracle.score_set(fr, d.shape[0], feats, wv)[0])
+    assert np.allclose(last["null_scores"], sc, rtol=0, atol=1e-9 * np.abs(wv).sum())
+    # result row (src/superdendrix.py:241-257)
+    head, row = open(out).read().splitlines()
+    assert head == "profile\tfeatures\t#samples\tscores\tW(M)(%)\tcoverage\tP_value\tdirection\tfeature_count"
+    f = row.split("\t")
+    assert f[0] == "GENE1" and set(f[1].split(",")) == set(module) and f[7] == "positive" and int(f[8]) == len(module)
+    assert f[5] == "%d/%d" % (cov, d.shape[0])
+    assert float(f[6]) == float((np.array(last["null_scores"]) >= last["zP"]).sum()) / 64
+    max_score = wv[wv > 0].sum()
+    assert abs(float(f[4]) - round(100 * zP / max_score, 4)) < 1e-3
+    counts = [int(x) for x in f[2].split(",")]
+    assert sorted(counts) == sorted(int(d[:, names.index(g)].sum()) for g in module)
+
+
+def test_driver_reads_null_files_like_the_reference(tmp_path):
+    dense, samples, features, w, mut, prof = _write_case(tmp_path, S=90, F=30, seed=8)
+    nm = tmp_path / "rand_mat"
+    nm.mkdir()
+    gnm.main(["-m", str(mut), "-p", "12", "-o", str(nm) + "/", "-rs", "4"])
+    out = tmp_path / "res.tsv"
+    args = sd.get_parser().parse_args(["-m", str(mut), "-nm", str(nm) + "/", "-T", str(prof), "-Tc", "GENE2", "-k", "2", "-cp", "-1",
+                                       "-p", "12", "-o", str(out), "-d", "positive", "--null-stat", "fixed"])
+    module = sd.run(args)
+    last = sd.run.last
+    profile = {s: float(w[1][i]) for i, s in enumerate(samples)}
+    sc = []
+    for i in range(12):
+        e2s = i_o.load_mutation_data(str(nm / ("%d.tsv" % i)), profile.keys())[4]
+        sc.append(refport.super_w([e2s[g] for g in module if g in e2s], profile))
+    assert np.allclose(last["null_scores"], sc, rtol=0, atol=1e-9 * np.abs(w[1]).sum())
+    assert float(open(out).read().splitlines()[1].split("\t")[6]) == float((np.array(sc) >= last["zP"]).sum()) / 12
+
+
+def test_too_many_bad_profile_values_aborts_like_the_reference(tmp_path):
+    dense, samples, features, w, mut, prof = _write_case(tmp_path, S=50, F=12, seed=1)
+    w[1, :10] = np.nan
+    synth.write_profile_tsv(str(prof), samples, w, ["GENE1", "GENE2"])
+    out = tmp_path / "res.tsv"
+    args = sd.get_parser().parse_args(["-m", str(mut), "-T", str(prof), "-Tc", "GENE2", "-k", "2", "-o", str(out)])
+    assert sd.run(args) == 1
+    assert "incomplete due to high Nan, Inf" in open(out).read()
+
+
+# ---------------------------------------------------------------- dist helpers over the real engine (world = 1)
+def test_dist_functions_single_rank():
+    dense, _, _ = synth.feature_matrix(200, 60, seed=2)
+    S, F = dense.shape
+    w = synth.weights(S, 2, seed=6)
+    modules = np.array([[0, 1, 2], [3, 4, -1]], dtype=np.int32)
+    with Engine(0) as eng:
+        eng.upload_dense(dense)
+        eng.upload_weights(w)
+        pv = dist.null_pvalue(eng, 3, 50, modules)
+        direct = eng.null_pvalue(3, 0, 50, modules)
+        assert np.array_equal(pv["n_ge"], direct["n_ge"]) and np.allclose(pv["p"], direct["n_ge"] / 50)
+        whole = eng.scan(0, 3, 8)
+        # two "ranks" emulated in one process: ranges merge to the whole
+        parts = [eng.scan(0, 3, 8, g_lo=lo, g_hi=hi) for lo, hi in dist.scan_feature_ranges(F, 3, 3)]
+        merged = dist.merge_hits(parts, 8)
+        assert np.array_equal(merged["features"], whole["features"]) and np.array_equal(merged["W"], whole["W"])
+        assert sum(p["n_scored"] for p in parts) == whole["n_scored"]
+        sc = dist.scan(eng, 0, 3, 8)
+        assert np.array_equal(sc["features"], whole["features"]) and sc["n_scored"] == whole["n_scored"]
+        cp = dist.condperm_batch(eng, modules, 100, seed=1, profile_of_job=np.array([0, 1], dtype=np.int32))
+        assert np.array_equal(cp[0], eng.condperm_batch(modules, 100, 1, 0, np.array([0, 1], dtype=np.int32))[0])
+        rs = dist.ranksum(eng, modules, np.array([0, 1], dtype=np.int32))
+        assert np.array_equal(rs["twice_rank_sum"], eng.ranksum(modules, np.array([0, 1], dtype=np.int32))["twice_rank_sum"])
