@@ -112,6 +112,8 @@ __global__ void k_transpose_bits(const uint32_t *__restrict__ in, int n_rows, in
                                  uint32_t *__restrict__ out, int wpr_out) {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    in += (size_t)blockIdx.y * n_rows * wpr_in;              // blockIdx.y = matrix of a batch
+    out += (size_t)blockIdx.y * n_cols * wpr_out;
     const int tiles_c = wpr_in;
     const int rw = tile / tiles_c, cw = tile - rw * tiles_c;     // row word (of out), col word (of in)
     if (rw >= wpr_out) return;
@@ -134,6 +136,16 @@ __global__ void k_row_sizes(const uint32_t *__restrict__ rows, int R, int RS, in
     for (int i = lane; i < RS; i += 32) c += __popc(rows[(size_t)r * RS + i]);
     c = warp_sum_i32(c);
     if (lane == 0) size[r] = c;
+}
+
+// batch of nb bit matrices (n_rows x wpr_in words each, dense) -> their transposes (n_cols x wpr_out words each)
+int sdx_transpose_batch(sdx_ctx *c, const uint32_t *d_in, int n_rows, int wpr_in, int n_cols, uint32_t *d_out, int wpr_out, int nb) {
+    const int tiles = wpr_out * wpr_in;
+    k_transpose_bits<<<dim3(ceil_div(tiles, 8), nb), 256, 0, c->stream>>>(d_in, n_rows, wpr_in, n_cols, d_out, wpr_out);
+    c->total_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return sdx_fail(c, SDX_ERR_CUDA, std::string("k_transpose_bits launch failed: ") + cudaGetErrorString(e));
+    return SDX_OK;
 }
 
 extern "C" int sdx_upload_matrix(sdx_ctx *c, const uint32_t *rows, int F, int S, int wpr) {

@@ -552,7 +552,7 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
                         if (hi > lo)
                             SDX_CUDA(c, cudaMemcpyAsync(out_rows + (size_t)(lo - null0) * out_per,
                                                         (uint32_t *)p_out + (size_t)(l0 + (int64_t)(lo - first)) * out_per,
-                                                        sizeof(uint32_t) * out_per * (hi - lo), cudaMemcpyDeviceToHost, c->stream));
+                                                        sizeof(uint32_t) * out_per * (hi - lo), cudaMemcpyDefault, c->stream));
                     }
                 }
                 SDX_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -582,6 +582,12 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
     rc = timer.finish();
     c->timing.plan_ms = plan_ms; c->timing.trade_ms = trade_ms;
     return rc;
+}
+
+// nulls null0 .. null0+n-1 as dense trade rows (n x R x wprL words) into DEVICE memory (used by the max_k statistic)
+int sdx_generate_to_device(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n, int64_t n_trades, int64_t chain_len,
+                           uint32_t *d_out) {
+    return sdx_run_nulls(ctx, seed, null0, n, n_trades, chain_len, d_out, nullptr, nullptr);
 }
 
 extern "C" int sdx_curveball(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
@@ -649,6 +655,6 @@ extern "C" int sdx_null_pvalue(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int6
     if (stat == SDX_STAT_FIXED)
         return sdx_null_pvalue_fixed(ctx, seed, null0, n_nulls, n_trades, chain_len, modules, k, z_obs, n_ge, null_scores, z_obs_out);
     if (stat == SDX_STAT_MAXK)
-        return sdx_fail(ctx, SDX_ERR_UNSUPPORTED, "stat = max_k is not built yet");
+        return sdx_null_pvalue_maxk(ctx, seed, null0, n_nulls, n_trades, chain_len, modules, k, z_obs, n_ge, null_scores, z_obs_out);
     return sdx_fail(ctx, SDX_ERR_INVALID, "unknown null statistic");
 }

