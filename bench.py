@@ -35,6 +35,7 @@ if ROOT not in sys.path:
 NULLS_PER_STEP = 100_000
 SEED = 1764          # the reference's default -rs (src/generate_null_matrices.py:32)
 POPC_PEAK_NOMINAL = 148 * 16 * 1.965e9     # 32-bit popc/s
+NCU_DRAM_BYTES_PER_NULL = (62.383360e6 + 591872.0) / 4000      # profiles/r01_k_trade_ncu_summary.md (r1c): the trade plan
 
 
 def workload():
@@ -154,7 +155,9 @@ def run_reference(args):
         "impl": "reference", "metric": "curveball_nulls_scored_per_s", "value": value, "unit": "nulls/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f64", "data": "synthetic",
-        "config": {"workload": "C1: BRAF-shape 770x%d, k=3 module, Curveball nulls (5*min(S,F) trades) + SuperW" % dense.shape[1],
+        "config": {"workload": "C1: BRAF-shape %dx%d (synthetic DepMap-20Q2 shape), fixed k=3 module, %d Curveball nulls per GPU per step, "
+                               "%d trades each, fused SuperW scoring + exceedance count" % (dense.shape[0], dense.shape[1], NULLS_PER_STEP,
+                                                                                            5 * min(dense.shape)),
                    "sample": "%d nulls per step (%d per process x %d processes) of the 100000-null workload" % (cores * per_proc, per_proc, cores)},
         "cpu_baseline": {"value": value, "unit": "nulls/s", "cores": cores, "kind": "port",
                          "sample": "%d nulls per step, %d processes, oracle/refport.py (CPython %s)" % (cores * per_proc, cores, sys.version.split()[0])},
@@ -297,8 +300,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(rows_np.nbytes + w_np.nbytes + modules.nbytes),
                     "d2h_bytes_per_step": int(8 + 8), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_trade<8,4,true>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peaks_src,
+            "roofline": {"bound": "hbm", "kernel": "k_trade", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_NULL * (n / -(-n // 32768)),
+                         "traffic_source": "ncu --set full capture profiles/r01_k_trade_c.ncu-rep: dram read+write per null x nulls per launch",
+                         "peak_source": peaks_src,
                          "bytes_per_null": bytes_per_null, "avg_launch_ms": avg_launch_ms,
                          "kernel_share_of_step": trade_ms / ms, "plan_share_of_step": plan_ms / ms,
                          "popc_per_s": popc_per_null * value / world, "popc_frac_of_nominal": popc_per_null * value / world / POPC_PEAK_NOMINAL,
@@ -323,10 +328,18 @@ def run_ours(args):
 
 
 def secondary(eng, torch):
-    """Scan / cond-perm / rank-sum throughput (not the headline; device-timed by the library's own events)."""
+    """Scan / max_k / cond-perm / rank-sum throughput (not the headline; device-timed by the library's own events)."""
     from superdendrix_b200 import bitpack, synth
+    from superdendrix_b200.engine import SDX_STAT_MAXK
     out = {}
-    try:
+
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:      # noqa: BLE001
+            out[name] = {"error": str(e)}
+
+    def scan_c2():
         dense, _, _ = synth.feature_matrix(1000, 2000, seed=20)
         w = synth.weights(1000, 1, seed=3)
         eng.upload_matrix(bitpack.pack_rows(dense.T), 1000)
@@ -336,11 +349,49 @@ def secondary(eng, torch):
         for _ in range(3):
             r = eng.scan(0, 3, 8)
             ts.append(eng.timing()["total_ms"])
-        out["scan_k3_2000"] = {"subsets": int(r["n_scored"]), "ms": min(ts), "subsets_per_s": r["n_scored"] / (min(ts) / 1e3),
-                               "best_W": float(r["W"][0]), "best": [int(x) for x in r["features"][0]],
-                               "popc_roofline_frac_of_nominal": r["n_scored"] / (min(ts) / 1e3) * 32 / POPC_PEAK_NOMINAL}
-    except Exception as e:      # noqa: BLE001
-        out["scan_k3_2000"] = {"error": str(e)}
+        return {"workload": "C2: exhaustive k<=3 scan, %d features x 1000 samples" % dense.shape[1], "subsets": int(r["n_scored"]),
+                "ms": min(ts), "subsets_per_s": r["n_scored"] / (min(ts) / 1e3), "best_W": float(r["W"][0]),
+                "best": [int(x) for x in r["features"][0]],
+                "popc_roofline_frac_of_nominal": r["n_scored"] / (min(ts) / 1e3) * 32 / POPC_PEAK_NOMINAL,
+                "note": "inclusion-exclusion over a pair table does fewer word operations than the per-subset popc count the roofline "
+                        "formula assumes (SURVEY 8d), so the fraction can exceed 1"}
+
+    def maxk_c0():
+        dense, w, module = workload()
+        eng.upload_matrix(bitpack.pack_rows(dense.T), dense.shape[0])
+        eng.upload_weights(w)
+        n = 1000
+        eng.null_pvalue(SEED, 0, 64, module[None, :], stat=SDX_STAT_MAXK)
+        r = eng.null_pvalue(SEED, 0, n, module[None, :], stat=SDX_STAT_MAXK)
+        t = eng.timing()
+        F = dense.shape[1]
+        per_null = F + F * (F - 1) // 2 + F * (F - 1) * (F - 2) // 6
+        return {"workload": "C0: 1000 nulls, each re-optimised over all |M|<=3 (the reference's per-null ILP statistic)",
+                "ms": t["total_ms"], "nulls_per_s": n / (t["total_ms"] / 1e3), "subsets_per_s": n * per_null / (t["total_ms"] / 1e3),
+                "n_ge": int(r["n_ge"][0]), "z_obs": float(r["z_obs"][0])}
+
+    def condperm_c4():
+        dense, _, _ = workload()
+        S, F = dense.shape
+        n_prof = 2000
+        w = synth.weights(S, n_prof, seed=11)
+        eng.upload_matrix(bitpack.pack_rows(dense.T), S)
+        eng.upload_weights(w)
+        rng = np.random.default_rng(1)
+        order = np.argsort(-dense.sum(0), kind="stable")[:40]
+        mods = np.sort(np.stack([rng.choice(order, 3, replace=False) for _ in range(n_prof)]), axis=1).astype(np.int32)
+        eng.condperm_batch(mods[:64], 1000, SEED, 0, np.arange(64, dtype=np.int32))
+        eng.condperm_batch(mods, 10000, SEED, 0, np.arange(n_prof, dtype=np.int32))
+        ms = eng.timing()["total_ms"]
+        res = eng.ranksum(mods, np.arange(n_prof, dtype=np.int32))
+        rms = eng.timing()["score_ms"]
+        return {"workload": "C4 slice: %d profiles x k=3 module x 10000 conditional permutations per feature; rank-sum per profile" % n_prof,
+                "condperm_ms": ms, "permuted_scores_per_s": n_prof * 3 * 10000 / (ms / 1e3),
+                "ranksum_ms": rms, "ranksum_profiles_per_s": n_prof / (rms / 1e3), "ranksum_p_median": float(np.median(res["p"]))}
+
+    guarded("scan_k3_2000", scan_c2)
+    guarded("maxk_c0", maxk_c0)
+    guarded("condperm_ranksum_c4", condperm_c4)
     return out
 
 
