@@ -38,38 +38,71 @@ struct NullIndexing {          // local null index (within a launch) -> global n
 // ---------------------------------------------------------------------------
 // plan: levels
 // ---------------------------------------------------------------------------
-__global__ void k_plan_levels(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T,
-                              uint16_t *__restrict__ lvl, int *__restrict__ depth,
-                              uint16_t *__restrict__ last_global) {
-    extern __shared__ uint16_t last_smem[];
-    const int tid = threadIdx.x;
-    const int n = blockIdx.x * blockDim.x + tid;
-    uint16_t *last;
-    size_t stride;
-    if (last_global) { last = last_global + (size_t)blockIdx.x * blockDim.x * R + tid; stride = blockDim.x; }
-    else { last = last_smem + tid; stride = blockDim.x; }
+// pairs of every trade of every null of the launch, one thread per (null, trade): pairs[n][t] = a | b << 16
+__global__ void k_plan_pairs(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T, int Tp,
+                             uint32_t *__restrict__ pairs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = (int)(i / Tp), t = (int)(i - (int64_t)n * Tp);
     if (n >= n_local) return;
-    const uint64_t null_id = ix.id(n);
-    for (int r = 0; r < R; ++r) last[(size_t)r * stride] = 0;
-    uint16_t *out = lvl + (size_t)n * T;
+    uint32_t a = 0, b = 0;
+    if (t < T) trade_pair(keys, ix.id(n), (uint32_t)t, (uint32_t)R, a, b);
+    pairs[i] = a | (b << 16);
+}
+
+// One THREAD per null walks its trades in order; pairs come in and levels go out through shared-memory
+// tiles of PL_TT trades x PL_NT nulls so that every global access is a coalesced row segment.
+#define PL_NT 64
+#define PL_TT 32
+__global__ void __launch_bounds__(PL_NT) k_plan_levels(int n_local, int R, int T, int Tp, const uint32_t *__restrict__ pairs,
+                                                       uint16_t *__restrict__ lvl, int *__restrict__ depth,
+                                                       uint16_t *__restrict__ last_global) {
+    extern __shared__ __align__(16) uint16_t plan_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n0 = blockIdx.x * PL_NT, n = n0 + tid;
+    // layout: tile_p[PL_NT][PL_TT + 1] u32 | tile_l[PL_NT][PL_TT + 2] u16 | last[R][PL_NT] u16 (unless in global memory)
+    uint32_t *tile_p = reinterpret_cast<uint32_t *>(plan_smem);
+    uint16_t *tile_l = reinterpret_cast<uint16_t *>(tile_p + PL_NT * (PL_TT + 1));
+    uint16_t *last = last_global ? last_global + (size_t)blockIdx.x * PL_NT * R + tid : tile_l + PL_NT * (PL_TT + 2) + tid;
+    for (int r = 0; r < R; ++r) last[(size_t)r * PL_NT] = 0;
     int d = 0;
-    for (int t = 0; t < T; ++t) {
-        uint32_t a, b;
-        trade_pair(keys, null_id, (uint32_t)t, (uint32_t)R, a, b);
-        int la = last[(size_t)a * stride], lb = last[(size_t)b * stride];
-        int l = (la > lb ? la : lb) + 1;
-        last[(size_t)a * stride] = (uint16_t)l;
-        last[(size_t)b * stride] = (uint16_t)l;
-        out[t] = (uint16_t)l;
-        d = l > d ? l : d;
+    constexpr int PER = PL_NT / (PL_NT / 32);                      // null rows each warp loads per tile
+    uint32_t nx[PER];                                              // next tile, in flight while the current one is processed
+    auto fetch = [&](int t0) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int i = wid + q * (PL_NT / 32);
+            nx[q] = (n0 + i < n_local && t0 + lane < Tp) ? pairs[(size_t)(n0 + i) * Tp + t0 + lane] : 0u;      // coalesced 128-byte segments
+        }
+    };
+    fetch(0);
+    for (int t0 = 0; t0 < T; t0 += PL_TT) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER; ++q) tile_p[(wid + q * (PL_NT / 32)) * (PL_TT + 1) + lane] = nx[q];
+        __syncthreads();
+        if (t0 + PL_TT < T) fetch(t0 + PL_TT);
+        const int cnt = T - t0 < PL_TT ? T - t0 : PL_TT;
+        for (int c = 0; c < cnt; ++c) {
+            const uint32_t e = tile_p[tid * (PL_TT + 1) + c];
+            const uint32_t a = e & 0xffffu, b = e >> 16;
+            const int la = last[(size_t)a * PL_NT], lb = last[(size_t)b * PL_NT];
+            const int l = (la > lb ? la : lb) + 1;
+            last[(size_t)a * PL_NT] = (uint16_t)l;
+            last[(size_t)b * PL_NT] = (uint16_t)l;
+            tile_l[tid * (PL_TT + 2) + c] = (uint16_t)l;
+            d = l > d ? l : d;
+        }
+        __syncthreads();
+        for (int i = wid; i < PL_NT; i += PL_NT / 32)
+            if (n0 + i < n_local && t0 + lane < T) lvl[(size_t)(n0 + i) * T + t0 + lane] = tile_l[i * (PL_TT + 2) + lane];
     }
-    depth[n] = d;
+    if (n < n_local) depth[n] = d;
 }
 
 // ---------------------------------------------------------------------------
 // plan: counting sort by level (one warp per null)
 // ---------------------------------------------------------------------------
-#define SDX_HCAP 1024          // deepest level schedule the plan kernels sort; deeper nulls run in sequential order
+#define SDX_HCAP 1024          // upper bound of the deepest level schedule the plan kernels sort (see dcap below)
 #define SDX_NCLS 4             // trade size classes inside a level (largest first)
 
 // Row sizes never change (Curveball preserves them), so min(|a|, |b|) bounds the number of picks of a
@@ -82,33 +115,28 @@ __device__ __forceinline__ int trade_class(int sa, int sb) {
     return kb > 8 ? 1 : (kb > 3 ? 2 : 3);
 }
 
-__global__ void k_plan_sort(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T,
+__global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const uint32_t *__restrict__ pairs,
                             const uint16_t *__restrict__ lvl, const int *__restrict__ depth, const int *__restrict__ rowsize,
                             uint2 *__restrict__ plan, uint16_t *__restrict__ offs, int offs_stride) {
-    __shared__ uint32_t hist_smem[2][SDX_HCAP * SDX_NCLS + 2];
+    extern __shared__ uint32_t hist_smem[];        // per warp: dcap * SDX_NCLS + 2 bins
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n = blockIdx.x * (blockDim.x >> 5) + wid;
     if (n >= n_local) return;
     const int D = depth[n];
-    uint32_t *hist = hist_smem[wid];
+    uint32_t *hist = hist_smem + (size_t)wid * (dcap * SDX_NCLS + 2);
     const uint16_t *lv = lvl + (size_t)n * T;
     uint2 *out = plan + (size_t)n * T;
-    const uint64_t null_id = ix.id(n);
-    if (D >= SDX_HCAP) {        // very deep schedule: fall back to the sequential order (always valid)
-        for (int t = lane; t < T; t += 32) {
-            uint32_t a, b;
-            trade_pair(keys, null_id, (uint32_t)t, (uint32_t)R, a, b);
-            out[t] = make_uint2(a | (b << 16), (uint32_t)t);
-        }
+    const uint32_t *pr = pairs + (size_t)n * Tp;
+    if (D >= dcap) {            // very deep schedule: fall back to the sequential order (always valid)
+        for (int t = lane; t < T; t += 32) out[t] = make_uint2(pr[t], (uint32_t)t);
         return;                 // k_trade runs such a null one trade per level, in order
     }
     const int NB = D * SDX_NCLS;                       // bin = (level - 1) * NCLS + class
     for (int i = lane; i <= NB; i += 32) hist[i] = 0;
     __syncwarp();
     for (int t = lane; t < T; t += 32) {
-        uint32_t a, b;
-        trade_pair(keys, null_id, (uint32_t)t, (uint32_t)R, a, b);
-        atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[a], rowsize[b])], 1u);
+        const uint32_t e = pr[t];
+        atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16])], 1u);
     }
     __syncwarp();
     // exclusive scan of the bins -> start offsets
@@ -131,10 +159,9 @@ __global__ void k_plan_sort(const __grid_constant__ PhiloxKeys keys, NullIndexin
     if (lane == 0) of[D] = (uint16_t)T;
     __syncwarp();
     for (int t = lane; t < T; t += 32) {
-        uint32_t a, b;
-        trade_pair(keys, null_id, (uint32_t)t, (uint32_t)R, a, b);
-        uint32_t pos = atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[a], rowsize[b])], 1u);
-        out[pos] = make_uint2(a | (b << 16), (uint32_t)t);
+        const uint32_t e = pr[t];
+        uint32_t pos = atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16])], 1u);
+        out[pos] = make_uint2(e, (uint32_t)t);
     }
 }
 
@@ -162,6 +189,7 @@ struct TradeArgs {
     uint32_t *carry;                  // n_units x R x RS: chain state between launches (or null)
     const uint2 *plan;                // n_local x T
     const uint16_t *offs;             // n_local x offs_stride level offsets
+    int dcap;                         // schedules at least this deep run in sequential order
     const int *depth;                 // n_local
     int offs_stride;
     int n_units;                      // chain segments in this launch
@@ -178,10 +206,10 @@ static __device__ __noinline__ SetScore score_module_call(const uint32_t *rows, 
     return score_module(rows, RS, rows_are_samples, mod, k, w, mask, S, lane);
 }
 
-// LB selects the launch bounds: 0 = (512, 1), 1 = (128, 5), 2 = (256, 5), 3 = (256, 4) — the latter three bound the
+// LB selects the launch bounds: 0 = (512, 1), 1 = (128, 5), 2 = (256, 5), 3 = (256, 4), 4 = (192, 5), 5 = (256, 3) — all but 0 bound the
 // registers so that five CTAs (five nulls) stay resident per SM when the matrix fits five times in shared memory.
 template <int G, int V, bool SMEM, int LB>
-__global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : 256), LB == 0 ? 1 : (LB == 3 ? 4 : 5)) k_trade(const __grid_constant__ TradeArgs p) {
+__global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : (LB == 4 ? 192 : 256)), LB == 0 ? 1 : (LB == 3 ? 4 : (LB == 5 ? 3 : 5))) k_trade(const __grid_constant__ TradeArgs p) {
     extern __shared__ __align__(16) uint32_t smem_rows[];
     __shared__ unsigned int s_applied;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NW = blockDim.x >> 5;
@@ -213,7 +241,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : 256), LB == 0
                 const uint2 *pl = p.plan + (size_t)local * T;
                 const uint16_t *of = p.offs + (size_t)local * p.offs_stride;
                 int D = p.depth[local];
-                const bool seq = D >= SDX_HCAP;          // very deep schedule: one trade per level, in order
+                const bool seq = D >= p.dcap;            // very deep schedule: one trade per level, in order
                 if (seq) D = T;
                 // level l covers plan entries [OFF(l), OFF(l+1)); e2 = end of level l+1, fetched one level ahead
                 auto OFF = [&](int lv) -> int { return seq ? lv : (int)of[lv]; };
@@ -357,7 +385,7 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
         cfg->LB = per_sm >= 4 ? (cfg->threads <= 128 ? 1 : (cfg->threads <= 256 ? 2 : 0)) : 0;
         if (const char *e = getenv("SDX_TRADE_LB")) {
             const int lb = atoi(e);
-            if (lb == 0 || (lb == 1 && cfg->threads <= 128) || ((lb == 2 || lb == 3) && cfg->threads <= 256)) cfg->LB = lb;
+            if (lb == 0 || (lb == 1 && cfg->threads <= 128) || ((lb == 2 || lb == 3 || lb == 5) && cfg->threads <= 256) || (lb == 4 && cfg->threads <= 192)) cfg->LB = lb;
         }
         cfg->grid_cap = 1 << 30;
     } else {
@@ -377,7 +405,7 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
 template <int G, int V>
 static cudaError_t launch_trade(const TradeConfig &cfg, int grid, cudaStream_t st, const TradeArgs &args) {
     if (cfg.smem) {
-        auto kern = cfg.LB == 1 ? k_trade<G, V, true, 1> : (cfg.LB == 2 ? k_trade<G, V, true, 2> : (cfg.LB == 3 ? k_trade<G, V, true, 3> : k_trade<G, V, true, 0>));
+        auto kern = cfg.LB == 1 ? k_trade<G, V, true, 1> : (cfg.LB == 2 ? k_trade<G, V, true, 2> : (cfg.LB == 3 ? k_trade<G, V, true, 3> : (cfg.LB == 4 ? k_trade<G, V, true, 4> : (cfg.LB == 5 ? k_trade<G, V, true, 5> : k_trade<G, V, true, 0>))));
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;
         kern<<<grid, cfg.threads, cfg.smem_bytes, st>>>(args);
@@ -407,7 +435,7 @@ struct HostScore {               // optional fused scoring request
     double *z_obs_out = nullptr;        // host out, P (or null)
 };
 
-enum { SL_LVL = 0, SL_PLAN, SL_AUX, SL_MOD, SL_Z, SL_SCORES, SL_CARRY, SL_OUT, SL_APPLIED, SL_WORK, SL_OFFS = 12 };
+enum { SL_LVL = 0, SL_PLAN, SL_AUX, SL_MOD, SL_Z, SL_SCORES, SL_CARRY, SL_OUT, SL_APPLIED, SL_WORK, SL_OFFS = 12, SL_PAIRS = 13 };
 
 // The common driver behind sdx_curveball and sdx_null_pvalue (stat = fixed).
 int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
@@ -475,22 +503,32 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
         const int64_t n_local_max = chains_per_launch * seg_cap;
         const int Tn = (int)(T > 0 ? T : 1);
 
-        // level kernel geometry: last[] (R x threads u16) in shared memory when it fits
-        int lv_threads = 128;
+        // level kernel geometry: last[] (R x PL_NT u16) in shared memory when it fits, else in global memory
+        const int lv_threads = PL_NT;
         const size_t smem_cap = c->smem_optin > 4096 ? c->smem_optin - 2048 : 0;
-        while (lv_threads > 32 && (size_t)lv_threads * R * 2 > (lv_threads == 128 ? (size_t)100 * 1024 : smem_cap)) lv_threads >>= 1;
-        const bool last_in_smem = (size_t)lv_threads * R * 2 <= smem_cap;
-        const size_t lv_smem = last_in_smem ? (size_t)lv_threads * R * 2 : 0;
+        const size_t lv_tiles = sizeof(uint32_t) * PL_NT * (PL_TT + 1) + sizeof(uint16_t) * PL_NT * (PL_TT + 2);
+        const bool last_in_smem = lv_tiles + (size_t)PL_NT * R * 2 <= smem_cap;
+        const size_t lv_smem = lv_tiles + (last_in_smem ? (size_t)PL_NT * R * 2 : 0);
         if (lv_smem > 48 * 1024)
             SDX_CUDA(c, cudaFuncSetAttribute(k_plan_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem));
 
         void *p_lvl, *p_plan, *p_offs, *p_aux = nullptr, *p_carry = nullptr, *p_work = nullptr, *p_out = nullptr, *p_app = nullptr;
-        const int offs_stride = (int)(((T < SDX_HCAP ? T : SDX_HCAP) + 2 + 1) & ~1ll);
+        // Expected depth of the level schedule is a small multiple of the trades per row (2T/R; C0: 10 -> depth ~41).
+        // dcap bounds the histogram of k_plan_sort; a null whose schedule is deeper runs in sequential order.
+        int dcap = (int)(16 * T / R) + 64;
+        if (dcap < 128) dcap = 128;
+        if (dcap > SDX_HCAP) dcap = SDX_HCAP;
+        const int offs_stride = (int)(((T < dcap ? T : dcap) + 2 + 1) & ~1ll);
+        const size_t sort_smem_warp = sizeof(uint32_t) * ((size_t)dcap * SDX_NCLS + 2);
+        const int sort_warps = sort_smem_warp * 8 <= 40 * 1024 ? 8 : (sort_smem_warp * 4 <= 40 * 1024 ? 4 : 2);
         if ((rc = sdx_scratch(c, SL_OFFS, sizeof(uint16_t) * (size_t)n_local_max * offs_stride + 64, &p_offs))) return rc;
         const size_t lvl_bytes = ((sizeof(uint16_t) * (size_t)n_local_max * Tn + 15) / 16) * 16;
         if ((rc = sdx_scratch(c, SL_LVL, lvl_bytes + sizeof(int) * n_local_max + 64, &p_lvl))) return rc;
         int *d_depth = (int *)((char *)p_lvl + lvl_bytes);
         if ((rc = sdx_scratch(c, SL_PLAN, sizeof(uint2) * (size_t)n_local_max * Tn, &p_plan))) return rc;
+        void *p_pairs;
+        const int Tp = (Tn + 3) & ~3;                       // pairs row length: 16-byte aligned rows
+        if ((rc = sdx_scratch(c, SL_PAIRS, sizeof(uint32_t) * (size_t)n_local_max * Tp + 64, &p_pairs))) return rc;
         if (!last_in_smem) {
             const size_t nb = (size_t)ceil_div(n_local_max, lv_threads) * lv_threads;
             if ((rc = sdx_scratch(c, SL_AUX, sizeof(uint16_t) * nb * R, &p_aux))) return rc;
@@ -519,17 +557,20 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
                 const int n_local = (int)(nch * ix.seg_len);
                 cudaEventRecord(c->ev[2], c->stream);
                 if (T > 0) {
+                    k_plan_pairs<<<ceil_div((int64_t)n_local * Tp, 256), 256, 0, c->stream>>>(keys, ix, n_local, R, (int)T, Tp, (uint32_t *)p_pairs);
                     k_plan_levels<<<ceil_div(n_local, lv_threads), lv_threads, lv_smem, c->stream>>>(
-                        keys, ix, n_local, R, (int)T, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux);
-                    k_plan_sort<<<ceil_div(n_local, 2), 64, 0, c->stream>>>(keys, ix, n_local, R, (int)T, (const uint16_t *)p_lvl,
-                                                                          d_depth, c->d_rowsize, (uint2 *)p_plan, (uint16_t *)p_offs, offs_stride);
-                    timer.count(2);
+                        n_local, R, (int)T, Tp, (const uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux);
+                    k_plan_sort<<<ceil_div(n_local, sort_warps), sort_warps * 32, sort_smem_warp * sort_warps, c->stream>>>(
+                                                                          n_local, R, (int)T, Tp, dcap, (const uint32_t *)p_pairs,
+                                                                          (const uint16_t *)p_lvl, d_depth, c->d_rowsize, (uint2 *)p_plan,
+                                                                          (uint16_t *)p_offs, offs_stride);
+                    timer.count(3);
                 }
                 cudaEventRecord(c->ev[3], c->stream);
                 TradeArgs ta{};
                 ta.keys = keys; ta.ix = ix; ta.observed = c->d_trade_obs; ta.work = (uint32_t *)p_work;
                 ta.carry = (uint32_t *)p_carry; ta.plan = (const uint2 *)p_plan; ta.n_units = (int)nch;
-                ta.offs = (const uint16_t *)p_offs; ta.depth = d_depth; ta.offs_stride = offs_stride;
+                ta.offs = (const uint16_t *)p_offs; ta.depth = d_depth; ta.offs_stride = offs_stride; ta.dcap = dcap;
                 ta.R = R; ta.RS = RS; ta.T = (int)T; ta.wprL = c->wprL;
                 ta.save_carry = need_carry && sg + 1 < n_segs;
                 ta.out_rows = (uint32_t *)p_out; ta.applied = (unsigned long long *)p_app; ta.sc = sc;

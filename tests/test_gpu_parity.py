@@ -70,6 +70,10 @@ def _dense_cases():
         "long_rows": (rng.random((50, 3000)) < 0.05).astype(np.uint8),  # 94 words: G=32, V=4
         "c3_like": (rng.random((64, 5000)) < 0.01).astype(np.uint8),    # 157 words: G=32, V=5
         "max_rows": (rng.random((30, 8000)) < 0.02).astype(np.uint8),   # 250 words: G=32, V=8
+        # rows of exactly 2 / 4 / 8 128-bit words: the one-trade-per-thread path (sparse rows) next to the group path
+        "nv2": (rng.random((40, 250)) < 0.04).astype(np.uint8),
+        "nv4": np.concatenate([(rng.random((500, 26)) < 0.02), (rng.random((500, 4)) < 0.3)], axis=1).astype(np.uint8),
+        "nv8": np.concatenate([(rng.random((1000, 90)) < 0.01), (rng.random((1000, 10)) < 0.2)], axis=1).astype(np.uint8),
     }
     return out
 
@@ -117,6 +121,18 @@ def test_long_chain_crosses_segment_boundaries(eng):
     want2, _ = oracle.curveball_nulls(obs, 7, 250, 30, 5 * obs.shape[0], 600)
     got2, _ = eng.curveball(7, 250, 30, -1, 600)
     assert np.array_equal(got2, want2)
+
+
+def test_very_deep_schedule_runs_in_sequential_order(eng):
+    """3 rows: every trade shares a row with the previous one, so the level schedule is as deep as the trade
+    count; beyond the planner's depth cap the kernel runs the trades one by one."""
+    rng = np.random.default_rng(9)
+    dense = (rng.random((3, 64)) < 0.4).astype(np.uint8)
+    upload_dense(eng, dense)
+    obs = rows_of(dense)
+    want, want_ap = oracle.curveball_nulls(obs, 21, 0, 3, 1500, 1)
+    got, got_ap = eng.curveball(21, 0, 3, n_trades=1500, chain_len=1)
+    assert np.array_equal(got, want) and np.array_equal(got_ap, want_ap)
 
 
 def test_results_do_not_depend_on_batching(eng):

@@ -1,7 +1,8 @@
 #!/bin/bash
+: ${SDX_TUNE_CFGS:="4,4,1 4,8,5 4,6,4 8,8,2 8,8,5 8,6,4"}
 # sweep of the k_trade launch configuration on the C1 workload (benchmarks only)
-for cfg in "8 4 1" "4 4 1" "4 8 2" "4 8 3" "4 6 3" "2 4 1" "2 8 3" "8 8 3"; do
-  set -- $cfg
+for cfg in ${SDX_TUNE_CFGS}; do
+  set -- ${cfg//,/ }
   v=$(SDX_TRADE_G=$1 SDX_TRADE_WARPS=$2 SDX_TRADE_LB=$3 python bench.py --steps 3 --warmup 2 --no-extra --nulls 100000 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
