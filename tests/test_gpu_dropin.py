@@ -239,3 +239,65 @@ def test_dist_functions_single_rank():
         assert np.array_equal(cp[0], eng.condperm_batch(modules, 100, 1, 0, np.array([0, 1], dtype=np.int32))[0])
         rs = dist.ranksum(eng, modules, np.array([0, 1], dtype=np.int32))
         assert np.array_equal(rs["twice_rank_sum"], eng.ranksum(modules, np.array([0, 1], dtype=np.int32))["twice_rank_sum"])
+
+
+# ---------------------------------------------------------------- batched screen (many profiles, one matrix, shared nulls)
+def test_batched_screen_equals_per_profile_pipeline(tmp_path):
+    from superdendrix_b200 import screen as scr
+    dense, samples, features = synth.feature_matrix(150, 40, seed=12)
+    S, F = dense.shape
+    P = 6
+    w = synth.weights(S, P, seed=4)
+    mask = np.ones((P, S), bool)
+    mask[2, ::9] = False
+    w[5] = -np.abs(w[5]) - 0.1                    # nothing to find: empty module
+    rows = bitpack.pack_rows(dense.T)
+    cond_it, n_nulls, seed = 300, 40, 31
+    with Engine(0) as eng:
+        res = scr.screen(eng, rows, S, w, mask, k=3, cond_it=cond_it, n_nulls=n_nulls, seed=seed, stat="fixed")
+    obs = rows_of(dense)
+    ras = F >= S
+    nulls, _ = oracle.curveball_nulls(obs, seed, 0, n_nulls, 5 * obs.shape[0], 1)
+    for p in range(P):
+        wm = np.where(mask[p], w[p], 0.0)
+        mk = bitpack.pack_mask(np.nonzero(mask[p])[0], S)
+        idx = np.nonzero(mask[p])[0]
+        tol = 1e-9 * np.abs(wm).sum()
+        oW, oF, _, _ = oracle.scan(rows, S, wm, 3, 1, mask=mk)
+        if oW[0] <= 0:
+            assert (res["modules"][p] == -1).all() and np.isnan(res["p_value"][p])
+            continue
+        assert abs(res["z"][p] - oW[0]) <= tol
+        mod = [int(f) for f in oF[0] if f >= 0]
+        rnd = 0
+        while len(mod) > 1:                        # src/superdendrix.py:151-158 with the oracle's counts
+            counts, _ = oracle.condperm(rows, S, mod, wm, idx, seed, 16 * rnd, cond_it)
+            worst, wc = -1, 0
+            for i, c in enumerate(counts):
+                if c > wc:
+                    worst, wc = i, int(c)
+            if worst < 0 or wc / float(cond_it) <= 1.0 / cond_it:
+                break
+            mod.pop(worst)
+            rnd += 1
+        assert [int(f) for f in res["modules"][p] if f >= 0] == mod
+        zP, cov, _, _ = oracle.score_set(rows, S, mod, wm, mk)
+        assert abs(res["zP"][p] - zP) <= tol and res["coverage"][p] == cov
+        ge = 0
+        for m in nulls:
+            fr = bitpack.pack_rows(bitpack.unpack_rows(m, max(S, F)).T) if ras else m
+            ge += oracle.score_set(fr, S, mod, wm, mk)[0] >= res["zP"][p]
+        assert res["n_ge"][p] == ge and res["p_value"][p] == ge / n_nulls
+        union = dense[:, mod].any(axis=1)
+        zz, pp, _, _ = oracle.ranksum(wm, idx, bitpack.pack_mask(np.nonzero(union)[0], S))
+        assert abs(res["ranksum_z"][p] - zz) <= 1e-12 * max(1, abs(zz)) and abs(res["ranksum_p"][p] - pp) <= 1e-12 + 1e-10 * pp
+    # the CLI writes one reference-format row per profile
+    mut, prof, out = tmp_path / "f.tsv", tmp_path / "p.tsv", tmp_path / "screen.tsv"
+    synth.write_features_tsv(str(mut), dense, samples, features)
+    synth.write_profile_tsv(str(prof), samples, np.where(mask, w, np.nan), ["P%d" % i for i in range(P)])
+    assert scr.main(["-m", str(mut), "-T", str(prof), "-k", "3", "-cp", "100", "-p", "20", "-o", str(out), "-d", "positive"]) == 0
+    lines = open(out).read().splitlines()
+    assert lines[0] + "\n" == scr.HEADER and len(lines) == P + 1
+    assert lines[-1].split("\t")[1:4] == ["nan", "nan", "nan"] and lines[-1].split("\t")[6] == "na"
+    f0 = lines[1].split("\t")
+    assert f0[0] == "P0" and f0[7] == "positive" and int(f0[8]) == len(f0[1].split(","))
