@@ -389,7 +389,28 @@ def secondary(eng, torch):
                 "condperm_ms": ms, "permuted_scores_per_s": n_prof * 3 * 10000 / (ms / 1e3),
                 "ranksum_ms": rms, "ranksum_profiles_per_s": n_prof / (rms / 1e3), "ranksum_p_median": float(np.median(res["p"]))}
 
+    def nulls_c3():
+        dense, _, _ = synth.feature_matrix(1000, 5000, seed=20)
+        S, F = dense.shape
+        n_prof = 500
+        w = synth.weights(S, n_prof, seed=5)
+        eng.upload_matrix(bitpack.pack_rows(dense.T), S)
+        eng.upload_weights(w)
+        rng = np.random.default_rng(2)
+        order = np.argsort(-dense.sum(0), kind="stable")[:60]
+        mods = np.sort(np.stack([rng.choice(order, 3, replace=False) for _ in range(n_prof)]), axis=1).astype(np.int32)
+        eng.null_pvalue(SEED, 0, 64, mods)
+        n = 1024
+        r = eng.null_pvalue(SEED, 0, n, mods)
+        t = eng.timing()
+        R, L, wpr, ras = eng.trade_shape()
+        return {"workload": "C3 slice: %d x %d matrix (rows = samples, %d-bit rows, %d trades per null, matrix in L2/global), "
+                            "%d nulls each scored for %d profiles" % (S, F, L, 5 * R, n, n_prof),
+                "ms": t["total_ms"], "trade_ms": t["trade_ms"], "plan_ms": t["plan_ms"], "nulls_per_s": n / (t["total_ms"] / 1e3),
+                "profile_null_scores_per_s": n * n_prof / (t["total_ms"] / 1e3), "n_ge_mean": float(np.mean(r["n_ge"]))}
+
     guarded("scan_k3_2000", scan_c2)
+    guarded("nulls_c3", nulls_c3)
     guarded("maxk_c0", maxk_c0)
     guarded("condperm_ranksum_c4", condperm_c4)
     return out

@@ -292,6 +292,8 @@ template <bool LISTS>
 __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ ScanArgs pa) {
     __shared__ uint32_t sI[SCAN_MAXW];
     __shared__ unsigned s_item;
+    __shared__ double s_sgh[SCAN_GT][SCAN_HB];
+    __shared__ unsigned char s_fl[SCAN_HB];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int F = pa.F, Fp = pa.Fp;
     WarpTop top;
@@ -332,21 +334,41 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
             }
         }
 
+        // per-h terms that do not depend on l, once per item: s_g + s_h + T_gh for the tile's 4 g, and which of them
+        // have a non-empty g∩h∩{w>0} (bits 0-3) plus the number of valid g (bits 4-6)
+        __syncthreads();
+        if (tid < SCAN_HB) {
+            const int h = hb * SCAN_HB + tid;
+            unsigned fl = 0;
+            if (h >= hlo && h < hhi) {
+                const double sh = p.s1[h];
+                int nv = 0;
+#pragma unroll
+                for (int gi = 0; gi < SCAN_GT; ++gi) {
+                    const int g = g0 + gi;
+                    const bool v = g < h && g >= p.g_lo && g < p.g_hi;
+                    const double tgh = v ? p.T[(size_t)g * Fp + h] : 0.0;
+                    s_sgh[gi][tid] = v ? (p.s1[g] + sh) + tgh : -INFINITY;
+                    fl |= (v && tgh != 0.0) ? (1u << gi) : 0u;
+                    nv += v;
+                }
+                fl |= (unsigned)nv << 4;
+            }
+            s_fl[tid] = (unsigned char)fl;
+        }
+        __syncthreads();
+
         for (int h = hlo; h < hhi; ++h) {
             double sgh[SCAN_GT];
             bool slow[SCAN_GT];
-            bool any_slow = false;
-            int nvg = 0;
-            const double sh = p.s1[h];
+            const int hi_ = h - hb * SCAN_HB;
+            const unsigned fl = s_fl[hi_];
+            const bool any_slow = (fl & 15u) != 0;
+            const int nvg = (int)(fl >> 4);
 #pragma unroll
             for (int gi = 0; gi < SCAN_GT; ++gi) {
-                const int g = g0 + gi;
-                const bool v = g < h && g >= p.g_lo && g < p.g_hi;
-                const double tgh = v ? p.T[(size_t)g * Fp + h] : 0.0;
-                sgh[gi] = v ? (p.s1[g] + sh) + tgh : -INFINITY;
-                slow[gi] = v && tgh != 0.0;
-                any_slow |= slow[gi];
-                nvg += v;
+                sgh[gi] = s_sgh[gi][hi_];
+                slow[gi] = (fl >> gi) & 1u;
             }
             const double *Th = p.T + (size_t)h * Fp;
             double t[SCAN_NJ];
@@ -360,6 +382,7 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
             if (!any_slow) {
 #pragma unroll
                 for (int j = 0; j < SCAN_NJ; ++j) {
+                    if (l0 + (j + 1) * SCAN_NT - 1 <= h) continue;          // CTA-uniform: every l of this slice is <= h
                     double W[SCAN_GT];
                     bool cand = false;
 #pragma unroll
@@ -406,6 +429,7 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
                     }
 #pragma unroll
                     for (int j = 0; j < SCAN_NJ; ++j) {
+                        if (l0 + (j + 1) * SCAN_NT - 1 <= h) continue;      // CTA-uniform
                         const double W = ((sgh[gi] + t[j]) + c[gi][j]) + 2.0 * p3[j];
                         if (LISTS) {
                             const bool cand = W >= top.gate;
