@@ -531,3 +531,38 @@ def test_maxk_statistic_dominates_fixed_statistic(eng):
     assert (mx["null_scores"] >= fx["null_scores"] - 1e-9 * np.abs(w).sum()).all()
     best = eng.scan(0, 3, 1)["W"][0]
     assert abs(mx["z_obs"][0] - max(best, 0.0)) <= 1e-9 * np.abs(w).sum()
+
+
+# ---------------------------------------------------------------- randomized shapes (property-style sweep)
+@pytest.mark.parametrize("case", range(16))
+def test_curveball_random_shapes_and_densities_match_oracle(eng, case):
+    """Random shapes around the layout boundaries (row lengths of 1..9 128-bit words, both orientations,
+    very sparse to dense, few to many rows): nulls, applied counts and margins equal the oracle's."""
+    rng = np.random.default_rng(1000 + case)
+    L = int(rng.choice([1, 31, 32, 33, 96, 127, 128, 129, 255, 256, 300, 511, 640, 897, 1024, 1100]))
+    R = int(rng.integers(2, 70))
+    density = float(rng.choice([0.01, 0.05, 0.2, 0.5, 0.9]))
+    rows_dense = (rng.random((R, L)) < density).astype(np.uint8)
+    if L >= R:
+        rows_dense[:, rng.integers(0, L)] = 1                      # a full column and an empty row are legal inputs
+        rows_dense[rng.integers(0, R)] = 0
+    dense = rows_dense if case % 2 == 0 and L >= R else rows_dense.T      # S x F with samples or features as trade rows
+    if dense.shape[1] < dense.shape[0] and min(dense.shape) < 2:
+        dense = dense.T
+    S, F = dense.shape
+    if min(S, F) < 2:
+        pytest.skip("Curveball needs two rows")
+    upload_dense(eng, dense)
+    obs = rows_of(dense)
+    Rr, Lr, wpr, ras = eng.trade_shape()
+    assert obs.shape == (Rr, wpr)
+    n, T = 3, int(rng.integers(1, 6 * Rr + 1))
+    seed = int(rng.integers(0, 2 ** 62))
+    null0 = int(rng.integers(0, 2 ** 40))
+    want, want_ap = oracle.curveball_nulls(obs, seed, null0, n, T, 2)
+    got, got_ap = eng.curveball(seed, null0, n, n_trades=T, chain_len=2)
+    assert np.array_equal(got_ap, want_ap)
+    assert np.array_equal(got, want)
+    for m in got:
+        assert np.array_equal(bitpack.popcount_rows(m), bitpack.popcount_rows(obs))
+        assert np.array_equal(bitpack.unpack_rows(m, Lr).sum(0), bitpack.unpack_rows(obs, Lr).sum(0))
