@@ -302,7 +302,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_trade", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_NULL * (n / -(-n // 32768)),
-                         "traffic_source": "ncu --set full capture profiles/r01_k_trade_c.ncu-rep: dram read+write per null x nulls per launch",
+                         "traffic_source": "ncu --set full capture profiles/r01_k_trade_d.ncu-rep: dram read+write per null x nulls per launch",
                          "peak_source": peaks_src,
                          "bytes_per_null": bytes_per_null, "avg_launch_ms": avg_launch_ms,
                          "kernel_share_of_step": trade_ms / ms, "plan_share_of_step": plan_ms / ms,
