@@ -176,6 +176,22 @@ int sdx_condperm_batch(sdx_ctx *ctx, const int32_t *profile_of_job, const int32_
 int sdx_ranksum(sdx_ctx *ctx, const int32_t *profile_of_job, const int32_t *modules, int64_t n_jobs,
                 int k, double *z, double *p, int64_t *twice_rank_sum, int32_t *n1);
 
+/* ---- host-side format path (no GPU, no ctx): the sample -> events TSV files ---------------------------
+ * The files that carry null matrices from the reference's generator to its driver
+ * (writer: src/generate_null_matrices.py:75-86; reader: src/i_o.py:18-88 as called at src/superdendrix.py:186).
+ * feature_rows: n_nulls x n_features x words_per_row packed feature rows over samples.  File i is
+ * <path_prefix><first_index + i>.tsv.  n_threads <= 0 uses all host threads.  Errors: sdx_io_last_error(). */
+int sdx_write_nulls_tsv(const uint32_t *feature_rows, int64_t n_nulls, int n_features, int n_samples,
+                        int words_per_row, const char *const *sample_names, const char *const *event_names,
+                        const char *path_prefix, int64_t first_index, int n_threads);
+/* Reads files written in that format into packed feature rows over the GIVEN sample and event tables
+ * (samples not in the table are skipped like the whitelist of src/i_o.py:57; events not in the table are
+ * counted in n_unknown_events and skipped like the gene whitelist of :58). */
+int sdx_read_nulls_tsv(const char *path_prefix, int64_t first_index, int64_t n_nulls, int n_features, int n_samples,
+                       int words_per_row, const char *const *sample_names, const char *const *event_names,
+                       uint32_t *feature_rows, int64_t *n_unknown_events, int n_threads);
+const char *sdx_io_last_error(void);
+
 /* Self-test hooks used by tests/ (known-answer vectors of the random streams). */
 int sdx_test_philox(sdx_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, int n, uint32_t *out4);
 int sdx_test_trade_pairs(sdx_ctx *ctx, uint64_t seed, uint64_t null_id, int n_trades, int n_rows,

@@ -67,6 +67,11 @@ PROTOTYPES = {
     "sdx_condperm": (C.c_int, [_ctx, C.c_int, _i32p, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _i64p, _f64p]),
     "sdx_condperm_batch": (C.c_int, [_ctx, _i32p, _i32p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _i64p, _f64p]),
     "sdx_ranksum": (C.c_int, [_ctx, _i32p, _i32p, C.c_int64, C.c_int, _f64p, _f64p, _i64p, _i32p]),
+    "sdx_write_nulls_tsv": (C.c_int, [_u32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
+                                      C.c_char_p, C.c_int64, C.c_int]),
+    "sdx_read_nulls_tsv": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_char_p),
+                                     C.POINTER(C.c_char_p), _u32p, _i64p, C.c_int]),
+    "sdx_io_last_error": (C.c_char_p, []),
     "sdx_test_philox": (C.c_int, [_ctx, _u32p, _u32p, C.c_int, _u32p]),
     "sdx_test_trade_pairs": (C.c_int, [_ctx, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _i32p, _i32p]),
 }

@@ -19,6 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libsdx.so")
 UNITS = ["sdx_api", "sdx_score", "sdx_curveball", "sdx_scan", "sdx_stats"]
+HOST_UNITS = ["sdx_io"]          # plain C++ (the host-side format path), compiled by the host compiler through nvcc
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wno-format-truncation", "-Xptxas", "-v"]
 
@@ -50,12 +51,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed on %s.cu:\n%s" % (u, r.stdout + r.stderr))
         return r.stderr
 
-    with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+    def compile_host_unit(u):
+        cmd = [nvcc, "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-pthread", "-c", os.path.join(CSRC, u + ".cpp"), "-o", os.path.join(OBJ, u + ".o")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("host compile failed on %s.cpp:\n%s" % (u, r.stdout + r.stderr))
+        return r.stderr
+
+    with ThreadPoolExecutor(max_workers=len(UNITS) + len(HOST_UNITS)) as ex:
+        host_logs = [ex.submit(compile_host_unit, u) for u in HOST_UNITS]
         logs = list(ex.map(compile_unit, UNITS))
+        logs += [h.result() for h in host_logs]
     if verbose:
         sys.stderr.write("".join(logs))
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", SO,
-           *[os.path.join(OBJ, u + ".o") for u in UNITS]]
+           *[os.path.join(OBJ, u + ".o") for u in UNITS + HOST_UNITS], "-Xcompiler", "-pthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link of libsdx.so failed:\n" + r.stdout + r.stderr)

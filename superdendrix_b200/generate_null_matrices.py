@@ -26,7 +26,7 @@ import numpy as np
 
 from . import bitpack
 from .engine import Engine
-from .i_o import dense_matrix, getLogger, load_mutation_data, write_sample_events
+from .i_o import dense_matrix, getLogger, load_mutation_data, write_nulls_tsv
 
 
 def get_parser():
@@ -52,8 +52,8 @@ def get_parser():
     return parser
 
 
-def generate(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None):
-    """Yields (global null index, S x F uint8 matrix) for n_nulls nulls of ``dense`` (S x F)."""
+def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None):
+    """Yields (first global null index, packed feature rows (n, F, ceil(S/32)) uint32) per device batch."""
     S, F = dense.shape
     eng = engine or Engine(device)
     try:
@@ -65,13 +65,23 @@ def generate(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=102
         while done < n_nulls:
             n = min(batch, n_nulls - done)
             rows, _ = eng.curveball(seed, prefix + done, n, n_trades=-1, chain_len=chain_len, want_applied=False)
-            bits = bitpack.unpack_rows(rows, L)                       # (n, R, L)
-            for i in range(n):
-                yield prefix + done + i, (bits[i] if rows_are_samples else bits[i].T)
+            if rows_are_samples:                      # trade rows are samples: transpose to feature rows on the host
+                bits = bitpack.unpack_rows(rows, L)   # (n, S, F)
+                rows = np.stack([bitpack.pack_rows(b.T) for b in bits])
+            yield prefix + done, rows
             done += n
     finally:
         if engine is None:
             eng.close()
+
+
+def generate(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None):
+    """Yields (global null index, S x F uint8 matrix) for n_nulls nulls of ``dense`` (S x F)."""
+    S = dense.shape[0]
+    for first, rows in generate_packed(dense, n_nulls, seed, prefix, mode, device, batch, engine):
+        bits = bitpack.unpack_rows(rows, S)           # (n, F, S)
+        for i in range(len(rows)):
+            yield first + i, bits[i].T
 
 
 def main(argv=None):
@@ -89,14 +99,15 @@ def main(argv=None):
     dense = dense_matrix(genes, samples, samples_to_genes)
     print(len(samples), len(genes))
     packed, ids = [], []
-    for idx, null in generate(dense, max(args.p_val_it, 0), args.random_seed, args.prefix, args.mode, args.device, args.batch):
+    for first, rows in generate_packed(dense, max(args.p_val_it, 0), args.random_seed, args.prefix, args.mode, args.device, args.batch):
         if not args.no_tsv:
-            write_sample_events("%s%d.tsv" % (args.output_file, idx), samples, genes, null)
+            write_nulls_tsv(args.output_file, first, rows, samples, genes)      # multi-threaded C++ writer, reference format
         if args.packed:
-            packed.append(bitpack.pack_rows(null.T))
-            ids.append(idx)
+            packed.append(rows)
+            ids.extend(range(first, first + len(rows)))
     if args.packed:
-        np.savez_compressed(args.packed, feature_rows=np.array(packed, dtype=np.uint32), null_index=np.array(ids, dtype=np.int64),
+        rows_all = np.concatenate(packed) if packed else np.zeros((0, len(genes), bitpack.words_for(len(samples))), dtype=np.uint32)
+        np.savez_compressed(args.packed, feature_rows=rows_all, null_index=np.array(ids, dtype=np.int64),
                             genes=np.array(genes), samples=np.array(samples))
     print(str((time.time() - t0) / 60), "min")
     return 0

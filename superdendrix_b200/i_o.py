@@ -163,3 +163,47 @@ def write_sample_events(path, samples, genes, dense) -> None:
     with open(path, "w") as fh:
         fh.write("#Samples\tEvents\n")
         fh.write("".join("\t".join([s, *p]) + "\n" for s, p in zip(samples, parts)))
+
+
+# ---------------------------------------------------------------------------
+# native (C++) writer / reader of the same files: the host-side format path of libsdx.so
+# ---------------------------------------------------------------------------
+def _names(seq):
+    import ctypes as C
+    arr = (C.c_char_p * len(seq))()
+    arr[:] = [str(x).encode() for x in seq]
+    return arr
+
+
+def write_nulls_tsv(path_prefix, first_index, feature_rows, samples, genes, n_threads=0) -> None:
+    """feature_rows: (n, F, ceil(S/32)) uint32.  Writes ``<path_prefix><first_index + i>.tsv`` for every null, in the
+    reference's format (src/generate_null_matrices.py:82-86), with the library's multi-threaded writer."""
+    import ctypes as C
+
+    from . import _capi
+    rows = np.ascontiguousarray(feature_rows, dtype=np.uint32)
+    if rows.ndim == 2:
+        rows = rows[None]
+    n, F, wpr = rows.shape
+    lib = _capi.load()
+    rc = lib.sdx_write_nulls_tsv(rows.ctypes.data_as(C.POINTER(C.c_uint32)), n, F, len(samples), wpr, _names(samples), _names(genes),
+                                 str(path_prefix).encode(), int(first_index), int(n_threads))
+    if rc != 0:
+        raise _capi.SdxError(rc, (lib.sdx_io_last_error() or b"").decode())
+
+
+def read_nulls_tsv(path_prefix, first_index, n_nulls, samples, genes, n_threads=0):
+    """Reads ``<path_prefix><first_index + i>.tsv`` into packed feature rows (n, F, ceil(S/32)) over the given sample and
+    event tables; returns (rows, number of events that were not in ``genes``)."""
+    import ctypes as C
+
+    from . import _capi
+    F, S = len(genes), len(samples)
+    rows = np.zeros((int(n_nulls), F, bitpack.words_for(S)), dtype=np.uint32)
+    unknown = C.c_int64(0)
+    lib = _capi.load()
+    rc = lib.sdx_read_nulls_tsv(str(path_prefix).encode(), int(first_index), int(n_nulls), F, S, rows.shape[2], _names(samples),
+                                _names(genes), rows.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(unknown), int(n_threads))
+    if rc != 0:
+        raise _capi.SdxError(rc, (lib.sdx_io_last_error() or b"").decode())
+    return rows, unknown.value

@@ -35,7 +35,7 @@ import numpy as np
 
 from . import bitpack
 from .engine import SDX_STAT_FIXED, SDX_STAT_MAXK, Engine
-from .i_o import getLogger, load_events, load_mutation_data, pack_features
+from .i_o import getLogger, load_events, load_mutation_data, pack_features, read_nulls_tsv
 
 _state = {"engine": None, "device": 0, "seed": 1764, "perm_calls": 0}
 
@@ -228,21 +228,23 @@ def null_loop(genes, samples, profile, events_to_samples, module, zP, args, logg
         chain = n if args.mode == "chained" else 1
         res = eng.null_pvalue(args.random_seed, 0, n, mod, chain_len=chain, stat=stat, z_obs=np.array([zP]), want_scores=True)
         return int(res["n_ge"][0]), n, res["null_scores"][0]
+    # files: <-nm><i>.tsv, restricted to the profiled samples as src/superdendrix.py:186 does.  Read in batches by the
+    # library's multi-threaded parser straight into packed rows over this run's sample / event tables (events with no
+    # carrier among the profiled samples are all-zero rows, which is what "missing from p_genes" means for W).
     scores = []
     no_better = 0
-    for i in range(n):
-        pm, pN, p_genes, p_samples, p_e2s, p_s2g = load_mutation_data(
-            "%s%d.tsv" % (args.null_matrices, i), profile.keys(), args.gene_file, args.mutations_only, args.min_freq, args.max_freq)
-        eng.upload_matrix(pack_features(p_genes, p_samples, p_e2s), len(p_samples))
-        eng.upload_weights(np.array([profile[s] for s in p_samples], dtype=np.float64))
-        if stat == SDX_STAT_MAXK:
-            p_z = max(float(eng.scan(0, k, 1)["W"][0]), 0.0)
-        else:
-            pg = {g: j for j, g in enumerate(p_genes)}
-            feats = [pg[g] for g in module if g in pg]
-            p_z = float(eng.score_sets(np.array([feats + [-1] * (max(k, 1) - len(feats))], dtype=np.int32))["W"][0]) if feats else 0.0
-        scores.append(p_z)
-        no_better += p_z >= zP
+    mod_idx = [gidx[g] for g in module]
+    for i0 in range(0, n, 256):
+        rows, _ = read_nulls_tsv(args.null_matrices, i0, min(256, n - i0), samples, genes)
+        for r in rows:
+            eng.upload_matrix(r, len(samples))
+            eng.upload_weights(w_vec)
+            if stat == SDX_STAT_MAXK:
+                p_z = max(float(eng.scan(0, k, 1)["W"][0]), 0.0)
+            else:
+                p_z = float(eng.score_sets(np.array([mod_idx + [-1] * (max(k, 1) - k)], dtype=np.int32))["W"][0])
+            scores.append(p_z)
+            no_better += p_z >= zP
     return int(no_better), n, np.array(scores)
 
 

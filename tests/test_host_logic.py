@@ -129,3 +129,42 @@ def test_synthetic_shapes_are_stable():
     assert dense.sum() == synth.feature_matrix(770, 400)[0].sum()
     w = synth.weights(770, 2)
     assert w.shape == (2, 770) and (w == 0).mean() > 0.005 and np.abs(w).max() <= 20
+
+
+def test_native_tsv_writer_and_reader_match_the_python_path(tmp_path):
+    """The C++ writer emits byte-identical files to the Python writer (reference format) and the C++ reader
+    reproduces the packed rows, applies the sample whitelist and skips unknown events like the gene whitelist."""
+    rng = np.random.default_rng(3)
+    S, F, n = 70, 45, 9
+    samples = ["ACH-%06d" % i for i in range(S)]
+    genes = ["G%d_%s_MUT" % (j, "AIO"[j % 3]) for j in range(F)]
+    dense = (rng.random((n, S, F)) < 0.08).astype(np.uint8)
+    dense[0, 5] = 0                                              # a sample without events: bare name line
+    rows = np.stack([bitpack.pack_rows(d.T) for d in dense])
+    out = tmp_path / "nulls"
+    out.mkdir()
+    i_o.write_nulls_tsv(str(out) + "/", 100, rows, samples, genes, n_threads=3)
+    for i in range(n):
+        ref = tmp_path / ("py%d.tsv" % i)
+        i_o.write_sample_events(str(ref), samples, genes, dense[i])
+        assert open(out / ("%d.tsv" % (100 + i))).read() == open(ref).read()
+    back, unknown = i_o.read_nulls_tsv(str(out) + "/", 100, n, samples, genes)
+    assert unknown == 0 and np.array_equal(back, rows)
+    # whitelist semantics: fewer samples (in another order) and fewer events
+    sub_s = [samples[i] for i in (9, 3, 50, 5)]
+    sub_g = genes[::2]
+    back, unknown = i_o.read_nulls_tsv(str(out) + "/", 100, n, sub_s, sub_g)
+    for i in range(n):
+        want = dense[i][[9, 3, 50, 5]][:, ::2]
+        assert np.array_equal(bitpack.unpack_rows(back[i], len(sub_s)), want.T)
+    assert unknown == int(sum(d[[9, 3, 50, 5]][:, 1::2].sum() for d in dense))
+    # files written by the reference generator parse to the same matrices as the Python loader
+    gdir = os.path.join(GOLDEN, "generator")
+    _, _, g, s, _, p2g = i_o.load_mutation_data(os.path.join(gdir, "features.tsv"))
+    rows, unknown = i_o.read_nulls_tsv(os.path.join(gdir, "ref_null_"), 5, 3, s, g)
+    for i in range(3):
+        pp2g = i_o.load_mutation_data(os.path.join(gdir, "ref_null_%d.tsv" % (5 + i)))[5]
+        assert np.array_equal(bitpack.unpack_rows(rows[i], len(s)).T, i_o.dense_matrix(g, s, pp2g))
+    assert unknown == 0
+    with pytest.raises(Exception):
+        i_o.read_nulls_tsv(str(out) + "/", 0, 1, samples, genes)        # missing file: error, not silence
