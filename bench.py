@@ -409,7 +409,32 @@ def secondary(eng, torch):
                 "ms": t["total_ms"], "trade_ms": t["trade_ms"], "plan_ms": t["plan_ms"], "nulls_per_s": n / (t["total_ms"] / 1e3),
                 "profile_null_scores_per_s": n * n_prof / (t["total_ms"] / 1e3), "n_ge_mean": float(np.mean(r["n_ge"]))}
 
+    def files_c0():
+        import shutil
+        import tempfile
+
+        from superdendrix_b200 import generate_null_matrices as gnm, i_o
+        dense, samples, features = synth.feature_matrix(770, 400, seed=20)
+        d = tempfile.mkdtemp(prefix="sdx_bench_")
+        try:
+            mut = os.path.join(d, "features.tsv")
+            synth.write_features_tsv(mut, dense, samples, features)
+            os.mkdir(os.path.join(d, "rand_mat"))
+            n = 2000
+            t0 = time.perf_counter()
+            gnm.main(["-m", mut, "-p", str(n), "-o", os.path.join(d, "rand_mat") + "/", "--mode", "restart", "-v", "40"])
+            t_gen = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            rows, _ = i_o.read_nulls_tsv(os.path.join(d, "rand_mat") + "/", 0, n, samples, features)
+            t_read = time.perf_counter() - t0
+            ok = bool((bitpack.popcount_rows(rows[0]) == dense.sum(0)).all())
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+        return {"workload": "drop-in generator CLI: %d null TSV files of the C0 matrix written in the reference's format, then parsed back" % n,
+                "generate_and_write_s": t_gen, "files_per_s": n / t_gen, "parse_s": t_read, "parsed_files_per_s": n / t_read, "margins_ok": ok}
+
     guarded("scan_k3_2000", scan_c2)
+    guarded("generator_files_c0", files_c0)
     guarded("nulls_c3", nulls_c3)
     guarded("maxk_c0", maxk_c0)
     guarded("condperm_ranksum_c4", condperm_c4)

@@ -23,7 +23,21 @@ from . import dist
 from .engine import SDX_STAT_FIXED, SDX_STAT_MAXK, Engine
 from .i_o import load_mutation_data, load_profiles, pack_features
 
-HEADER = "profile\tfeatures\t#samples\tscores\tW(M)(%)\tcoverage\tP_value\tdirection\tfeature_count\tranksum_z\tranksum_p\n"
+HEADER = "profile\tfeatures\t#samples\tscores\tW(M)(%)\tcoverage\tP_value\tdirection\tfeature_count\tranksum_z\tranksum_p\tFDR\n"
+
+
+def benjamini_hochberg(p):
+    """BH-adjusted p-values (what utils/compute_FDR.py:35 obtains from R's p.adjust(method="BH")); NaN stays NaN."""
+    p = np.asarray(p, dtype=np.float64)
+    out = np.full(p.shape, np.nan)
+    ok = np.flatnonzero(~np.isnan(p))
+    if len(ok):
+        order = ok[np.argsort(p[ok], kind="stable")]
+        n = len(order)
+        adj = p[order] * n / np.arange(1, n + 1)
+        adj = np.minimum(np.minimum.accumulate(adj[::-1])[::-1], 1.0)
+        out[order] = adj
+    return out
 
 
 def select_modules(eng, modules, cond_it, seed):
@@ -109,6 +123,7 @@ def screen(eng: Engine, feature_rows, n_samples, weights, sample_mask=None, k=3,
 
 def write_results(path, names, genes, res, n_samples_of_profile, direction):
     """One row per profile in the column order of src/superdendrix.py:243-257 (+ rank-sum columns)."""
+    fdr = benjamini_hochberg(res["p_value"])
     with open(path, "w") as fh:
         fh.write(HEADER)
         for p, name in enumerate(names):
@@ -126,7 +141,8 @@ def write_results(path, names, genes, res, n_samples_of_profile, direction):
             cols += [str(round(100 * float(res["zP"][p]) / float(res["max_score"][p]), 4)),
                      "%d/%d" % (int(res["coverage"][p]), int(n_samples_of_profile[p])),
                      "na" if np.isnan(pv) else str(float(pv)), direction, str(len(feats)),
-                     "nan" if not feats else repr(float(res["ranksum_z"][p])), "nan" if not feats else repr(float(res["ranksum_p"][p]))]
+                     "nan" if not feats else repr(float(res["ranksum_z"][p])), "nan" if not feats else repr(float(res["ranksum_p"][p])),
+                     "na" if np.isnan(fdr[p]) else repr(float(fdr[p]))]
             fh.write("\t".join(cols) + "\n")
 
 

@@ -168,3 +168,12 @@ def test_native_tsv_writer_and_reader_match_the_python_path(tmp_path):
     assert unknown == 0
     with pytest.raises(Exception):
         i_o.read_nulls_tsv(str(out) + "/", 0, 1, samples, genes)        # missing file: error, not silence
+
+
+def test_benjamini_hochberg_matches_definition():
+    from superdendrix_b200.screen import benjamini_hochberg
+    p = np.array([0.01, 0.04, 0.03, np.nan, 0.005, 0.5])
+    adj = benjamini_hochberg(p)
+    # R: p.adjust(c(0.01, 0.04, 0.03, 0.005, 0.5), "BH") = 0.025 0.05 0.05 0.025 0.5
+    assert np.allclose(adj[[0, 1, 2, 4, 5]], [0.025, 0.05, 0.05, 0.025, 0.5]) and np.isnan(adj[3])
+    assert np.isnan(benjamini_hochberg([np.nan])).all() and benjamini_hochberg([0.2]).tolist() == [0.2]
