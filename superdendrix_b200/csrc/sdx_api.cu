@@ -60,8 +60,12 @@ static void free_matrix(sdx_ctx *c) {
     if (c->d_samp) cudaFree(c->d_samp);
     if (c->d_trade_obs) cudaFree(c->d_trade_obs);
     if (c->d_rowsize) cudaFree(c->d_rowsize);
+    if (c->d_sp_desc) cudaFree(c->d_sp_desc);
+    if (c->d_sp_obs) cudaFree(c->d_sp_obs);
     c->d_feat = c->d_samp = c->d_trade_obs = nullptr;
     c->d_rowsize = nullptr;
+    c->d_sp_desc = c->d_sp_obs = nullptr;
+    c->sp_state = 0;
 }
 
 static void free_weights(sdx_ctx *c) {

@@ -43,6 +43,9 @@ struct sdx_ctx {
     int rows_are_samples = 0;
     uint32_t *d_trade_obs = nullptr;      // R x RS, observed matrix in trade orientation
     int *d_rowsize = nullptr;             // R: popcount of each trade row (invariant under Curveball)
+    // sparse layout of the trade rows (sdx_sparse.cuh): 0 = not built yet, 1 = in use, -1 = not applicable
+    int sp_state = 0, sp_n_dense = 0, sp_fp_words = 0;
+    uint32_t *d_sp_desc = nullptr, *d_sp_obs = nullptr;
 
     // weights
     int P = 0;

@@ -21,7 +21,7 @@
 //                   then the fused scorer and the outputs.
 #include <stdlib.h>
 
-#include "sdx_trade.cuh"
+#include "sdx_sparse.cuh"
 
 // ---------------------------------------------------------------------------
 struct NullIndexing {          // local null index (within a launch) -> global null id
@@ -109,15 +109,23 @@ __global__ void __launch_bounds__(PL_NT) k_plan_levels(int n_local, int R, int T
 // trade and |a| + |b| bounds its symmetric difference.  Inside a level the plan lists the large
 // trades first and groups similar sizes, so the groups of one warp run loops of similar length and
 // the register fast path of trade_rows (n <= 64) is taken by whole warps.
-__device__ __forceinline__ int trade_class(int sa, int sb) {
+// With the sparse layout (ts >= 0: rows of at most ts carriers are index lists, sdx_sparse.cuh) classes 0 and 1 are
+// the trades that involve a bit-packed row and classes 2 and 3 the list x list trades (one per thread), split by the
+// total list length so that the threads of a warp walk lists of similar length.
+__device__ __forceinline__ int trade_class(int sa, int sb, int ts) {
     const int kb = sa < sb ? sa : sb;
+    if (ts >= 0) {
+        if (sa > ts || sb > ts) return sa + sb > 64 ? 0 : 1;
+        return sa + sb > 12 ? 2 : 3;
+    }
     if (sa + sb > 64) return 0;
     return kb > 8 ? 1 : (kb > 3 ? 2 : 3);
 }
 
 __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const uint32_t *__restrict__ pairs,
                             const uint16_t *__restrict__ lvl, const int *__restrict__ depth, const int *__restrict__ rowsize,
-                            uint2 *__restrict__ plan, uint16_t *__restrict__ offs, int offs_stride) {
+                            const uint32_t *__restrict__ desc, int ts, uint4 *__restrict__ plan, uint16_t *__restrict__ offs,
+                            int offs_stride) {
     extern __shared__ uint32_t hist_smem[];        // per warp: dcap * SDX_NCLS + 2 bins
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n = blockIdx.x * (blockDim.x >> 5) + wid;
@@ -125,10 +133,13 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
     const int D = depth[n];
     uint32_t *hist = hist_smem + (size_t)wid * (dcap * SDX_NCLS + 2);
     const uint16_t *lv = lvl + (size_t)n * T;
-    uint2 *out = plan + (size_t)n * T;
+    uint4 *out = plan + (size_t)n * T;          // (a | b << 16, t, descriptor of a, descriptor of b)
     const uint32_t *pr = pairs + (size_t)n * Tp;
     if (D >= dcap) {            // very deep schedule: fall back to the sequential order (always valid)
-        for (int t = lane; t < T; t += 32) out[t] = make_uint2(pr[t], (uint32_t)t);
+        for (int t = lane; t < T; t += 32) {
+            const uint32_t e = pr[t];
+            out[t] = make_uint4(e, (uint32_t)t, desc ? desc[e & 0xffffu] : 0u, desc ? desc[e >> 16] : 0u);
+        }
         return;                 // k_trade runs such a null one trade per level, in order
     }
     const int NB = D * SDX_NCLS;                       // bin = (level - 1) * NCLS + class
@@ -136,7 +147,7 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
     __syncwarp();
     for (int t = lane; t < T; t += 32) {
         const uint32_t e = pr[t];
-        atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16])], 1u);
+        atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16], ts)], 1u);
     }
     __syncwarp();
     // exclusive scan of the bins -> start offsets
@@ -154,14 +165,15 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
         carry += __shfl_sync(0xffffffffu, inc, 31);
     }
     __syncwarp();
-    uint16_t *of = offs + (size_t)n * offs_stride;          // of[l] = first entry of level l+1, of[D] = T
-    for (int l = lane; l < D; l += 32) of[l] = (uint16_t)hist[l * SDX_NCLS];
-    if (lane == 0) of[D] = (uint16_t)T;
+    // of[2l] = first entry of level l+1, of[2l+1] = its first class-2 entry (list x list trades start there), of[2D] = T
+    uint16_t *of = offs + (size_t)n * offs_stride;
+    for (int l = lane; l < D; l += 32) { of[2 * l] = (uint16_t)hist[l * SDX_NCLS]; of[2 * l + 1] = (uint16_t)hist[l * SDX_NCLS + 2]; }
+    if (lane == 0) of[2 * D] = (uint16_t)T;
     __syncwarp();
     for (int t = lane; t < T; t += 32) {
         const uint32_t e = pr[t];
-        uint32_t pos = atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16])], 1u);
-        out[pos] = make_uint2(e, (uint32_t)t);
+        uint32_t pos = atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16], ts)], 1u);
+        out[pos] = make_uint4(e, (uint32_t)t, desc ? desc[e & 0xffffu] : 0u, desc ? desc[e >> 16] : 0u);
     }
 }
 
@@ -187,7 +199,7 @@ struct TradeArgs {
     const uint32_t *observed;         // R x RS
     uint32_t *work;                   // gridDim.x x R x RS (global-resident variant only)
     uint32_t *carry;                  // n_units x R x RS: chain state between launches (or null)
-    const uint2 *plan;                // n_local x T
+    const uint4 *plan;                // n_local x T: (a | b << 16, t, descriptor of a, descriptor of b)
     const uint16_t *offs;             // n_local x offs_stride level offsets
     int dcap;                         // schedules at least this deep run in sequential order
     const int *depth;                 // n_local
@@ -198,6 +210,10 @@ struct TradeArgs {
     uint32_t *out_rows;               // staging: rows of launch-local null l go to out_rows + l * R * wprL
     unsigned long long *applied;      // (i - ix.null_lo)
     ScoreArgs sc;
+    // sparse layout (k_trade_sparse only)
+    const uint32_t *desc;             // R row descriptors
+    const uint32_t *obs_state;        // fp_words: observed matrix in the sparse layout
+    int n_dense, fp_words;
 };
 
 // out-of-line copy of the scorer for the trade kernel: keeps its registers out of the trade loop's budget
@@ -238,19 +254,19 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : (LB == 4 ? 19
             // ---- trades, level by level -------------------------------------
             unsigned int my_applied = 0;
             if (T > 0) {
-                const uint2 *pl = p.plan + (size_t)local * T;
+                const uint4 *pl = p.plan + (size_t)local * T;
                 const uint16_t *of = p.offs + (size_t)local * p.offs_stride;
                 int D = p.depth[local];
                 const bool seq = D >= p.dcap;            // very deep schedule: one trade per level, in order
                 if (seq) D = T;
                 // level l covers plan entries [OFF(l), OFF(l+1)); e2 = end of level l+1, fetched one level ahead
-                auto OFF = [&](int lv) -> int { return seq ? lv : (int)of[lv]; };
+                auto OFF = [&](int lv) -> int { return seq ? lv : (int)of[2 * lv]; };
                 int l = 0, base = OFF(0), e = OFF(1);
                 int e2 = (D >= 2) ? OFF(2) : e;
-                const uint2 none = make_uint2(0u, 0u);
-                uint2 ent_n = (base + myg < e) ? pl[base + myg] : none;
+                const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+                uint4 ent_n = (base + myg < e) ? pl[base + myg] : none;
                 while (l < D) {
-                    const uint2 ent = ent_n;
+                    const uint4 ent = ent_n;
                     const bool act = base + myg < e;
                     int nbase = base + NG, nl = l, ne = e;
                     const bool level_end = nbase >= e;
@@ -298,6 +314,158 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : (LB == 4 ? 19
                 reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(rows)[i];
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Sparse layout: conversion of the observed matrix and the one-warp-per-null trade kernel (sdx_sparse.cuh)
+// ---------------------------------------------------------------------------
+__global__ void k_to_sparse(const uint32_t *__restrict__ rows, int R, int RS, const uint32_t *__restrict__ desc, int n_dense,
+                            uint32_t *__restrict__ state) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R) return;
+    const uint32_t d = desc[r];
+    const uint32_t w = lane < RS ? rows[(size_t)r * RS + lane] : 0u;     // RS <= 32: lane i holds word i
+    if (sp_is_dense(d)) {
+        if (lane < RS) state[(size_t)sp_off(d) * RS + lane] = w;
+        return;
+    }
+    uint16_t *list = reinterpret_cast<uint16_t *>(state + (size_t)n_dense * RS) + sp_off(d);
+    int inc = __popc(w);
+    const int cnt = inc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += x;
+    }
+    int pos = inc - cnt;
+    for (uint32_t x = w; x; x &= x - 1) list[pos++] = (uint16_t)(lane * 32 + __ffs(x) - 1);
+}
+
+__global__ void __launch_bounds__(32, 18) k_trade_sparse(const __grid_constant__ TradeArgs p) {
+    extern __shared__ __align__(16) uint32_t sp_smem[];
+    __shared__ int32_t s_mod[SDX_MAX_K];
+    const int lane = threadIdx.x;
+    const int sub = lane & (SP_G - 1), grp = lane / SP_G;
+    const int R = p.R, RS = p.RS, T = p.T;
+    // layout: state (bit-packed rows, then the list pool) | 2 scratch rows per group | list scratch of the 32 threads
+    uint32_t *state = sp_smem;
+    uint32_t *gscr = sp_smem + p.fp_words;
+    uint16_t *lscr = reinterpret_cast<uint16_t *>(gscr + SP_GPW * 2 * RS);
+    SparseView v;
+    v.bits = state; v.lists = reinterpret_cast<uint16_t *>(state + (size_t)p.n_dense * RS); v.desc = p.desc; v.RS = RS;
+    const int nvec = p.fp_words / 4;
+
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        for (int j = 0; j < p.ix.seg_len; ++j) {
+            const int64_t local = (int64_t)u * p.ix.seg_len + j;
+            const uint64_t null_id = p.ix.id(local);
+            if (null_id >= p.ix.null_hi) break;
+            const bool restart = (null_id % (uint64_t)p.ix.chain_len) == 0;
+            if (restart || j == 0) {
+                const uint32_t *src = restart ? p.obs_state : p.carry + (size_t)u * p.fp_words;
+                for (int i = lane; i < nvec; i += 32)
+                    reinterpret_cast<uint4 *>(state)[i] = reinterpret_cast<const uint4 *>(src)[i];
+            }
+            __syncwarp();
+
+            unsigned int my_applied = 0;
+            if (T > 0) {
+                const uint4 *pl = p.plan + (size_t)local * T;
+                const uint16_t *of = p.offs + (size_t)local * p.offs_stride;
+                int D = p.depth[local];
+                const bool seq = D >= p.dcap;            // very deep schedule: one trade per level, in order
+                if (seq) D = T;
+                // Level l = plan entries [s, e): [s, m) involve a bit-packed row (SP_GPW per round, 4 lanes each),
+                // [m, e) are list x list trades (32 per round, one per thread).  Offsets are fetched two levels
+                // ahead and the entry of a level's first round one level ahead.
+                auto OFFS = [&](int lv, int &s_, int &m_, int &e_) {
+                    if (lv >= D) { s_ = m_ = e_ = 0; }
+                    else if (seq) { s_ = lv; m_ = lv + 1; e_ = lv + 1; }
+                    else { s_ = of[2 * lv]; m_ = of[2 * lv + 1]; e_ = of[2 * lv + 2]; }
+                };
+                const uint4 none = make_uint4(0xffffffffu, 0u, 0u, 0u);
+                auto ENTRY = [&](int s_, int m_, int e_, int r_) -> uint4 {       // this lane's entry of round r_ of a level
+                    const int ug_ = (m_ - s_ + SP_GPW - 1) / SP_GPW;
+                    const int idx = r_ < ug_ ? s_ + r_ * SP_GPW + grp : m_ + (r_ - ug_) * 32 + lane;
+                    return idx < (r_ < ug_ ? m_ : e_) ? pl[idx] : none;
+                };
+                int s0, m0, e0, s1, m1, e1, s2, m2, e2;
+                OFFS(0, s0, m0, e0);
+                OFFS(1, s1, m1, e1);
+                uint4 ent_n = ENTRY(s0, m0, e0, 0);
+                for (int l = 0; l < D; ++l) {
+                    OFFS(l + 2, s2, m2, e2);
+                    const int ug = (m0 - s0 + SP_GPW - 1) / SP_GPW, un = ug + ((e0 - m0 + 31) >> 5);
+                    for (int r = 0; r < un; ++r) {
+                        const uint4 ent = ent_n;
+                        ent_n = r + 1 < un ? ENTRY(s0, m0, e0, r + 1) : (l + 1 < D ? ENTRY(s1, m1, e1, 0) : none);
+                        const bool act = ent.x != 0xffffffffu;
+                        if (r < ug) {
+                            // bit-packed path: list rows go through the group's scratch bitmaps
+                            const bool la = act && !sp_is_dense(ent.z), lb = act && !sp_is_dense(ent.w);
+                            uint32_t *pa = act ? (la ? gscr + (grp * 2) * RS : v.dense_row(ent.z)) : state;
+                            uint32_t *pb = act ? (lb ? gscr + (grp * 2 + 1) * RS : v.dense_row(ent.w)) : state;
+                            sp_group_expand(v.lists + sp_off(ent.z), sp_size(ent.z), pa, RS, sub, la);
+                            sp_group_expand(v.lists + sp_off(ent.w), sp_size(ent.w), pb, RS, sub, lb);
+                            const bool ap = trade_row_ptrs<SP_G, SP_V>(pa, pb, RS, act, ent.y, null_id, p.keys, sub);
+                            __syncwarp();
+                            sp_group_compact(pa, v.lists + sp_off(ent.z), RS, sub, la && ap);
+                            sp_group_compact(pb, v.lists + sp_off(ent.w), RS, sub, lb && ap);
+                            my_applied += (ap && sub == 0) ? 1u : 0u;
+                        } else {
+                            uint16_t *A = v.lists + sp_off(ent.z), *B = v.lists + sp_off(ent.w);
+                            const bool ap = sp_trade_lists(A, sp_size(ent.z), B, sp_size(ent.w), act, ent.y, null_id, p.keys,
+                                                           lscr + lane, lscr + (SP_TS + 1) * 32 + lane, 32);
+                            my_applied += ap ? 1u : 0u;
+                        }
+                    }
+                    __syncwarp();
+                    s0 = s1; m0 = m1; e0 = e1; s1 = s2; m1 = m2; e1 = e2;
+                }
+            }
+            __syncwarp();
+
+            // ---- outputs -----------------------------------------------------
+            const bool emit = null_id >= p.ix.null_lo;
+            if (emit && p.applied) {
+                my_applied = __reduce_add_sync(0xffffffffu, my_applied);
+                if (lane == 0) p.applied[null_id - p.ix.null_lo] = my_applied;
+            }
+            if (emit && p.out_rows) {
+                uint32_t *dst = p.out_rows + (size_t)local * R * p.wprL;
+                for (int r = 0; r < R; ++r) {
+                    sp_row_to_bitmap(v, p.desc[r], gscr, lane);
+                    if (lane < p.wprL) dst[(size_t)r * p.wprL + lane] = gscr[lane];
+                    __syncwarp();
+                }
+            }
+            if (emit && p.sc.n_profiles > 0) {
+                for (int pr = 0; pr < p.sc.n_profiles; ++pr) {
+                    const int32_t *mod = p.sc.modules + (size_t)pr * p.sc.k;
+                    for (int q = 0; q < p.sc.k; ++q) {             // the module's rows as bitmaps in the group scratch
+                        const int g = mod[q];
+                        if (g >= 0) sp_row_to_bitmap(v, p.desc[g], gscr + q * RS, lane);
+                        if (lane == 0) s_mod[q] = g >= 0 ? q : -1;
+                    }
+                    __syncwarp();
+                    SetScore sc = score_module(gscr, RS, false, s_mod, p.sc.k, p.sc.w + (size_t)pr * p.sc.S,
+                                               p.sc.mask + (size_t)pr * p.sc.wprS, p.sc.S, lane);
+                    if (lane == 0) {
+                        if (sc.W >= p.sc.z_obs[pr]) atomicAdd(&p.sc.n_ge[pr], 1ull);
+                        if (p.sc.null_scores) p.sc.null_scores[(size_t)pr * p.sc.n_total + (null_id - p.ix.null_lo)] = sc.W;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (p.save_carry) {
+            uint32_t *dst = p.carry + (size_t)u * p.fp_words;
+            for (int i = lane; i < nvec; i += 32)
+                reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(state)[i];
+        }
+        __syncwarp();
     }
 }
 
@@ -437,6 +605,43 @@ struct HostScore {               // optional fused scoring request
 
 enum { SL_LVL = 0, SL_PLAN, SL_AUX, SL_MOD, SL_Z, SL_SCORES, SL_CARRY, SL_OUT, SL_APPLIED, SL_WORK, SL_OFFS = 12, SL_PAIRS = 13 };
 
+// Builds (once per uploaded matrix) the sparse layout of the trade rows: rows of at most SP_TS carriers become
+// index lists, the others stay bit-packed.  Applicable when the rows are features, fit 32 words, the lists are the
+// majority and the footprint shrinks at least by half.  EXPERIMENTAL: measured at 10.5 ms per 32 768 C1 nulls against
+// 9.8 ms for the bit-packed kernel (profiles/r01_k_trade_ncu_summary.md), so it is only used with SDX_TRADE_SPARSE=1.
+static int sparse_layout(sdx_ctx *c) {
+    if (c->sp_state != 0) return SDX_OK;           // 1 = in use, -1 = not applicable
+    c->sp_state = -1;
+    const int R = c->R, RS = c->RS;
+    if (c->rows_are_samples || RS > SP_G * SP_V || c->L > 65535 || R < 2) return SDX_OK;
+    std::vector<int> size((size_t)R);
+    SDX_CUDA(c, cudaMemcpyAsync(size.data(), c->d_rowsize, sizeof(int) * R, cudaMemcpyDeviceToHost, c->stream));
+    SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<uint32_t> desc((size_t)R);
+    int n_dense = 0, n_list = 0, n_sparse_rows = 0;
+    for (int r = 0; r < R; ++r) {
+        if (size[r] > SP_TS) desc[r] = sp_desc(true, size[r] > 0x7fff ? 0x7fff : size[r], n_dense++);
+        else { desc[r] = sp_desc(false, size[r], n_list); n_list += size[r]; ++n_sparse_rows; }
+    }
+    const int list_words = (((n_list + 1) / 2) + 3) & ~3;
+    const int fp_words = n_dense * RS + list_words;
+    bool use = n_list <= 65535 && n_dense <= 65535 && 2 * n_sparse_rows >= R && 2 * fp_words <= R * RS;
+    const char *env = getenv("SDX_TRADE_SPARSE");
+    use = use && env != nullptr && atoi(env) != 0;
+    if (!use) return SDX_OK;
+    c->sp_n_dense = n_dense; c->sp_fp_words = fp_words > 4 ? fp_words : 4;
+    SDX_CUDA(c, cudaMalloc(&c->d_sp_desc, sizeof(uint32_t) * R));
+    SDX_CUDA(c, cudaMalloc(&c->d_sp_obs, sizeof(uint32_t) * c->sp_fp_words));
+    SDX_CUDA(c, cudaMemsetAsync(c->d_sp_obs, 0, sizeof(uint32_t) * c->sp_fp_words, c->stream));
+    SDX_CUDA(c, cudaMemcpyAsync(c->d_sp_desc, desc.data(), sizeof(uint32_t) * R, cudaMemcpyHostToDevice, c->stream));
+    k_to_sparse<<<ceil_div(R, 8), 256, 0, c->stream>>>(c->d_trade_obs, R, RS, c->d_sp_desc, n_dense, c->d_sp_obs);
+    c->total_launches++;
+    SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    SDX_CUDA(c, cudaGetLastError());
+    c->sp_state = 1;
+    return SDX_OK;
+}
+
 // The common driver behind sdx_curveball and sdx_null_pvalue (stat = fixed).
 int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
                   uint32_t *out_rows, int64_t *applied, const HostScore *hs) {
@@ -449,11 +654,14 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
     TradeConfig cfg;
     int rc = pick_config(c, &cfg);
     if (rc) return rc;
+    if ((rc = sparse_layout(c))) return rc;
+    const bool sparse = c->sp_state == 1;
+    const size_t sp_smem = sparse ? sizeof(uint32_t) * ((size_t)c->sp_fp_words + SP_GPW * 2 * c->RS) + sizeof(uint16_t) * 2 * (SP_TS + 1) * 32 : 0;
 
     LaunchTimer timer(c);
     const PhiloxKeys keys = make_keys(seed);
     const int R = c->R, RS = c->RS;
-    const size_t mat_words = (size_t)R * RS;
+    const size_t mat_words = sparse ? (size_t)c->sp_fp_words : (size_t)R * RS;      // state of one chain (carry buffer)
     const size_t out_per = (size_t)R * c->wprL;
 
     // ---- fused scoring set-up ------------------------------------------------
@@ -518,14 +726,14 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
         int dcap = (int)(16 * T / R) + 64;
         if (dcap < 128) dcap = 128;
         if (dcap > SDX_HCAP) dcap = SDX_HCAP;
-        const int offs_stride = (int)(((T < dcap ? T : dcap) + 2 + 1) & ~1ll);
+        const int offs_stride = (int)((2 * (T < dcap ? T : dcap) + 2 + 1) & ~1ll);
         const size_t sort_smem_warp = sizeof(uint32_t) * ((size_t)dcap * SDX_NCLS + 2);
         const int sort_warps = sort_smem_warp * 8 <= 40 * 1024 ? 8 : (sort_smem_warp * 4 <= 40 * 1024 ? 4 : 2);
         if ((rc = sdx_scratch(c, SL_OFFS, sizeof(uint16_t) * (size_t)n_local_max * offs_stride + 64, &p_offs))) return rc;
         const size_t lvl_bytes = ((sizeof(uint16_t) * (size_t)n_local_max * Tn + 15) / 16) * 16;
         if ((rc = sdx_scratch(c, SL_LVL, lvl_bytes + sizeof(int) * n_local_max + 64, &p_lvl))) return rc;
         int *d_depth = (int *)((char *)p_lvl + lvl_bytes);
-        if ((rc = sdx_scratch(c, SL_PLAN, sizeof(uint2) * (size_t)n_local_max * Tn, &p_plan))) return rc;
+        if ((rc = sdx_scratch(c, SL_PLAN, sizeof(uint4) * (size_t)n_local_max * Tn, &p_plan))) return rc;
         void *p_pairs;
         const int Tp = (Tn + 3) & ~3;                       // pairs row length: 16-byte aligned rows
         if ((rc = sdx_scratch(c, SL_PAIRS, sizeof(uint32_t) * (size_t)n_local_max * Tp + 64, &p_pairs))) return rc;
@@ -562,20 +770,31 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
                         n_local, R, (int)T, Tp, (const uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux);
                     k_plan_sort<<<ceil_div(n_local, sort_warps), sort_warps * 32, sort_smem_warp * sort_warps, c->stream>>>(
                                                                           n_local, R, (int)T, Tp, dcap, (const uint32_t *)p_pairs,
-                                                                          (const uint16_t *)p_lvl, d_depth, c->d_rowsize, (uint2 *)p_plan,
+                                                                          (const uint16_t *)p_lvl, d_depth, c->d_rowsize, sparse ? c->d_sp_desc : nullptr,
+                                                                          sparse ? SP_TS : -1, (uint4 *)p_plan,
                                                                           (uint16_t *)p_offs, offs_stride);
                     timer.count(3);
                 }
                 cudaEventRecord(c->ev[3], c->stream);
                 TradeArgs ta{};
                 ta.keys = keys; ta.ix = ix; ta.observed = c->d_trade_obs; ta.work = (uint32_t *)p_work;
-                ta.carry = (uint32_t *)p_carry; ta.plan = (const uint2 *)p_plan; ta.n_units = (int)nch;
+                ta.carry = (uint32_t *)p_carry; ta.plan = (const uint4 *)p_plan; ta.n_units = (int)nch;
                 ta.offs = (const uint16_t *)p_offs; ta.depth = d_depth; ta.offs_stride = offs_stride; ta.dcap = dcap;
                 ta.R = R; ta.RS = RS; ta.T = (int)T; ta.wprL = c->wprL;
                 ta.save_carry = need_carry && sg + 1 < n_segs;
                 ta.out_rows = (uint32_t *)p_out; ta.applied = (unsigned long long *)p_app; ta.sc = sc;
                 const int grid = (int)(nch < grid_cap ? nch : grid_cap);
-                cudaError_t e = dispatch_trade(cfg, grid, c->stream, ta);
+                cudaError_t e;
+                if (sparse) {
+                    ta.desc = c->d_sp_desc; ta.obs_state = c->d_sp_obs; ta.n_dense = c->sp_n_dense; ta.fp_words = c->sp_fp_words;
+                    e = cudaFuncSetAttribute(k_trade_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem);
+                    if (e == cudaSuccess) {
+                        k_trade_sparse<<<(unsigned)nch, 32, sp_smem, c->stream>>>(ta);
+                        e = cudaGetLastError();
+                    }
+                } else {
+                    e = dispatch_trade(cfg, grid, c->stream, ta);
+                }
                 if (e != cudaSuccess) return sdx_fail(c, SDX_ERR_CUDA, std::string("trade kernel launch failed: ") + cudaGetErrorString(e));
                 timer.count();
                 cudaEventRecord(c->ev[4], c->stream);

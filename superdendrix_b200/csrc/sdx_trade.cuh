@@ -43,13 +43,14 @@ static __device__ __noinline__ uint32_t deal_below_slow(const PhiloxKeys *keys, 
 // slice of the mask onto the set bits of its own words.
 // Returns true when the trade was applied (src/curveball.py:29 skip rule).
 // ---------------------------------------------------------------------------
+// row_a / row_b point at the first word of the two rows (RS words each, 16-byte aligned).
 template <int G, int V>
-__device__ __forceinline__ bool trade_rows(uint32_t *rows, int RS, bool act, uint32_t a, uint32_t b,
-                                           uint32_t t, uint64_t null_id, const PhiloxKeys &keys, int sub) {
+__device__ __forceinline__ bool trade_row_ptrs(uint32_t *row_a, uint32_t *row_b, int RS, bool act,
+                                               uint32_t t, uint64_t null_id, const PhiloxKeys &keys, int sub) {
     constexpr unsigned FULL = 0xffffffffu;
     uint32_t A[V], B[V], sym[V];
-    uint32_t *ra = rows + (size_t)a * RS + sub * V;
-    uint32_t *rb = rows + (size_t)b * RS + sub * V;
+    uint32_t *ra = row_a + sub * V;
+    uint32_t *rb = row_b + sub * V;
     if constexpr (V % 4 == 0) {
 #pragma unroll
         for (int q = 0; q < V / 4; ++q) {
@@ -153,7 +154,7 @@ __device__ __forceinline__ bool trade_rows(uint32_t *rows, int RS, bool act, uin
         }
     } else {
         // ---- general path: the mask lives in the storage of row a (both rows are in registers) ------
-        volatile uint32_t *cm = rows + (size_t)a * RS;
+        volatile uint32_t *cm = row_a;
         const uint32_t nw = go ? (n + 31) >> 5 : 0u;
         for (uint32_t i = sub; i < nw; i += G) cm[i] = 0u;
         __syncwarp();
@@ -234,6 +235,12 @@ __device__ __forceinline__ bool trade_rows(uint32_t *rows, int RS, bool act, uin
         }
     }
     return go;
+}
+
+template <int G, int V>
+__device__ __forceinline__ bool trade_rows(uint32_t *rows, int RS, bool act, uint32_t a, uint32_t b,
+                                           uint32_t t, uint64_t null_id, const PhiloxKeys &keys, int sub) {
+    return trade_row_ptrs<G, V>(rows + (size_t)a * RS, rows + (size_t)b * RS, RS, act, t, null_id, keys, sub);
 }
 
 // ---------------------------------------------------------------------------

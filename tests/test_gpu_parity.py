@@ -566,3 +566,40 @@ def test_curveball_random_shapes_and_densities_match_oracle(eng, case):
     for m in got:
         assert np.array_equal(bitpack.popcount_rows(m), bitpack.popcount_rows(obs))
         assert np.array_equal(bitpack.unpack_rows(m, Lr).sum(0), bitpack.unpack_rows(obs, Lr).sum(0))
+
+
+# ---------------------------------------------------------------- experimental sparse-layout kernel (SDX_TRADE_SPARSE=1)
+def test_sparse_layout_kernel_is_bit_identical(monkeypatch):
+    """k_trade_sparse (index lists for rare rows, one warp per null) must give the same nulls, counts and scores
+    as the oracle / the default bit-packed kernel; the layout is chosen at upload time from the environment."""
+    monkeypatch.setenv("SDX_TRADE_SPARSE", "1")
+    cases, _ = curveball_cases()
+    rng = np.random.default_rng(4)
+    mats = {"c0_shape": cases["c0_shape"]["dense"],
+            "rare": (rng.random((500, 60)) < 0.01).astype(np.uint8),
+            "mixed": np.concatenate([(rng.random((300, 50)) < 0.02), (rng.random((300, 6)) < 0.4)], axis=1).astype(np.uint8)}
+    with Engine(0) as e2:
+        for name, dense in mats.items():
+            S, F = dense.shape
+            upload_dense(e2, dense)
+            obs = rows_of(dense)
+            R = obs.shape[0]
+            for chain_len, null0, n in ((1, 0, 5), (3, 1, 6)):
+                want, want_ap = oracle.curveball_nulls(obs, 11, null0, n, 5 * R, chain_len)
+                got, got_ap = e2.curveball(11, null0, n, -1, chain_len)
+                assert np.array_equal(got_ap, want_ap), name
+                assert np.array_equal(got, want), name
+            w = synth.weights(S, 2, seed=S)
+            e2.upload_weights(w)
+            order = np.argsort(-dense.sum(0), kind="stable")
+            modules = np.stack([np.sort(order[:3]), np.array([order[1], order[-1], -1])]).astype(np.int32)
+            res = e2.null_pvalue(3, 0, 16, modules, want_scores=True)
+            nulls, _ = oracle.curveball_nulls(obs, 3, 0, 16, 5 * R, 1)
+            frows = bitpack.pack_rows(dense.T)
+            for p in range(2):
+                feats = modules[p][modules[p] >= 0]
+                z = oracle.score_set(frows, S, feats, w[p])[0]
+                assert abs(res["z_obs"][p] - z) <= 1e-9 * np.abs(w[p]).sum()
+                want_sc = [oracle.score_set(m, S, feats, w[p])[0] for m in nulls]
+                assert np.allclose(res["null_scores"][p], want_sc, rtol=0, atol=1e-9 * np.abs(w[p]).sum())
+                assert res["n_ge"][p] == int((res["null_scores"][p] >= res["z_obs"][p]).sum())
