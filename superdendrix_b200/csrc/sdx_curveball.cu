@@ -21,6 +21,8 @@
 //                   then the fused scorer and the outputs.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "sdx_sparse.cuh"
 
 // ---------------------------------------------------------------------------
@@ -319,6 +321,9 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : (LB == 4 ? 19
 
 // ---------------------------------------------------------------------------
 // Sparse layout: conversion of the observed matrix and the one-warp-per-null trade kernel (sdx_sparse.cuh)
+#ifndef SP_MINB
+#define SP_MINB 16
+#endif
 // ---------------------------------------------------------------------------
 __global__ void k_to_sparse(const uint32_t *__restrict__ rows, int R, int RS, const uint32_t *__restrict__ desc, int n_dense,
                             uint32_t *__restrict__ state) {
@@ -343,7 +348,7 @@ __global__ void k_to_sparse(const uint32_t *__restrict__ rows, int R, int RS, co
     for (uint32_t x = w; x; x &= x - 1) list[pos++] = (uint16_t)(lane * 32 + __ffs(x) - 1);
 }
 
-__global__ void __launch_bounds__(32, 18) k_trade_sparse(const __grid_constant__ TradeArgs p) {
+__global__ void __launch_bounds__(32, SP_MINB) k_trade_sparse(const __grid_constant__ TradeArgs p) {
     extern __shared__ __align__(16) uint32_t sp_smem[];
     __shared__ int32_t s_mod[SDX_MAX_K];
     const int lane = threadIdx.x;
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(32, 18) k_trade_sparse(const __grid_constant__
     // layout: state (bit-packed rows, then the list pool) | 2 scratch rows per group | list scratch of the 32 threads
     uint32_t *state = sp_smem;
     uint32_t *gscr = sp_smem + p.fp_words;
-    uint16_t *lscr = reinterpret_cast<uint16_t *>(gscr + SP_GPW * 2 * RS);
+    uint16_t *lscr = reinterpret_cast<uint16_t *>(gscr);       // the two scratch areas are never live at the same time
     SparseView v;
     v.bits = state; v.lists = reinterpret_cast<uint16_t *>(state + (size_t)p.n_dense * RS); v.desc = p.desc; v.RS = RS;
     const int nvec = p.fp_words / 4;
@@ -656,7 +661,8 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
     if (rc) return rc;
     if ((rc = sparse_layout(c))) return rc;
     const bool sparse = c->sp_state == 1;
-    const size_t sp_smem = sparse ? sizeof(uint32_t) * ((size_t)c->sp_fp_words + SP_GPW * 2 * c->RS) + sizeof(uint16_t) * 2 * (SP_TS + 1) * 32 : 0;
+    const size_t sp_scr = std::max(sizeof(uint32_t) * SP_GPW * 2 * (size_t)c->RS, sizeof(uint16_t) * 2 * (SP_TS + 1) * 32);
+    const size_t sp_smem = sparse ? sizeof(uint32_t) * (size_t)c->sp_fp_words + sp_scr : 0;
 
     LaunchTimer timer(c);
     const PhiloxKeys keys = make_keys(seed);

@@ -177,3 +177,46 @@ def test_benjamini_hochberg_matches_definition():
     # R: p.adjust(c(0.01, 0.04, 0.03, 0.005, 0.5), "BH") = 0.025 0.05 0.05 0.025 0.5
     assert np.allclose(adj[[0, 1, 2, 4, 5]], [0.025, 0.05, 0.05, 0.025, 0.5]) and np.isnan(adj[3])
     assert np.isnan(benjamini_hochberg([np.nan])).all() and benjamini_hochberg([0.2]).tolist() == [0.2]
+
+
+# ---------------------------------------------------------------- property tests (hypothesis)
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 40), st.integers(1, 200), st.integers(0, 2 ** 31 - 1))
+def test_property_bitpack_round_trip(rows, bits, seed):
+    d = np.random.default_rng(seed).random((rows, bits)) < 0.3
+    p = bitpack.pack_rows(d)
+    assert np.array_equal(bitpack.unpack_rows(p, bits), d.astype(np.uint8))
+    assert np.array_equal(bitpack.popcount_rows(p), d.sum(1))
+    if bits % 32:
+        assert ((p[:, -1] >> (bits % 32)) == 0).all()          # padding bits stay zero (contract of include/sdx.h)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(1, 25), st.integers(1, 40), st.floats(0.0, 0.6), st.integers(0, 2 ** 31 - 1))
+def test_property_tsv_round_trip_native_equals_python(S, F, density, seed):
+    import tempfile
+    rng = np.random.default_rng(seed)
+    dense = (rng.random((S, F)) < density).astype(np.uint8)
+    samples = ["s%d" % i for i in range(S)]
+    genes = ["g%d_MUT" % j for j in range(F)]
+    with tempfile.TemporaryDirectory() as d:
+        rows = bitpack.pack_rows(dense.T)
+        i_o.write_nulls_tsv(d + "/", 3, rows, samples, genes, n_threads=1)
+        i_o.write_sample_events(d + "/py.tsv", samples, genes, dense)
+        assert open(d + "/3.tsv").read() == open(d + "/py.tsv").read()
+        back, unknown = i_o.read_nulls_tsv(d + "/", 3, 1, samples, genes, n_threads=1)
+        assert unknown == 0 and np.array_equal(back[0], rows)
+        m, n, g2, s2, g2c, p2g = i_o.load_mutation_data(d + "/3.tsv")
+        assert s2 == samples                                        # every sample is listed, even without events
+        assert np.array_equal(i_o.dense_matrix(genes, samples, p2g), dense)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 10 ** 6), st.integers(1, 16))
+def test_property_shard_ranges_partition(n, world):
+    r = [dist.shard_range(n, k, world) for k in range(world)]
+    assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+    assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
