@@ -95,6 +95,12 @@ int sdx_upload_weights(sdx_ctx *ctx, const double *w, const uint32_t *sample_mas
 int sdx_score_sets(sdx_ctx *ctx, const int32_t *sets, const int32_t *profile_of_set, int64_t n_sets,
                    int k, double *W, int32_t *coverage, int32_t *overlap, int32_t *act_cov);
 
+/* sum_w[i] = sum of w over the union of set i — the total_score of
+ * utils/compute_individual_contribution_SELECT.py:69-85 (m_i_score is the same for the single feature); the
+ * leave-one-out contribution W(M) - W(M \ {g}) comes from sdx_score_sets. */
+int sdx_union_sums(sdx_ctx *ctx, const int32_t *sets, const int32_t *profile_of_set, int64_t n_sets, int k,
+                   double *sum_w);
+
 /* Per-feature outputs for one profile: sum of w over carriers and the argmax
  * (first maximum wins, src/superdendrix.py:281-286), W of the singleton
  * (:219-227, unrounded), carrier count (:229-232). */

@@ -56,6 +56,7 @@ PROTOTYPES = {
     "sdx_upload_matrix": (C.c_int, [_ctx, _u32p, C.c_int, C.c_int, C.c_int]),
     "sdx_upload_weights": (C.c_int, [_ctx, _f64p, _u32p, C.c_int, C.c_int]),
     "sdx_score_sets": (C.c_int, [_ctx, _i32p, _i32p, C.c_int64, C.c_int, _f64p, _i32p, _i32p, _i32p]),
+    "sdx_union_sums": (C.c_int, [_ctx, _i32p, _i32p, C.c_int64, C.c_int, _f64p]),
     "sdx_feature_scores": (C.c_int, [_ctx, C.c_int, _f64p, _f64p, _i32p, _i32p]),
     "sdx_trade_shape": (C.c_int, [_ctx, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sdx_curveball": (C.c_int, [_ctx, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, _u32p, _i64p]),

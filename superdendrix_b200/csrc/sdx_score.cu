@@ -64,6 +64,41 @@ extern "C" int sdx_score_sets(sdx_ctx *c, const int32_t *sets, const int32_t *pr
     return rc;
 }
 
+// sum of w over the union of each set (the "total_score" of utils/compute_individual_contribution_SELECT.py:75)
+__global__ void k_union_sums(const uint32_t *__restrict__ feat, int wprS, int S, const int32_t *__restrict__ sets,
+                             const int32_t *__restrict__ prof, int64_t n_sets, int k, const double *__restrict__ w,
+                             const uint32_t *__restrict__ mask, double *sum_w) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n_sets) return;
+    const int p = prof ? prof[i] : 0;
+    SetScore s = score_module(feat, wprS, false, sets + i * k, k, w + (size_t)p * S, mask + (size_t)p * wprS, S, lane);
+    if (lane == 0) sum_w[i] = s.sw;
+}
+
+extern "C" int sdx_union_sums(sdx_ctx *c, const int32_t *sets, const int32_t *prof, int64_t n, int k, double *sum_w) {
+    if (!c) return SDX_ERR_INVALID;
+    SDX_REQUIRE(c, c->d_feat && c->d_w, SDX_ERR_STATE, "matrix and weights must be uploaded first");
+    SDX_REQUIRE(c, n >= 0 && k >= 1 && k <= SDX_MAX_K && (n == 0 || (sets && sum_w)), SDX_ERR_INVALID, "bad sets / k");
+    for (int64_t i = 0; i < n * k; ++i)
+        SDX_REQUIRE(c, sets[i] >= -1 && sets[i] < c->F, SDX_ERR_INVALID, "feature index out of range");
+    if (prof) for (int64_t i = 0; i < n; ++i)
+        SDX_REQUIRE(c, prof[i] >= 0 && prof[i] < c->P, SDX_ERR_INVALID, "profile index out of range");
+    LaunchTimer timer(c);
+    if (n == 0) return timer.finish();
+    void *p_in, *p_out;
+    int rc;
+    if ((rc = sdx_scratch(c, 0, sizeof(int32_t) * n * (k + 1) + 64, &p_in))) return rc;
+    if ((rc = sdx_scratch(c, 1, sizeof(double) * n + 64, &p_out))) return rc;
+    int32_t *d_sets = (int32_t *)p_in, *d_prof = prof ? d_sets + n * k : nullptr;
+    SDX_CUDA(c, cudaMemcpyAsync(d_sets, sets, sizeof(int32_t) * n * k, cudaMemcpyHostToDevice, c->stream));
+    if (prof) SDX_CUDA(c, cudaMemcpyAsync(d_prof, prof, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    k_union_sums<<<ceil_div(n, 8), 256, 0, c->stream>>>(c->d_feat, c->wprS, c->S, d_sets, d_prof, n, k, c->d_w, c->d_mask, (double *)p_out);
+    timer.count();
+    SDX_CUDA(c, cudaMemcpyAsync(sum_w, p_out, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    return timer.finish();
+}
+
 // per-feature: one warp per feature
 __global__ void k_feature_scores(const uint32_t *__restrict__ feat, int F, int wprS, int S, const double *__restrict__ w,
                                  const uint32_t *__restrict__ mask, double *sum_w, double *W1, int32_t *count) {

@@ -255,6 +255,7 @@ __device__ __forceinline__ bool trade_rows(uint32_t *rows, int RS, bool act, uin
 // ---------------------------------------------------------------------------
 struct SetScore {
     double W;
+    double sw;            // sum of w over the union (utils/compute_individual_contribution_SELECT.py:73-75)
     int cov, tot, act;
 };
 
@@ -262,7 +263,7 @@ __device__ __forceinline__ SetScore score_module(const uint32_t *__restrict__ ro
                                                  const int32_t *__restrict__ mod, int k,
                                                  const double *__restrict__ w, const uint32_t *__restrict__ mask,
                                                  int S, int lane) {
-    double pos = 0.0, neg = 0.0;
+    double pos = 0.0, neg = 0.0, sw = 0.0;
     int cov = 0, tot = 0, act = 0;
     int g[SDX_MAX_K];
 #pragma unroll
@@ -290,6 +291,7 @@ __device__ __forceinline__ SetScore score_module(const uint32_t *__restrict__ ro
                 for (int j = 0; j < SDX_MAX_K; ++j) mult += (r[j] >> bp) & 1;
                 if (ws > 0.0) { pos += ws; ++act; }
                 neg += (double)mult * fabs(ws);
+                sw += ws;
             }
         }
     } else {
@@ -304,6 +306,7 @@ __device__ __forceinline__ SetScore score_module(const uint32_t *__restrict__ ro
                 ++cov; tot += mult;
                 if (ws > 0.0) { pos += ws; ++act; }
                 neg += (double)mult * fabs(ws);
+                sw += ws;
             }
         }
     }
@@ -311,6 +314,7 @@ __device__ __forceinline__ SetScore score_module(const uint32_t *__restrict__ ro
     neg = warp_sum_f64(neg);
     SetScore o;
     o.W = 2.0 * pos - neg;
+    o.sw = warp_sum_f64(sw);
     o.cov = warp_sum_i32(cov);
     o.tot = warp_sum_i32(tot);
     o.act = warp_sum_i32(act);

@@ -118,6 +118,15 @@ class Engine:
                                              _ptr(act, C.c_int32)))
         return {"W": W, "coverage": cov, "overlap": ovl, "act_cov": act}
 
+    def union_sums(self, sets, profile_of_set=None):
+        """Sum of w over the union of each set (n, k) -> (n,) fp64."""
+        s = np.ascontiguousarray(np.atleast_2d(np.asarray(sets, dtype=np.int32)))
+        n, k = s.shape
+        pr = None if profile_of_set is None else np.ascontiguousarray(profile_of_set, dtype=np.int32)
+        out = np.zeros(n)
+        self._check(self._lib.sdx_union_sums(self._ctx, _ptr(s, C.c_int32), _ptr(pr, C.c_int32), n, k, _ptr(out, C.c_double)))
+        return out
+
     def feature_scores(self, profile: int = 0):
         F = self.F
         sw, W1 = np.zeros(F), np.zeros(F)

@@ -603,3 +603,33 @@ def test_sparse_layout_kernel_is_bit_identical(monkeypatch):
                 want_sc = [oracle.score_set(m, S, feats, w[p])[0] for m in nulls]
                 assert np.allclose(res["null_scores"][p], want_sc, rtol=0, atol=1e-9 * np.abs(w[p]).sum())
                 assert res["n_ge"][p] == int((res["null_scores"][p] >= res["z_obs"][p]).sum())
+
+
+# ---------------------------------------------------------------- individual contributions
+def test_contributions_match_the_reference_arithmetic(eng):
+    """utils/compute_individual_contribution_SELECT.py:69-85 restated with Python sets, against the GPU sums."""
+    from superdendrix_b200 import contribution
+    dense, _, _ = synth.feature_matrix(300, 50, seed=6)
+    S, F = dense.shape
+    w = synth.weights(S, 2, seed=8)
+    upload_dense(eng, dense)
+    eng.upload_weights(w)
+    rng = np.random.default_rng(1)
+    pairs = np.stack([rng.choice(F, 2, replace=False) for _ in range(40)]).astype(np.int32)
+    prof = rng.integers(0, 2, 40).astype(np.int32)
+    m1, m2 = contribution.pair_contributions(eng, pairs, prof)
+    for i in range(40):
+        cl1 = set(np.flatnonzero(dense[:, pairs[i, 0]])); cl2 = set(np.flatnonzero(dense[:, pairs[i, 1]]))
+        total = sum(w[prof[i]][s] for s in cl1 | cl2)
+        assert abs(m1[i] - sum(w[prof[i]][s] for s in cl1) / total) <= 1e-9 * max(1.0, abs(m1[i]))
+        assert abs(m2[i] - sum(w[prof[i]][s] for s in cl2) / total) <= 1e-9 * max(1.0, abs(m2[i]))
+    mods = np.array([[0, 1, 2], [3, 4, -1]], dtype=np.int32)
+    loo = contribution.leave_one_out(eng, mods, np.array([0, 1], dtype=np.int32))
+    rows = bitpack.pack_rows(dense.T)
+    for j, (m, p) in enumerate(zip(mods, (0, 1))):
+        feats = [int(f) for f in m if f >= 0]
+        full = oracle.score_set(rows, S, feats, w[p])[0]
+        for q, f in enumerate(feats):
+            rest = [g for g in feats if g != f]
+            assert abs(loo[j, q] - (full - oracle.score_set(rows, S, rest, w[p])[0])) <= 1e-9 * np.abs(w[p]).sum()
+    assert np.isnan(loo[1, 2])
