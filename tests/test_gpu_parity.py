@@ -633,3 +633,87 @@ def test_contributions_match_the_reference_arithmetic(eng):
             rest = [g for g in feats if g != f]
             assert abs(loo[j, q] - (full - oracle.score_set(rows, S, rest, w[p])[0])) <= 1e-9 * np.abs(w[p]).sum()
     assert np.isnan(loo[1, 2])
+
+
+# ---------------------------------------------------------------- BASELINE.json sizes: size-independent properties
+def test_c1_full_size_counts_are_additive_and_match_the_oracle_within_mc_error(eng):
+    """configs[1]: 100 000 nulls of the BRAF-shape matrix.  Shards add up exactly (what multi-GPU relies on); the
+    p-value agrees with the oracle's estimate from an independent set of nulls within binomial error."""
+    dense, _, _ = synth.feature_matrix(770, 400)
+    S, F = dense.shape
+    w = synth.weights(S, 1)
+    module = synth.pick_module(dense, 3)[None, :]
+    upload_dense(eng, dense)
+    eng.upload_weights(w)
+    n = 100_000
+    whole = eng.null_pvalue(1764, 0, n, module, want_scores=True)
+    parts = [eng.null_pvalue(1764, lo, 12_500, module, z_obs=whole["z_obs"])["n_ge"][0] for lo in range(0, n, 12_500)]
+    assert sum(parts) == whole["n_ge"][0] == int((whole["null_scores"][0] >= whole["z_obs"][0]).sum())
+    obs = rows_of(dense)
+    m = 1500
+    nulls, applied = oracle.curveball_nulls(obs, 99, 5_000_000, m, 5 * obs.shape[0], 1)
+    sc = np.array([oracle.score_set(x, S, module[0], w[0])[0] for x in nulls])
+    p_gpu, p_cpu = whole["n_ge"][0] / n, float((sc >= whole["z_obs"][0]).mean())
+    sd = np.sqrt(p_cpu * (1 - p_cpu) / m + p_gpu * (1 - p_gpu) / n)
+    assert abs(p_gpu - p_cpu) < 4.5 * sd + 1e-9
+    # the null score distribution itself: mean and spread agree
+    assert abs(whole["null_scores"][0].mean() - sc.mean()) < 4.5 * sc.std() / np.sqrt(m)
+    assert (applied > 0.9 * 5 * obs.shape[0]).all()
+
+
+def test_c3_shape_global_memory_variant(eng):
+    """configs[3] shape: 1 000 samples x 5 000 features (rows = samples, 157-word rows, matrix in global memory / L2,
+    5 000 trades per null), several profiles scored per null."""
+    dense, _, _ = synth.feature_matrix(1000, 5000)
+    S, F = dense.shape
+    P = 6
+    w = synth.weights(S, P, seed=5)
+    upload_dense(eng, dense)
+    eng.upload_weights(w)
+    R, L, wpr, ras = eng.trade_shape()
+    assert ras and R == S and L == F
+    obs = rows_of(dense)
+    got, got_ap = eng.curveball(7, 10, 3, chain_len=2)
+    want, want_ap = oracle.curveball_nulls(obs, 7, 10, 3, 5 * R, 2)
+    assert np.array_equal(got_ap, want_ap) and np.array_equal(got, want)
+    assert np.array_equal(bitpack.popcount_rows(got[2]), bitpack.popcount_rows(obs))
+    assert np.array_equal(bitpack.unpack_rows(got[2], L).sum(0), dense.sum(0))
+    order = np.argsort(-dense.sum(0), kind="stable")[:30]
+    rng = np.random.default_rng(0)
+    mods = np.sort(np.stack([rng.choice(order, 3, replace=False) for _ in range(P)]), axis=1).astype(np.int32)
+    res = eng.null_pvalue(7, 0, 48, mods, want_scores=True)
+    a = eng.null_pvalue(7, 0, 24, mods, z_obs=res["z_obs"])["n_ge"]
+    b = eng.null_pvalue(7, 24, 24, mods, z_obs=res["z_obs"])["n_ge"]
+    assert np.array_equal(a + b, res["n_ge"])
+    nulls, _ = oracle.curveball_nulls(obs, 7, 0, 2, 5 * R, 1)
+    for i in range(2):
+        fr = bitpack.pack_rows(bitpack.unpack_rows(nulls[i], L).T)
+        for p in range(P):
+            assert abs(res["null_scores"][p, i] - oracle.score_set(fr, S, mods[p], w[p])[0]) <= 1e-9 * np.abs(w[p]).sum()
+
+
+def test_c4_slice_batched_model_selection_statistics(eng):
+    """configs[4] slice: many profiles over the C0 matrix, 10 000 conditional permutations per feature and a
+    rank-sum per profile; a sample of jobs is checked against the oracle exactly."""
+    dense, _, _ = synth.feature_matrix(770, 400)
+    S, F = dense.shape
+    n_prof = 300
+    w = synth.weights(S, n_prof, seed=21)
+    upload_dense(eng, dense)
+    eng.upload_weights(w)
+    rng = np.random.default_rng(3)
+    order = np.argsort(-dense.sum(0), kind="stable")[:40]
+    mods = np.sort(np.stack([rng.choice(order, 3, replace=False) for _ in range(n_prof)]), axis=1).astype(np.int32)
+    pj = np.arange(n_prof, dtype=np.int32)
+    counts, realW = eng.condperm_batch(mods, 10_000, 1764, 0, pj)
+    rs = eng.ranksum(mods, pj)
+    rows = bitpack.pack_rows(dense.T)
+    assert counts.shape == (n_prof, 3) and (counts >= 0).all() and (counts <= 10_000).all()
+    for j in (0, 17, 299):
+        oc, orw = oracle.condperm(rows, S, mods[j], w[j], np.arange(S), 1764, 0, 10_000)
+        assert np.array_equal(counts[j], oc) and np.array_equal(realW[j], orw)
+        union = dense[:, mods[j]].any(axis=1)
+        zz, pp, s2, n1 = oracle.ranksum(w[j], np.arange(S), bitpack.pack_mask(np.nonzero(union)[0], S))
+        assert (rs["twice_rank_sum"][j], rs["n1"][j]) == (s2, n1) and abs(rs["z"][j] - zz) <= 1e-12 * max(1, abs(zz))
+    # random profiles carry no signal: rank-sum p-values are roughly uniform
+    assert 0.3 < np.median(rs["p"]) < 0.7
