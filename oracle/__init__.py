@@ -85,6 +85,13 @@ def below_from_draws(draws, m):
     return int(v), used.value
 
 
+def deal_stats(reset=False):
+    """(times the Lemire rejection zone was entered, draws rejected) by the canonical trade since the last reset."""
+    z, r = C.c_uint64(0), C.c_uint64(0)
+    lib().sdxo_deal_stats(C.byref(z), C.byref(r), C.c_int(1 if reset else 0))
+    return z.value, r.value
+
+
 def trade_pair(seed, null_id, t, R):
     a, b = C.c_uint32(0), C.c_uint32(0)
     lib().sdxo_trade_pair(C.c_uint64(seed), C.c_uint64(null_id), C.c_uint32(t), C.c_uint32(R),

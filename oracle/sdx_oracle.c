@@ -162,6 +162,14 @@ static uint32_t deal_draw(uint64_t seed, uint64_t null_id, uint32_t t, uint32_t 
     return out[i & 3];
 }
 
+/* how often the rejection zone of Lemire's method was entered / a draw was rejected (test instrumentation) */
+static uint64_t g_deal_zone = 0, g_deal_redraw = 0;
+SDXO_API void sdxo_deal_stats(uint64_t *zone, uint64_t *redraw, int reset) {
+    if (zone) *zone = g_deal_zone;
+    if (redraw) *redraw = g_deal_redraw;
+    if (reset) g_deal_zone = g_deal_redraw = 0;
+}
+
 /* exactly uniform integer in [0, m) for pick i (Lemire with rejection) */
 static uint32_t deal_below(uint64_t seed, uint64_t null_id, uint32_t t, uint32_t i, uint32_t m) {
     uint32_t attempt = 0;
@@ -169,7 +177,9 @@ static uint32_t deal_below(uint64_t seed, uint64_t null_id, uint32_t t, uint32_t
     uint32_t lo = (uint32_t)prod;
     if (lo < m) {
         uint32_t thr = (uint32_t)(-m) % m;
+        g_deal_zone++;
         while (lo < thr) {
+            g_deal_redraw++;
             prod = (uint64_t)deal_draw(seed, null_id, t, i, ++attempt) * m;
             lo = (uint32_t)prod;
         }

@@ -717,3 +717,57 @@ def test_c4_slice_batched_model_selection_statistics(eng):
         assert (rs["twice_rank_sum"][j], rs["n1"][j]) == (s2, n1) and abs(rs["z"][j] - zz) <= 1e-12 * max(1, abs(zz))
     # random profiles carry no signal: rank-sum p-values are roughly uniform
     assert 0.3 < np.median(rs["p"]) < 0.7
+
+
+# ---------------------------------------------------------------- the rare branch of Lemire's method
+# (half, sparse layout?, null indices of seed 4242 whose single trade enters the rejection zone; found by scanning the
+#  oracle: tools/find_lemire_cases.py.  The last index of each list also RE-DRAWS.)
+LEMIRE_CASES = [
+    (400, "0", [18883, 55949]),          # n = 800: general pick path (rank mask in the row's shared-memory storage)
+    (32, "0", [314870, 16882340]),       # n = 64: register pick path
+    (16, "1", [21381922]),               # n = 32: list x list path of the sparse-layout kernel
+]
+
+
+@pytest.mark.parametrize("half,sparse,hits", LEMIRE_CASES)
+def test_lemire_rejection_branch_matches_oracle(monkeypatch, half, sparse, hits):
+    """A pick enters the rejection zone with probability m / 2^32, so ordinary parity cases never exercise the
+    device's out-of-line branch (deal_below_slow: re-draw from the pick's own sub-stream with attempt + 1).
+    Two disjoint rows of `half` bits make every null one trade of `half` picks; the null indices below are known
+    (from the oracle) to enter the zone and to re-draw.  Windows around them must be bit-identical."""
+    monkeypatch.setenv("SDX_TRADE_SPARSE", sparse)
+    L = max(2 * half, 64)
+    rows_dense = np.zeros((2, L), dtype=np.uint8)
+    rows_dense[0, :half] = 1
+    rows_dense[1, half:2 * half] = 1
+    dense = rows_dense.T                                   # S = L samples x F = 2 features: the trade rows are the features
+    with Engine(0) as e2:
+        upload_dense(e2, dense)
+        obs = rows_of(dense)
+        assert obs.shape[0] == 2
+        zone = redraw = 0
+        for idx in hits:
+            oracle.deal_stats(reset=True)
+            want, want_ap = oracle.curveball_nulls(obs, 4242, idx - 40, 80, 1, 1)
+            z, r = oracle.deal_stats()
+            zone += z
+            redraw += r
+            got, got_ap = e2.curveball(4242, idx - 40, 80, n_trades=1, chain_len=1)
+            assert np.array_equal(got_ap, want_ap)
+            assert np.array_equal(got, want)
+    assert zone >= len(hits) and redraw >= 1
+
+
+def test_trade_pair_rejection_zone_is_covered(eng):
+    """With R = 65 535 rows a pair draw enters Lemire's rejection zone with probability ~1.5e-5; 400 000 trades
+    contain about a dozen such draws (sequential stream: a rejected draw shifts the following ones)."""
+    R, T = 65535, 400_000
+    a, b = eng.test_trade_pairs(77, 5, T, R)
+    import ctypes as C
+    lib = oracle.lib()
+    x, y = C.c_uint32(0), C.c_uint32(0)
+    for t in range(T):
+        lib.sdxo_trade_pair(C.c_uint64(77), C.c_uint64(5), C.c_uint32(t), C.c_uint32(R), C.byref(x), C.byref(y))
+        if x.value != a[t] or y.value != b[t]:
+            raise AssertionError("pair %d differs: device (%d, %d) oracle (%d, %d)" % (t, a[t], b[t], x.value, y.value))
+    assert (a != b).all() and a.max() < R and b.max() < R
