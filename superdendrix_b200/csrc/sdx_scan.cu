@@ -288,8 +288,9 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan12(const __grid_constant__ Scan
 
 // LISTS == true: one matrix, per-warp top lists (sdx_scan).  LISTS == false: a batch of nb matrices, only the
 // maximum of each is kept (the max_k null statistic); `bp` below then carries the batch offsets.
-template <bool LISTS>
-__global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ ScanArgs pa) {
+// NT threads per CTA, NJ values of l per thread: one l-chunk is NT * NJ wide (small NT for small F).
+template <bool LISTS, int NT, int NJ>
+__global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 4) k_scan3(const __grid_constant__ ScanArgs pa) {
     __shared__ uint32_t sI[SCAN_MAXW];
     __shared__ unsigned s_item;
     __shared__ double s_sgh[SCAN_GT][SCAN_HB];
@@ -317,15 +318,15 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
         p.wprS = pa.wprS; p.g_lo = pa.g_lo; p.g_hi = pa.g_hi; p.gt0 = pa.gt0; p.n_lc = pa.n_lc; p.g_thr = pa.g_thr;
         double best = -DBL_MAX;
         const int gt = p.gt0 + it / per_gt, rem = it % per_gt, hb = rem / p.n_lc, lc = rem - hb * p.n_lc;
-        const int g0 = gt * SCAN_GT, l0 = lc * (SCAN_NT * SCAN_NJ);
+        const int g0 = gt * SCAN_GT, l0 = lc * (NT * NJ);
         const int hlo = max(hb * SCAN_HB, g0 + 1), hhi = min(hb * SCAN_HB + SCAN_HB, F - 1);
-        if (hlo >= hhi || l0 + SCAN_NT * SCAN_NJ - 1 <= hlo) continue;
+        if (hlo >= hhi || l0 + NT * NJ - 1 <= hlo) continue;
         if (LISTS) top.refresh(p.g_thr);
 
-        double c[SCAN_GT][SCAN_NJ];
+        double c[SCAN_GT][NJ];
 #pragma unroll
-        for (int j = 0; j < SCAN_NJ; ++j) {
-            const int l = l0 + tid + j * SCAN_NT;
+        for (int j = 0; j < NJ; ++j) {
+            const int l = l0 + tid + j * NT;
             const double sl = l < F ? p.s1[l] : 0.0;
 #pragma unroll
             for (int gi = 0; gi < SCAN_GT; ++gi) {
@@ -371,18 +372,18 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
                 slow[gi] = (fl >> gi) & 1u;
             }
             const double *Th = p.T + (size_t)h * Fp;
-            double t[SCAN_NJ];
+            double t[NJ];
 #pragma unroll
-            for (int j = 0; j < SCAN_NJ; ++j) {
-                const int l = l0 + tid + j * SCAN_NT;
+            for (int j = 0; j < NJ; ++j) {
+                const int l = l0 + tid + j * NT;
                 const bool v = l > h && l < F;
                 t[j] = v ? Th[l] : -INFINITY;
                 cnt += v ? nvg : 0;
             }
             if (!any_slow) {
 #pragma unroll
-                for (int j = 0; j < SCAN_NJ; ++j) {
-                    if (l0 + (j + 1) * SCAN_NT - 1 <= h) continue;          // CTA-uniform: every l of this slice is <= h
+                for (int j = 0; j < NJ; ++j) {
+                    if (l0 + (j + 1) * NT - 1 <= h) continue;          // CTA-uniform: every l of this slice is <= h
                     double W[SCAN_GT];
                     bool cand = false;
 #pragma unroll
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
                         else best = fmax(best, W[gi]);
                     }
                     if (LISTS && __any_sync(0xffffffffu, cand)) {
-                        const int l = l0 + tid + j * SCAN_NT;
+                        const int l = l0 + tid + j * NT;
 #pragma unroll
                         for (int gi = 0; gi < SCAN_GT; ++gi)
                             top.offer(W[gi] >= top.gate, W[gi], scan_key(3, g0 + gi, h, l), lane);
@@ -402,13 +403,13 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
 #pragma unroll
                 for (int gi = 0; gi < SCAN_GT; ++gi) {
                     if (sgh[gi] == -INFINITY) continue;           // uniform
-                    double p3[SCAN_NJ];
+                    double p3[NJ];
 #pragma unroll
-                    for (int j = 0; j < SCAN_NJ; ++j) p3[j] = 0.0;
+                    for (int j = 0; j < NJ; ++j) p3[j] = 0.0;
                     if (slow[gi]) {                               // uniform: g∩h∩{w>0} is non-empty
                         const int g = g0 + gi;
                         __syncthreads();
-                        for (int wi = tid; wi < p.wprS; wi += SCAN_NT)
+                        for (int wi = tid; wi < p.wprS; wi += NT)
                             sI[wi] = p.feat[(size_t)g * p.fstride + wi] & p.feat[(size_t)h * p.fstride + wi] & p.pos[wi];
                         __syncthreads();
                         for (int wi = 0; wi < p.wprS; ++wi) {
@@ -420,21 +421,21 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
                                 const double wp = p.wpos[s];
                                 const uint32_t *sr = p.samp + (size_t)s * p.sstride;
 #pragma unroll
-                                for (int j = 0; j < SCAN_NJ; ++j) {
-                                    const int l = l0 + tid + j * SCAN_NT;
+                                for (int j = 0; j < NJ; ++j) {
+                                    const int l = l0 + tid + j * NT;
                                     if (l < F && ((sr[l >> 5] >> (l & 31)) & 1u)) p3[j] += wp;
                                 }
                             }
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < SCAN_NJ; ++j) {
-                        if (l0 + (j + 1) * SCAN_NT - 1 <= h) continue;      // CTA-uniform
+                    for (int j = 0; j < NJ; ++j) {
+                        if (l0 + (j + 1) * NT - 1 <= h) continue;      // CTA-uniform
                         const double W = ((sgh[gi] + t[j]) + c[gi][j]) + 2.0 * p3[j];
                         if (LISTS) {
                             const bool cand = W >= top.gate;
                             if (__any_sync(0xffffffffu, cand))
-                                top.offer(cand, W, scan_key(3, g0 + gi, h, l0 + tid + j * SCAN_NT), lane);
+                                top.offer(cand, W, scan_key(3, g0 + gi, h, l0 + tid + j * NT), lane);
                         } else {
                             best = fmax(best, W);
                         }
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(SCAN_NT, 2) k_scan3(const __grid_constant__ Sc
         else publish_best(pa.best + b, best);
     }
     if (LISTS) {
-        const size_t slot = (size_t)((gridDim.x + blockIdx.x) * (SCAN_NT / 32) + wid) * SCAN_NL;      // after the k_scan12 lists
+        const size_t slot = (size_t)((gridDim.x + blockIdx.x) * (NT / 32) + wid) * SCAN_NL;      // after the k_scan12 lists
         top.store(pa.outW + slot, pa.outKey + slot, lane);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -538,7 +539,7 @@ extern "C" int sdx_scan_range(sdx_ctx *c, int profile, int k, int topn, int g_lo
     timer.count();
     int used_lists = grid12 * (SCAN_NT / 32);
     if (k >= 3 && F >= 3) {
-        k_scan3<true><<<grid3, SCAN_NT, 0, c->stream>>>(a);
+        k_scan3<true, SCAN_NT, SCAN_NJ><<<grid3, SCAN_NT, 0, c->stream>>>(a);
         timer.count();
         used_lists = n_lists;
     }
@@ -682,7 +683,9 @@ int sdx_null_pvalue_maxk(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nu
         ScanArgs a{};
         a.feat = feat; a.fstride = wprS; a.samp = samp; a.sstride = wprF; a.pos = d_pos; a.wpos = d_wpos; a.s1 = d_s1;
         a.T = (const double *)p_T; a.Fp = Fp; a.F = F; a.S = S; a.wprS = wprS; a.k = kp[p];
-        a.g_lo = 0; a.g_hi = F; a.gt0 = 0; a.n_gt = ceil_div(F, SCAN_GT); a.n_hb = ceil_div(F, SCAN_HB); a.n_lc = ceil_div(F, SCAN_NT * SCAN_NJ);
+        const bool narrow = F <= 512;                      // few features: 128-thread CTAs, 512-wide l-chunks
+        a.g_lo = 0; a.g_hi = F; a.gt0 = 0; a.n_gt = ceil_div(F, SCAN_GT); a.n_hb = ceil_div(F, SCAN_HB);
+        a.n_lc = ceil_div(F, narrow ? 128 * SCAN_NJ : SCAN_NT * SCAN_NJ);
         a.nb = nb; a.feat_b = feat_b; a.samp_b = samp_b; a.s1_b = (size_t)F; a.T_b = (size_t)F * Fp;
         a.best = d_best; a.item_counter = d_item;
         if ((int64_t)a.n_gt * a.n_hb * a.n_lc * nb >= (1ll << 31)) return sdx_fail(c, SDX_ERR_UNSUPPORTED, "too many scan work items");
@@ -694,7 +697,8 @@ int sdx_null_pvalue_maxk(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nu
         k_scan12_max<<<dim3(std::max(1, std::min(F, c->sm_count * 2 / std::max(1, nb) + 1)), nb), SCAN_NT, 0, c->stream>>>(a);
         c->total_launches++; c->timing.launches++;
         if (kp[p] >= 3 && F >= 3) {
-            k_scan3<false><<<grid3, SCAN_NT, 0, c->stream>>>(a);
+            if (narrow) k_scan3<false, 128, SCAN_NJ><<<c->sm_count * 4, 128, 0, c->stream>>>(a);
+            else k_scan3<false, SCAN_NT, SCAN_NJ><<<grid3, SCAN_NT, 0, c->stream>>>(a);
             c->total_launches++; c->timing.launches++;
         }
         SDX_CUDA(c, cudaGetLastError());
