@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 NULLS_PER_STEP = 100_000
 SEED = 1764          # the reference's default -rs (src/generate_null_matrices.py:32)
 POPC_PEAK_NOMINAL = 148 * 16 * 1.965e9     # 32-bit popc/s
-NCU_DRAM_BYTES_PER_NULL = (124.152576e6 + 3.602176e6) / 4000    # profiles/r01_k_trade_ncu_summary.md (r1f): the trade plan, 16 B per trade
+NCU_DRAM_BYTES_PER_NULL = (62717952.0 + 299264.0) / 4000         # profiles/r01_k_trade_traffic_g.csv: the trade plan, 8 B per trade
 
 
 def workload():
@@ -302,12 +302,12 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_trade", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_NULL * (n / -(-n // 32768)),
-                         "traffic_source": "ncu --set full capture profiles/r01_k_trade_f.ncu-rep: dram read+write per null x nulls per launch",
+                         "traffic_source": "ncu capture profiles/r01_k_trade_traffic_g.csv (dram__bytes_read.sum + dram__bytes_write.sum of one 4000-null launch): per null x nulls per launch",
                          "peak_source": peaks_src,
                          "bytes_per_null": bytes_per_null, "avg_launch_ms": avg_launch_ms,
                          "kernel_share_of_step": trade_ms / ms, "plan_share_of_step": plan_ms / ms,
                          "popc_per_s": popc_per_null * value / world, "popc_frac_of_nominal": popc_per_null * value / world / POPC_PEAK_NOMINAL,
-                         "note": "working set is shared-memory resident: algorithmic bytes are SMEM row transfers, compulsory HBM traffic is ~0"},
+                         "note": "working set is shared-memory resident: algorithmic bytes are SMEM row transfers; the only compulsory HBM traffic of the kernel is the trade plan (traffic)"},
             "clocks": sampler.summary(),
             "exceedances": int(counts.item()), "p_value": float(counts.item()) / total_nulls,
             "wall_s_timed_region": wall,

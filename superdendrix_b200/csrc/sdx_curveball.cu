@@ -126,7 +126,7 @@ __device__ __forceinline__ int trade_class(int sa, int sb, int ts) {
 
 __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const uint32_t *__restrict__ pairs,
                             const uint16_t *__restrict__ lvl, const int *__restrict__ depth, const int *__restrict__ rowsize,
-                            const uint32_t *__restrict__ desc, int ts, uint4 *__restrict__ plan, uint16_t *__restrict__ offs,
+                            const uint32_t *__restrict__ desc, int ts, void *__restrict__ plan, uint16_t *__restrict__ offs,
                             int offs_stride) {
     extern __shared__ uint32_t hist_smem[];        // per warp: dcap * SDX_NCLS + 2 bins
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -135,13 +135,16 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
     const int D = depth[n];
     uint32_t *hist = hist_smem + (size_t)wid * (dcap * SDX_NCLS + 2);
     const uint16_t *lv = lvl + (size_t)n * T;
-    uint4 *out = plan + (size_t)n * T;          // (a | b << 16, t, descriptor of a, descriptor of b)
+    // plan entry: (a | b << 16, t) for k_trade; (a | b << 16, t, descriptor of a, descriptor of b) for k_trade_sparse
+    uint2 *out2 = reinterpret_cast<uint2 *>(plan) + (size_t)n * T;
+    uint4 *out4 = reinterpret_cast<uint4 *>(plan) + (size_t)n * T;
+    auto emit = [&](uint32_t pos, uint32_t e, uint32_t t) {
+        if (desc) out4[pos] = make_uint4(e, t, desc[e & 0xffffu], desc[e >> 16]);
+        else out2[pos] = make_uint2(e, t);
+    };
     const uint32_t *pr = pairs + (size_t)n * Tp;
     if (D >= dcap) {            // very deep schedule: fall back to the sequential order (always valid)
-        for (int t = lane; t < T; t += 32) {
-            const uint32_t e = pr[t];
-            out[t] = make_uint4(e, (uint32_t)t, desc ? desc[e & 0xffffu] : 0u, desc ? desc[e >> 16] : 0u);
-        }
+        for (int t = lane; t < T; t += 32) emit((uint32_t)t, pr[t], (uint32_t)t);
         return;                 // k_trade runs such a null one trade per level, in order
     }
     const int NB = D * SDX_NCLS;                       // bin = (level - 1) * NCLS + class
@@ -175,7 +178,7 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
     for (int t = lane; t < T; t += 32) {
         const uint32_t e = pr[t];
         uint32_t pos = atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16], ts)], 1u);
-        out[pos] = make_uint4(e, (uint32_t)t, desc ? desc[e & 0xffffu] : 0u, desc ? desc[e >> 16] : 0u);
+        emit(pos, e, (uint32_t)t);
     }
 }
 
@@ -201,7 +204,7 @@ struct TradeArgs {
     const uint32_t *observed;         // R x RS
     uint32_t *work;                   // gridDim.x x R x RS (global-resident variant only)
     uint32_t *carry;                  // n_units x R x RS: chain state between launches (or null)
-    const uint4 *plan;                // n_local x T: (a | b << 16, t, descriptor of a, descriptor of b)
+    const void *plan;                 // n_local x T: uint2 (a | b << 16, t), or uint4 with the two row descriptors (sparse layout)
     const uint16_t *offs;             // n_local x offs_stride level offsets
     int dcap;                         // schedules at least this deep run in sequential order
     const int *depth;                 // n_local
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : (LB == 4 ? 19
             // ---- trades, level by level -------------------------------------
             unsigned int my_applied = 0;
             if (T > 0) {
-                const uint4 *pl = p.plan + (size_t)local * T;
+                const uint2 *pl = reinterpret_cast<const uint2 *>(p.plan) + (size_t)local * T;
                 const uint16_t *of = p.offs + (size_t)local * p.offs_stride;
                 int D = p.depth[local];
                 const bool seq = D >= p.dcap;            // very deep schedule: one trade per level, in order
@@ -265,10 +268,10 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : (LB == 4 ? 19
                 auto OFF = [&](int lv) -> int { return seq ? lv : (int)of[2 * lv]; };
                 int l = 0, base = OFF(0), e = OFF(1);
                 int e2 = (D >= 2) ? OFF(2) : e;
-                const uint4 none = make_uint4(0u, 0u, 0u, 0u);
-                uint4 ent_n = (base + myg < e) ? pl[base + myg] : none;
+                const uint2 none = make_uint2(0u, 0u);
+                uint2 ent_n = (base + myg < e) ? pl[base + myg] : none;
                 while (l < D) {
-                    const uint4 ent = ent_n;
+                    const uint2 ent = ent_n;
                     const bool act = base + myg < e;
                     int nbase = base + NG, nl = l, ne = e;
                     const bool level_end = nbase >= e;
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(32, SP_MINB) k_trade_sparse(const __grid_const
 
             unsigned int my_applied = 0;
             if (T > 0) {
-                const uint4 *pl = p.plan + (size_t)local * T;
+                const uint4 *pl = reinterpret_cast<const uint4 *>(p.plan) + (size_t)local * T;
                 const uint16_t *of = p.offs + (size_t)local * p.offs_stride;
                 int D = p.depth[local];
                 const bool seq = D >= p.dcap;            // very deep schedule: one trade per level, in order
@@ -739,7 +742,7 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
         const size_t lvl_bytes = ((sizeof(uint16_t) * (size_t)n_local_max * Tn + 15) / 16) * 16;
         if ((rc = sdx_scratch(c, SL_LVL, lvl_bytes + sizeof(int) * n_local_max + 64, &p_lvl))) return rc;
         int *d_depth = (int *)((char *)p_lvl + lvl_bytes);
-        if ((rc = sdx_scratch(c, SL_PLAN, sizeof(uint4) * (size_t)n_local_max * Tn, &p_plan))) return rc;
+        if ((rc = sdx_scratch(c, SL_PLAN, (sparse ? sizeof(uint4) : sizeof(uint2)) * (size_t)n_local_max * Tn, &p_plan))) return rc;
         void *p_pairs;
         const int Tp = (Tn + 3) & ~3;                       // pairs row length: 16-byte aligned rows
         if ((rc = sdx_scratch(c, SL_PAIRS, sizeof(uint32_t) * (size_t)n_local_max * Tp + 64, &p_pairs))) return rc;
@@ -777,14 +780,14 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
                     k_plan_sort<<<ceil_div(n_local, sort_warps), sort_warps * 32, sort_smem_warp * sort_warps, c->stream>>>(
                                                                           n_local, R, (int)T, Tp, dcap, (const uint32_t *)p_pairs,
                                                                           (const uint16_t *)p_lvl, d_depth, c->d_rowsize, sparse ? c->d_sp_desc : nullptr,
-                                                                          sparse ? SP_TS : -1, (uint4 *)p_plan,
+                                                                          sparse ? SP_TS : -1, p_plan,
                                                                           (uint16_t *)p_offs, offs_stride);
                     timer.count(3);
                 }
                 cudaEventRecord(c->ev[3], c->stream);
                 TradeArgs ta{};
                 ta.keys = keys; ta.ix = ix; ta.observed = c->d_trade_obs; ta.work = (uint32_t *)p_work;
-                ta.carry = (uint32_t *)p_carry; ta.plan = (const uint4 *)p_plan; ta.n_units = (int)nch;
+                ta.carry = (uint32_t *)p_carry; ta.plan = p_plan; ta.n_units = (int)nch;
                 ta.offs = (const uint16_t *)p_offs; ta.depth = d_depth; ta.offs_stride = offs_stride; ta.dcap = dcap;
                 ta.R = R; ta.RS = RS; ta.T = (int)T; ta.wprL = c->wprL;
                 ta.save_carry = need_carry && sg + 1 < n_segs;
