@@ -123,6 +123,16 @@ int sdx_trade_shape(const sdx_ctx *ctx, int *n_rows, int *n_bits, int *words_per
 int sdx_curveball(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
                   int64_t chain_len, uint32_t *out_trade_rows, int64_t *applied);
 
+/* Burn-in.  5*min(S,F) trades do not mix the dense rows: the reference's single chain is
+ * stationary only because null i has already seen (i+1) rounds (src/generate_null_matrices.py:73-74).  With
+ * burn_rounds > 0 every chain starts, instead of from the observed matrix, from one of pool_size start states:
+ * state j = the observed matrix after burn_rounds rounds of n_trades trades drawn from reserved stream ids
+ * ((2^61 / burn_rounds + j) * burn_rounds + r, r < burn_rounds); chain c uses state c % pool_size.  Null i keeps the
+ * stream id i, so results still depend only on (seed, i, chain_len, burn_rounds, pool_size) and not on batching or
+ * on the GPU count.  The pool is built on first use and cached until the matrix, the seed or n_trades change.
+ * burn_rounds = 0 (default) starts every chain from the observed matrix. */
+int sdx_set_burn_in(sdx_ctx *ctx, int64_t burn_rounds, int pool_size);
+
 /* Replay of a recorded schedule (parity with the reference under its own
  * random draws): trade t exchanges rows a[t], b[t]; to_a[t] (words_per_row
  * words) holds the symmetric-difference elements given to row a, i.e.

@@ -99,16 +99,17 @@ def trade_pair(seed, null_id, t, R):
     return a.value, b.value
 
 
-def curveball_nulls(observed, seed, null0, n, n_trades, chain_len=1, want_matrices=True):
+def curveball_nulls(observed, seed, null0, n, n_trades, chain_len=1, want_matrices=True, burn=0, pool_size=1024):
     """observed: (R, wpr) uint32 packed rows over the longer dimension.
+    burn > 0: chains start from the burn-in pool (see sdx_oracle.c).
     Returns (nulls (n, R, wpr) or None, applied (n,))."""
     obs = _u32(observed)
     R, wpr = obs.shape
     out = np.zeros((n, R, wpr), dtype=np.uint32) if want_matrices else None
     applied = np.zeros(n, dtype=np.int64)
-    lib().sdxo_curveball_nulls(_p(obs, C.c_uint32), C.c_int(R), C.c_int(wpr), C.c_uint64(seed),
-                               C.c_uint64(null0), C.c_int64(n), C.c_int64(n_trades), C.c_int64(chain_len),
-                               _p(out, C.c_uint32), _p(applied, C.c_int64))
+    lib().sdxo_curveball_nulls_burn(_p(obs, C.c_uint32), C.c_int(R), C.c_int(wpr), C.c_uint64(seed),
+                                    C.c_uint64(null0), C.c_int64(n), C.c_int64(n_trades), C.c_int64(chain_len),
+                                    C.c_int64(burn), C.c_int(pool_size), _p(out, C.c_uint32), _p(applied, C.c_int64))
     return out, applied
 
 

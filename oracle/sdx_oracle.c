@@ -247,29 +247,57 @@ SDXO_API int64_t sdxo_curveball(uint32_t *rows, int R, int wpr, uint64_t seed, u
 }
 
 /* The null-driver loop of src/generate_null_matrices.py:71-74: nulls
- * null0 .. null0+n-1; null i starts from the observed matrix when
- * i % chain_len == 0 and from null i-1 otherwise (chain_len = n reproduces the
- * reference's single Markov chain over the mutable `presence`, chain_len = 1
- * the independent restarts of src/curveball_main.py:136).  out = n packed
- * matrices (may be NULL); applied[n] optional. */
-SDXO_API void sdxo_curveball_nulls(const uint32_t *observed, int R, int wpr, uint64_t seed,
-                                   uint64_t null0, int64_t n, int64_t n_trades, int64_t chain_len,
-                                   uint32_t *out, int64_t *applied) {
+ * null0 .. null0+n-1; null i starts a new chain when i % chain_len == 0 and
+ * continues from null i-1 otherwise (chain_len = n reproduces the reference's
+ * single Markov chain over the mutable `presence`, chain_len = 1 the
+ * independent restarts of src/curveball_main.py:136).
+ * Burn-in: with burn > 0 a chain does not start from the
+ * observed matrix but from start state (c % pool_size) of its chain index c,
+ * where state j = the observed matrix after `burn` rounds drawn from the
+ * reserved stream ids ((2^61 / burn + j) * burn + r), r < burn.
+ * out = n packed matrices (may be NULL); applied[n] optional. */
+SDXO_API void sdxo_curveball_nulls_burn(const uint32_t *observed, int R, int wpr, uint64_t seed,
+                                        uint64_t null0, int64_t n, int64_t n_trades, int64_t chain_len,
+                                        int64_t burn, int pool_size, uint32_t *out, int64_t *applied) {
     size_t msz = (size_t)R * wpr;
     uint32_t *cur = (uint32_t *)malloc(sizeof(uint32_t) * msz);
+    uint32_t **pool = NULL;
+    if (burn > 0) pool = (uint32_t **)calloc((size_t)pool_size, sizeof(uint32_t *));
     for (int64_t i = 0; i < n; ++i) {
         uint64_t id = null0 + (uint64_t)i;
         if (i == 0 || id % (uint64_t)chain_len == 0) {
-            memcpy(cur, observed, sizeof(uint32_t) * msz);
+            uint64_t chain = id / (uint64_t)chain_len;
+            if (burn > 0) {
+                int j = (int)(chain % (uint64_t)pool_size);
+                if (!pool[j]) {
+                    pool[j] = (uint32_t *)malloc(sizeof(uint32_t) * msz);
+                    memcpy(pool[j], observed, sizeof(uint32_t) * msz);
+                    uint64_t base = ((1ull << 61) / (uint64_t)burn + (uint64_t)j) * (uint64_t)burn;
+                    for (int64_t r = 0; r < burn; ++r) sdxo_curveball(pool[j], R, wpr, seed, base + (uint64_t)r, n_trades);
+                }
+                memcpy(cur, pool[j], sizeof(uint32_t) * msz);
+            } else {
+                memcpy(cur, observed, sizeof(uint32_t) * msz);
+            }
             /* a shard that starts inside a chain replays the chain prefix */
-            for (uint64_t j = id - id % (uint64_t)chain_len; j < id; ++j)
-                sdxo_curveball(cur, R, wpr, seed, j, n_trades);
+            for (uint64_t q = chain * (uint64_t)chain_len; q < id; ++q)
+                sdxo_curveball(cur, R, wpr, seed, q, n_trades);
         }
         int64_t ap = sdxo_curveball(cur, R, wpr, seed, id, n_trades);
         if (applied) applied[i] = ap;
         if (out) memcpy(out + (size_t)i * msz, cur, sizeof(uint32_t) * msz);
     }
+    if (pool) {
+        for (int j = 0; j < pool_size; ++j) free(pool[j]);
+        free(pool);
+    }
     free(cur);
+}
+
+SDXO_API void sdxo_curveball_nulls(const uint32_t *observed, int R, int wpr, uint64_t seed,
+                                   uint64_t null0, int64_t n, int64_t n_trades, int64_t chain_len,
+                                   uint32_t *out, int64_t *applied) {
+    sdxo_curveball_nulls_burn(observed, R, wpr, seed, null0, n, n_trades, chain_len, 0, 0, out, applied);
 }
 
 /* Replay of a recorded reference schedule: trade t uses

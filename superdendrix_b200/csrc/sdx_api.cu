@@ -66,6 +66,9 @@ static void free_matrix(sdx_ctx *c) {
     c->d_rowsize = nullptr;
     c->d_sp_desc = c->d_sp_obs = nullptr;
     c->sp_state = 0;
+    if (c->d_pool) cudaFree(c->d_pool);
+    c->d_pool = nullptr;
+    c->pool_valid = false;
 }
 
 static void free_weights(sdx_ctx *c) {
@@ -93,6 +96,16 @@ extern "C" int sdx_set_stream(sdx_ctx *c, void *s) {
     if (!c) return SDX_ERR_INVALID;
     cudaStreamSynchronize(c->stream);
     c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return SDX_OK;
+}
+
+extern "C" int sdx_set_burn_in(sdx_ctx *c, int64_t burn_rounds, int pool_size) {
+    if (!c) return SDX_ERR_INVALID;
+    SDX_REQUIRE(c, burn_rounds >= 0 && burn_rounds <= 256, SDX_ERR_INVALID, "burn_rounds must be in 0..256");
+    SDX_REQUIRE(c, burn_rounds == 0 || (pool_size >= 1 && pool_size <= 65536), SDX_ERR_INVALID, "pool_size must be in 1..65536");
+    if (burn_rounds != c->burn || pool_size != c->pool_size) c->pool_valid = false;
+    c->burn = burn_rounds;
+    c->pool_size = burn_rounds > 0 ? pool_size : 0;
     return SDX_OK;
 }
 

@@ -46,6 +46,14 @@ struct sdx_ctx {
     // sparse layout of the trade rows (sdx_sparse.cuh): 0 = not built yet, 1 = in use, -1 = not applicable
     int sp_state = 0, sp_n_dense = 0, sp_fp_words = 0;
     uint32_t *d_sp_desc = nullptr, *d_sp_obs = nullptr;
+    // burn-in pool (sdx_set_burn_in): pool_size well-mixed start states, each the observed matrix after `burn` rounds
+    int64_t burn = 0;
+    int pool_size = 0;
+    uint32_t *d_pool = nullptr;
+    size_t pool_state_words = 0;
+    bool pool_valid = false;
+    uint64_t pool_seed = 0;
+    int64_t pool_T = 0;
 
     // weights
     int P = 0;

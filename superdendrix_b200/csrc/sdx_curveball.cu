@@ -215,6 +215,8 @@ struct TradeArgs {
     uint32_t *out_rows;               // staging: rows of launch-local null l go to out_rows + l * R * wprL
     unsigned long long *applied;      // (i - ix.null_lo)
     ScoreArgs sc;
+    const uint32_t *pool;             // burn-in pool: pool_size start states in the kernel's state layout, or null
+    int pool_size;
     // sparse layout (k_trade_sparse only)
     const uint32_t *desc;             // R row descriptors
     const uint32_t *obs_state;        // fp_words: observed matrix in the sparse layout
@@ -249,7 +251,8 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : (LB == 4 ? 19
             if (null_id >= p.ix.null_hi) break;
             const bool restart = (null_id % (uint64_t)p.ix.chain_len) == 0;
             if (restart || j == 0) {
-                const uint32_t *src = restart ? p.observed : p.carry + (size_t)u * R * RS;
+                const uint32_t *src = p.carry + (size_t)u * R * RS;
+                if (restart) src = p.pool ? p.pool + (size_t)((null_id / (uint64_t)p.ix.chain_len) % (uint64_t)p.pool_size) * R * RS : p.observed;
                 for (int i = tid; i < nvec; i += blockDim.x)
                     reinterpret_cast<uint4 *>(rows)[i] = reinterpret_cast<const uint4 *>(src)[i];
             }
@@ -372,7 +375,8 @@ __global__ void __launch_bounds__(32, SP_MINB) k_trade_sparse(const __grid_const
             if (null_id >= p.ix.null_hi) break;
             const bool restart = (null_id % (uint64_t)p.ix.chain_len) == 0;
             if (restart || j == 0) {
-                const uint32_t *src = restart ? p.obs_state : p.carry + (size_t)u * p.fp_words;
+                const uint32_t *src = p.carry + (size_t)u * p.fp_words;
+                if (restart) src = p.pool ? p.pool + (size_t)((null_id / (uint64_t)p.ix.chain_len) % (uint64_t)p.pool_size) * p.fp_words : p.obs_state;
                 for (int i = lane; i < nvec; i += 32)
                     reinterpret_cast<uint4 *>(state)[i] = reinterpret_cast<const uint4 *>(src)[i];
             }
@@ -651,12 +655,40 @@ static int sparse_layout(sdx_ctx *c) {
 }
 
 // The common driver behind sdx_curveball and sdx_null_pvalue (stat = fixed).
+static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
+                          uint32_t *out_rows, int64_t *applied, const HostScore *hs, uint32_t *save_states, bool use_pool);
+
+#define SDX_POOL_BASE (1ull << 61)      // stream ids of the burn-in rounds live above every null index
+
+// The burn-in pool of sdx_set_burn_in: pool_size chains of `burn` rounds from the observed matrix; their final states
+// (in the trade kernel's own state layout) are the start states of the real chains.  Cached per (seed, T).
+static int ensure_pool(sdx_ctx *c, uint64_t seed, int64_t T, size_t state_words) {
+    if (c->burn <= 0) return SDX_OK;
+    if (c->pool_valid && c->pool_seed == seed && c->pool_T == T && c->pool_state_words == state_words) return SDX_OK;
+    if (c->d_pool) cudaFree(c->d_pool);
+    c->d_pool = nullptr;
+    c->pool_valid = false;
+    SDX_CUDA(c, cudaMalloc(&c->d_pool, sizeof(uint32_t) * state_words * (size_t)c->pool_size));
+    const uint64_t base_chain = SDX_POOL_BASE / (uint64_t)c->burn;
+    int rc = run_nulls_impl(c, seed, base_chain * (uint64_t)c->burn, (int64_t)c->pool_size * c->burn, T, c->burn, nullptr, nullptr, nullptr,
+                            c->d_pool, false);
+    if (rc) return rc;
+    c->pool_valid = true; c->pool_seed = seed; c->pool_T = T; c->pool_state_words = state_words;
+    return SDX_OK;
+}
+
 int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
                   uint32_t *out_rows, int64_t *applied, const HostScore *hs) {
+    return run_nulls_impl(c, seed, null0, n_nulls, n_trades, chain_len, out_rows, applied, hs, nullptr, true);
+}
+
+static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
+                          uint32_t *out_rows, int64_t *applied, const HostScore *hs, uint32_t *save_states, bool use_pool) {
     SDX_REQUIRE(c, c->d_trade_obs, SDX_ERR_STATE, "sdx_upload_matrix has not been called");
     SDX_REQUIRE(c, n_nulls >= 0 && chain_len >= 1, SDX_ERR_INVALID, "n_nulls must be >= 0 and chain_len >= 1");
     SDX_REQUIRE(c, c->R >= 2, SDX_ERR_INVALID, "Curveball needs at least two trade rows");
-    SDX_REQUIRE(c, null0 + (uint64_t)n_nulls < (1ull << 62), SDX_ERR_INVALID, "null index out of range");
+    SDX_REQUIRE(c, null0 + (uint64_t)n_nulls < (1ull << 62) && (!use_pool || null0 + (uint64_t)n_nulls <= SDX_POOL_BASE), SDX_ERR_INVALID,
+                "null index out of range");
     const int64_t T = n_trades < 0 ? 5 * (int64_t)(c->S < c->F ? c->S : c->F) : n_trades;
     SDX_REQUIRE(c, T <= 60000, SDX_ERR_UNSUPPORTED, "more than 60000 trades per null are not supported");
     TradeConfig cfg;
@@ -667,9 +699,13 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
     const size_t sp_scr = std::max(sizeof(uint32_t) * SP_GPW * 2 * (size_t)c->RS, sizeof(uint16_t) * 2 * (SP_TS + 1) * 32);
     const size_t sp_smem = sparse ? sizeof(uint32_t) * (size_t)c->sp_fp_words + sp_scr : 0;
 
+    const int R = c->R, RS = c->RS;
+    if (use_pool && c->burn > 0) {
+        const int64_t Tp_ = n_trades < 0 ? 5 * (int64_t)(c->S < c->F ? c->S : c->F) : n_trades;
+        if ((rc = ensure_pool(c, seed, Tp_, sparse ? (size_t)c->sp_fp_words : (size_t)R * RS))) return rc;
+    }
     LaunchTimer timer(c);
     const PhiloxKeys keys = make_keys(seed);
-    const int R = c->R, RS = c->RS;
     const size_t mat_words = sparse ? (size_t)c->sp_fp_words : (size_t)R * RS;      // state of one chain (carry buffer)
     const size_t out_per = (size_t)R * c->wprL;
 
@@ -751,6 +787,7 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
             if ((rc = sdx_scratch(c, SL_AUX, sizeof(uint16_t) * nb * R, &p_aux))) return rc;
         }
         const bool need_carry = n_segs > 1;
+        SDX_REQUIRE(c, !save_states || n_segs == 1, SDX_ERR_INVALID, "burn-in chains must fit one segment");
         if (need_carry && (rc = sdx_scratch(c, SL_CARRY, sizeof(uint32_t) * mat_words * chains_per_launch, &p_carry))) return rc;
         if (out_rows && (rc = sdx_scratch(c, SL_OUT, sizeof(uint32_t) * out_per * n_local_max, &p_out))) return rc;
         if (applied) {
@@ -791,6 +828,9 @@ int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, in
                 ta.offs = (const uint16_t *)p_offs; ta.depth = d_depth; ta.offs_stride = offs_stride; ta.dcap = dcap;
                 ta.R = R; ta.RS = RS; ta.T = (int)T; ta.wprL = c->wprL;
                 ta.save_carry = need_carry && sg + 1 < n_segs;
+                if (save_states) { ta.carry = save_states + (size_t)cb * mat_words; ta.save_carry = 1; }
+                ta.pool = (use_pool && c->burn > 0) ? c->d_pool : nullptr;
+                ta.pool_size = c->pool_size;
                 ta.out_rows = (uint32_t *)p_out; ta.applied = (unsigned long long *)p_app; ta.sc = sc;
                 const int grid = (int)(nch < grid_cap ? nch : grid_cap);
                 cudaError_t e;

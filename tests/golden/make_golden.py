@@ -18,6 +18,7 @@ pins are made here from the reference's own functions:
   ranksum.npz           scipy.stats.ranksums (utils/compute_p_value.py:306-318).
   loader.json           src/i_o.py:18-88 on a small TSV with every filter.
   generator/            src/generate_null_matrices.py run as a subprocess.
+  nulldist.npz          null distribution of SuperW of a fixed module over 2000 nulls of the reference's own chain.
 
 Nothing from the reference is copied into the repo: only inputs and outputs.
 """
@@ -309,7 +310,39 @@ def make_generator():
     print("generator/", sorted(os.listdir(d)))
 
 
+def make_nulldist():
+    """Null distribution of the set objective under the REFERENCE's own generator: curve_ball driven as
+    src/generate_null_matrices.py:71-74 drives it (one chain), SuperW (src/superdendrix.py:387-391) of a fixed module on
+    every null.  Pins criterion (3) of the north star — p-values within Monte-Carlo error — against the reference
+    itself rather than against the oracle."""
+    dense, samples, features = synth.feature_matrix(200, 60, 33)
+    S, F = dense.shape
+    w = synth.weights(S, 1, seed=34)[0]
+    module = synth.pick_module(dense, 3)
+    profile = {samples[i]: float(w[i]) for i in range(S)}
+    random.seed(2024)
+    np.random.seed(2024)
+    mat = dense.astype(np.float64)
+    presence = ref_cb.find_presences(mat)
+    n = 2000
+    scores = np.zeros(n)
+    cell = np.zeros(dense.shape)
+    for i in range(n):
+        null = ref_cb.curve_ball(mat, presence)
+        cases = [set(samples[r] for r in np.flatnonzero(null[:, g])) for g in module]
+        scores[i] = ref_sd.SuperW(cases, profile, samples)
+        cell += null
+    obs_cases = [set(samples[r] for r in np.flatnonzero(dense[:, g])) for g in module]
+    np.savez_compressed(os.path.join(HERE, "nulldist.npz"), dense=dense, w=w, module=module, scores=scores,
+                        z_obs=ref_sd.SuperW(obs_cases, profile, samples), cell_mean=cell / n,
+                        python=platform.python_version())
+    print("nulldist.npz", n, "nulls, mean W %.4f sd %.4f" % (scores.mean(), scores.std()))
+
+
 if __name__ == "__main__":
+    if "--nulldist-only" in sys.argv:
+        make_nulldist()
+        sys.exit(0)
     make_curveball()
     make_superw()
     make_scan()
@@ -317,3 +350,4 @@ if __name__ == "__main__":
     make_ranksum()
     make_loader()
     make_generator()
+    make_nulldist()

@@ -771,3 +771,75 @@ def test_trade_pair_rejection_zone_is_covered(eng):
         if x.value != a[t] or y.value != b[t]:
             raise AssertionError("pair %d differs: device (%d, %d) oracle (%d, %d)" % (t, a[t], b[t], x.value, y.value))
     assert (a != b).all() and a.max() < R and b.max() < R
+
+
+# ---------------------------------------------------------------- burn-in pool
+@pytest.mark.parametrize("sparse", ["0", "1"])
+def test_burn_in_pool_matches_oracle(monkeypatch, sparse):
+    """sdx_set_burn_in: chains start from pool states (observed + burn rounds on reserved stream ids); nulls, applied
+    counts and scores equal the oracle's, the pool is rebuilt when the seed changes, shards add up."""
+    monkeypatch.setenv("SDX_TRADE_SPARSE", sparse)
+    cases, _ = curveball_cases()
+    dense = cases["c0_shape"]["dense"]
+    S, F = dense.shape
+    obs = rows_of(dense)
+    R = obs.shape[0]
+    w = synth.weights(S, 2, seed=12)
+    modules = np.array([[0, 1, 2], [5, 9, -1]], dtype=np.int32)
+    with Engine(0) as e2:
+        upload_dense(e2, dense)
+        e2.upload_weights(w)
+        e2.set_burn_in(6, 8)
+        for seed, chain_len, null0, n in ((1764, 5, 3, 17), (99, 1, 0, 11), (1764, 4, 40, 9)):
+            want, want_ap = oracle.curveball_nulls(obs, seed, null0, n, 5 * R, chain_len, burn=6, pool_size=8)
+            got, got_ap = e2.curveball(seed, null0, n, -1, chain_len)
+            assert np.array_equal(got_ap, want_ap) and np.array_equal(got, want), (seed, chain_len)
+        res = e2.null_pvalue(7, 0, 24, modules, chain_len=4, want_scores=True)
+        nulls, _ = oracle.curveball_nulls(obs, 7, 0, 24, 5 * R, 4, burn=6, pool_size=8)
+        frows = bitpack.pack_rows(dense.T)
+        for p in range(2):
+            feats = modules[p][modules[p] >= 0]
+            want_sc = [oracle.score_set(m, S, feats, w[p])[0] for m in nulls]
+            assert np.allclose(res["null_scores"][p], want_sc, rtol=0, atol=1e-9 * np.abs(w[p]).sum())
+        a = e2.null_pvalue(7, 0, 12, modules, chain_len=4, z_obs=res["z_obs"])["n_ge"]
+        b = e2.null_pvalue(7, 12, 12, modules, chain_len=4, z_obs=res["z_obs"])["n_ge"]
+        assert np.array_equal(a + b, res["n_ge"])
+        # the re-optimised statistic draws its nulls from the same pool (small matrix: the oracle scan is brute force)
+        small = (np.random.default_rng(3).random((120, 40)) < 0.12).astype(np.uint8)
+        ws = synth.weights(120, 1, seed=4)
+        upload_dense(e2, small)
+        e2.upload_weights(ws)
+        mk = e2.null_pvalue(7, 0, 6, np.array([[0, 1, 2]], dtype=np.int32), chain_len=3, stat=SDX_STAT_MAXK, want_scores=True)
+        nulls6, _ = oracle.curveball_nulls(rows_of(small), 7, 0, 6, 5 * 40, 3, burn=6, pool_size=8)
+        want_mk = [max(oracle.scan(m, 120, ws[0], 3, 1)[0][0], 0.0) for m in nulls6]
+        assert np.allclose(mk["null_scores"][0], want_mk, rtol=0, atol=1e-9 * np.abs(ws[0]).sum())
+        upload_dense(e2, dense)
+        e2.set_burn_in(0)                                           # back to chains that start from the observed matrix
+        want, _ = oracle.curveball_nulls(obs, 1764, 0, 4, 5 * R, 1)
+        assert np.array_equal(e2.curveball(1764, 0, 4, -1, 1)[0], want)
+        with pytest.raises(SdxError):
+            e2.set_burn_in(1000, 4)
+
+
+def test_burn_in_removes_the_memory_of_the_observed_matrix(eng):
+    """C0: after 5*min(S,F) trades the densest feature still shares ~440 of its 469 carriers with the observed
+    matrix; the stationary overlap is ~295 (reached after ~30 rounds).  With a burn-in of 32 rounds the nulls are there."""
+    dense, _, _ = synth.feature_matrix(770, 400)
+    S, F = dense.shape
+    upload_dense(eng, dense)
+    R, L, wpr, ras = eng.trade_shape()
+    g = int(np.argmax(dense.sum(0)))
+    obs_row = dense[:, g].astype(np.int64)
+
+    def overlap(burn, chain_len, n):
+        eng.set_burn_in(burn, 64)
+        rows, _ = eng.curveball(5, 0, n, -1, chain_len, want_applied=False)
+        return float((bitpack.unpack_rows(rows[:, g, :], L).astype(np.int64) * obs_row).sum(1).mean())
+    try:
+        raw = overlap(0, 1, 200)
+        mixed = overlap(32, 8, 400)
+        longer = overlap(64, 8, 400)
+    finally:
+        eng.set_burn_in(0)
+    assert raw > mixed + 80                       # restart nulls remember the observed matrix
+    assert abs(mixed - longer) < 6                # 32 rounds are enough: doubling the burn-in changes nothing

@@ -254,3 +254,56 @@ def test_refport_loader_matches_reference():
         assert sorted(genes) == c["genes"] and list(patients) == c["patients"]
         assert {g: sorted(v) for g, v in g2c.items()} == c["geneToCases"]
         assert {p: sorted(v) for p, v in p2g.items()} == c["patientToGenes"]
+
+
+# ---------------------------------------------------------------- null distribution of the reference's own generator
+def _autocorr_inflation(x, max_lag=20):
+    """Variance inflation of the mean of a (weakly) autocorrelated series: 1 + 2 * sum of positive autocorrelations."""
+    x = np.asarray(x, dtype=np.float64) - np.mean(x)
+    v = float(np.dot(x, x))
+    rho = [float(np.dot(x[:-k], x[k:])) / v for k in range(1, max_lag + 1)]
+    return 1.0 + 2.0 * sum(r for r in rho if r > 0)
+
+
+def _null_sample(obs, S, F, module, w, n, **kw):
+    nulls, _ = oracle.curveball_nulls(obs, 31337, 0, n, 5 * obs.shape[0], **kw)
+    ras = F >= S
+    L = max(S, F)
+    sc = np.array([oracle.score_set(bitpack.pack_rows(bitpack.unpack_rows(m, L).T) if ras else m, S, module, w)[0] for m in nulls])
+    occ = np.mean([bitpack.unpack_rows(m, L) if ras else bitpack.unpack_rows(m, L).T for m in nulls], axis=0)      # S x F
+    return sc, occ
+
+
+def test_canonical_nulls_follow_the_reference_null_distribution():
+    """north star (3): with burn-in, the canonical (Philox / Floyd) nulls and the reference's own chain (CPython
+    random; null i has seen i+1 rounds) sample the same null distribution: mean, spread and exceedance probabilities
+    of W and the per-cell occupancy agree within Monte-Carlo error (the reference series is one Markov chain, so its
+    effective sample size is deflated by its autocorrelation)."""
+    z = load_npz("nulldist.npz")
+    dense, w, module, ref = z["dense"], z["w"], z["module"], z["scores"]
+    S, F = dense.shape
+    obs = rows_of(dense)
+    n = 1500
+    sc, occ = _null_sample(obs, S, F, module, w, n, chain_len=8, burn=24, pool_size=64)
+    infl = _autocorr_inflation(ref)
+    se = np.sqrt(ref.var() * infl / len(ref) + 2 * sc.var() / n)
+    assert abs(sc.mean() - ref.mean()) < 4.5 * se
+    assert 0.85 < sc.std() / ref.std() < 1.18
+    for q in (0.1, 0.5, 0.9):                                  # exceedance probabilities at reference quantiles
+        thr = np.quantile(ref, q)
+        p_ref, p_new = (ref >= thr).mean(), (sc >= thr).mean()
+        sd = np.sqrt(p_ref * (1 - p_ref) * infl / len(ref) + 2 * p_new * (1 - p_new) / n)
+        assert abs(p_ref - p_new) < 4.5 * sd + 0.01
+    diff = np.abs(occ - z["cell_mean"])
+    assert diff.max() < 0.12 and diff.mean() < 0.008
+
+
+def test_without_burn_in_restart_nulls_are_not_mixed():
+    """Why the burn-in exists: 5*min(S,F) trades from the observed matrix leave the dense rows close to where they
+    started (the reference only gets away with it because its nulls form one long chain)."""
+    z = load_npz("nulldist.npz")
+    dense, w, module = z["dense"], z["w"], z["module"]
+    S, F = dense.shape
+    _, occ = _null_sample(rows_of(dense), S, F, module, w, 400, chain_len=1)
+    diff = np.abs(occ - z["cell_mean"])
+    assert diff.max() > 0.3                 # e.g. carriers of the densest feature keep it with p ~0.8 instead of ~0.36
