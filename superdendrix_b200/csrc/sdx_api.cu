@@ -69,6 +69,16 @@ static void free_matrix(sdx_ctx *c) {
     if (c->d_pool) cudaFree(c->d_pool);
     c->d_pool = nullptr;
     c->pool_valid = false;
+    c->cap_feat = c->cap_samp = c->cap_obs = c->cap_rowsize = c->cap_pool = 0;
+}
+
+// a new matrix invalidates everything derived from the old one; the buffers themselves are kept and reused
+static void invalidate_matrix(sdx_ctx *c) {
+    if (c->d_sp_desc) cudaFree(c->d_sp_desc);
+    if (c->d_sp_obs) cudaFree(c->d_sp_obs);
+    c->d_sp_desc = c->d_sp_obs = nullptr;
+    c->sp_state = 0;
+    c->pool_valid = false;
 }
 
 static void free_weights(sdx_ctx *c) {
@@ -76,6 +86,7 @@ static void free_weights(sdx_ctx *c) {
     if (c->d_mask) cudaFree(c->d_mask);
     if (c->d_nsamp) cudaFree(c->d_nsamp);
     c->d_w = nullptr; c->d_mask = nullptr; c->d_nsamp = nullptr;
+    c->cap_w = c->cap_mask = c->cap_nsamp = 0;
     c->P = 0;
 }
 
@@ -175,10 +186,11 @@ extern "C" int sdx_upload_matrix(sdx_ctx *c, const uint32_t *rows, int F, int S,
             SDX_REQUIRE(c, (rows[(size_t)g * wpr + wpr - 1] & pad) == 0, SDX_ERR_INVALID, "padding bits of a feature row are not zero");
     }
     SDX_CUDA(c, cudaSetDevice(c->device));
-    free_matrix(c);
+    invalidate_matrix(c);
+    if (S != c->S) free_weights(c);          // weights are per sample: a matrix over other samples needs new ones
     c->F = F; c->S = S; c->wprS = wpr; c->wprF = (F + 31) / 32;
-    SDX_CUDA(c, cudaMalloc(&c->d_feat, sizeof(uint32_t) * (size_t)F * c->wprS));
-    SDX_CUDA(c, cudaMalloc(&c->d_samp, sizeof(uint32_t) * (size_t)S * c->wprF));
+    SDX_TRY(sdx_reserve(c, c->d_feat, c->cap_feat, sizeof(uint32_t) * (size_t)F * c->wprS));
+    SDX_TRY(sdx_reserve(c, c->d_samp, c->cap_samp, sizeof(uint32_t) * (size_t)S * c->wprF));
     SDX_CUDA(c, cudaMemcpyAsync(c->d_feat, rows, sizeof(uint32_t) * (size_t)F * c->wprS, cudaMemcpyHostToDevice, c->stream));
     SDX_CUDA(c, cudaMemsetAsync(c->d_samp, 0, sizeof(uint32_t) * (size_t)S * c->wprF, c->stream));
     const int tiles = c->wprF * c->wprS;
@@ -190,11 +202,11 @@ extern "C" int sdx_upload_matrix(sdx_ctx *c, const uint32_t *rows, int F, int S,
     c->L = c->rows_are_samples ? F : S;
     c->wprL = c->rows_are_samples ? c->wprF : c->wprS;
     c->RS = ((c->wprL + 3) / 4) * 4;
-    SDX_CUDA(c, cudaMalloc(&c->d_trade_obs, sizeof(uint32_t) * (size_t)c->R * c->RS));
+    SDX_TRY(sdx_reserve(c, c->d_trade_obs, c->cap_obs, sizeof(uint32_t) * (size_t)c->R * c->RS));
     SDX_CUDA(c, cudaMemsetAsync(c->d_trade_obs, 0, sizeof(uint32_t) * (size_t)c->R * c->RS, c->stream));
     SDX_CUDA(c, cudaMemcpy2DAsync(c->d_trade_obs, (size_t)c->RS * 4, c->rows_are_samples ? c->d_samp : c->d_feat,
                                   (size_t)c->wprL * 4, (size_t)c->wprL * 4, c->R, cudaMemcpyDeviceToDevice, c->stream));
-    SDX_CUDA(c, cudaMalloc(&c->d_rowsize, sizeof(int) * (size_t)c->R));
+    SDX_TRY(sdx_reserve(c, c->d_rowsize, c->cap_rowsize, sizeof(int) * (size_t)c->R));
     k_row_sizes<<<ceil_div(c->R, 8), 256, 0, c->stream>>>(c->d_trade_obs, c->R, c->RS, c->d_rowsize);
     c->total_launches++;
     SDX_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -232,10 +244,10 @@ extern "C" int sdx_upload_weights(sdx_ctx *c, const double *w, const uint32_t *m
         hn[p] = cnt;
     }
     SDX_CUDA(c, cudaSetDevice(c->device));
-    free_weights(c);
-    SDX_CUDA(c, cudaMalloc(&c->d_w, sizeof(double) * (size_t)P * S));
-    SDX_CUDA(c, cudaMalloc(&c->d_mask, sizeof(uint32_t) * (size_t)P * wpr));
-    SDX_CUDA(c, cudaMalloc(&c->d_nsamp, sizeof(int) * (size_t)P));
+    c->P = 0;
+    SDX_TRY(sdx_reserve(c, c->d_w, c->cap_w, sizeof(double) * (size_t)P * S));
+    SDX_TRY(sdx_reserve(c, c->d_mask, c->cap_mask, sizeof(uint32_t) * (size_t)P * wpr));
+    SDX_TRY(sdx_reserve(c, c->d_nsamp, c->cap_nsamp, sizeof(int) * (size_t)P));
     SDX_CUDA(c, cudaMemcpyAsync(c->d_w, hw.data(), sizeof(double) * (size_t)P * S, cudaMemcpyHostToDevice, c->stream));
     SDX_CUDA(c, cudaMemcpyAsync(c->d_mask, hm.data(), sizeof(uint32_t) * (size_t)P * wpr, cudaMemcpyHostToDevice, c->stream));
     SDX_CUDA(c, cudaMemcpyAsync(c->d_nsamp, hn.data(), sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, c->stream));

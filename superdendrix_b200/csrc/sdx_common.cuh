@@ -63,6 +63,8 @@ struct sdx_ctx {
 
     // reusable scratch
     DevBuf scratch[16];
+    // capacities (bytes) of the grow-only matrix / weight / pool buffers: re-uploads of the same shape never touch the allocator
+    size_t cap_feat = 0, cap_samp = 0, cap_obs = 0, cap_rowsize = 0, cap_pool = 0, cap_w = 0, cap_mask = 0, cap_nsamp = 0;
 };
 
 inline int sdx_fail(sdx_ctx *c, int code, const std::string &msg) {
@@ -100,6 +102,19 @@ inline int sdx_scratch(sdx_ctx *c, int slot, size_t bytes, void **out) {
     *out = b.p;
     return SDX_OK;
 }
+
+// grow-only typed buffer with its capacity kept in the context
+template <typename T>
+inline int sdx_reserve(sdx_ctx *c, T *&p, size_t &cap, size_t bytes) {
+    if (cap < bytes || !p) {
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        SDX_CUDA(c, cudaMalloc(&p, bytes));
+        cap = bytes;
+    }
+    return SDX_OK;
+}
+#define SDX_TRY(call) do { int rc_ = (call); if (rc_ != SDX_OK) return rc_; } while (0)
 
 struct LaunchTimer {      // CUDA-event bracket on the ctx stream
     sdx_ctx *c;

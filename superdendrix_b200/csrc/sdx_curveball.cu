@@ -524,6 +524,7 @@ __global__ void k_replay(uint32_t *rows, int RS, int wprL, const int32_t *a, con
 // host side
 // ---------------------------------------------------------------------------
 struct TradeConfig {
+    int slots;         // CTAs of the trade kernel resident on the whole GPU (one wave)
     int G, V, LB;
     bool smem;
     int threads;
@@ -568,6 +569,13 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
             if (lb == 0 || (lb == 1 && cfg->threads <= 128) || ((lb == 2 || lb == 3 || lb == 5) && cfg->threads <= 256) || (lb == 4 && cfg->threads <= 192)) cfg->LB = lb;
         }
         cfg->grid_cap = 1 << 30;
+        {
+            int resident = per_sm;                                      // shared memory limit
+            const int by_threads = 2048 / cfg->threads;
+            if (resident > by_threads) resident = by_threads;
+            if (cfg->LB != 0 && resident > (cfg->LB == 3 ? 4 : (cfg->LB == 5 ? 3 : 5))) resident = cfg->LB == 3 ? 4 : (cfg->LB == 5 ? 3 : 5);
+            cfg->slots = resident * c->sm_count;
+        }
     } else {
         cfg->smem_bytes = 0;
         cfg->LB = 0;
@@ -578,6 +586,7 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
         int cap = (int)((size_t)96 * 1024 * 1024 / per);   // working set ~ within L2
         if (cap < c->sm_count) cap = c->sm_count;
         cfg->grid_cap = cap;
+        cfg->slots = cap;
     }
     return SDX_OK;
 }
@@ -665,10 +674,8 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
 static int ensure_pool(sdx_ctx *c, uint64_t seed, int64_t T, size_t state_words) {
     if (c->burn <= 0) return SDX_OK;
     if (c->pool_valid && c->pool_seed == seed && c->pool_T == T && c->pool_state_words == state_words) return SDX_OK;
-    if (c->d_pool) cudaFree(c->d_pool);
-    c->d_pool = nullptr;
     c->pool_valid = false;
-    SDX_CUDA(c, cudaMalloc(&c->d_pool, sizeof(uint32_t) * state_words * (size_t)c->pool_size));
+    SDX_TRY(sdx_reserve(c, c->d_pool, c->cap_pool, sizeof(uint32_t) * state_words * (size_t)c->pool_size));
     const uint64_t base_chain = SDX_POOL_BASE / (uint64_t)c->burn;
     int rc = run_nulls_impl(c, seed, base_chain * (uint64_t)c->burn, (int64_t)c->pool_size * c->burn, T, c->burn, nullptr, nullptr, nullptr,
                             c->d_pool, false);
@@ -751,6 +758,10 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
         const int64_t NB = 32768;                                   // nulls planned per launch
         const int seg_cap = (int)(chain_len < 256 ? chain_len : 256);
         int64_t chains_per_launch = NB / seg_cap;
+        {   // one CTA per chain and every chain of a launch does the same work: launch whole waves to avoid a ragged tail
+            const int64_t slots = sparse ? (int64_t)16 * c->sm_count : (int64_t)cfg.slots;
+            if (slots > 0 && chains_per_launch > slots) chains_per_launch = (chains_per_launch / slots) * slots;
+        }
         if (chains_per_launch > n_chains) chains_per_launch = n_chains;
         const int64_t n_segs = (chain_len + seg_cap - 1) / seg_cap;
         const int64_t n_local_max = chains_per_launch * seg_cap;

@@ -115,14 +115,26 @@ def allgather_array(a, group=None):
 # ---------------------------------------------------------------------------
 # sharded operations.  `engine` is a superdendrix_b200.engine.Engine (or any object with the same methods).
 # ---------------------------------------------------------------------------
-def null_pvalue(engine, seed, n_nulls, modules, null0=0, n_trades=-1, stat=0, z_obs=None, group=None):
-    """Permutation p-values over n_nulls nulls sharded by null index.  Independent restarts (chain_len = 1),
-    so the counts do not depend on the number of ranks.  Returns dict(n_ge, p, z_obs, n_nulls)."""
+def shard_chains(n, chain_len, rank, world):
+    """Null range of a rank as whole chains (so no rank has to replay the prefix of a chain another rank owns)."""
+    n_chains = -(-int(n) // int(chain_len))
+    c_lo, c_hi = shard_range(n_chains, rank, world)
+    return min(c_lo * chain_len, n), min(c_hi * chain_len, n)
+
+
+def null_pvalue(engine, seed, n_nulls, modules, null0=0, n_trades=-1, stat=0, z_obs=None, chain_len=16, burn=32,
+                pool_size=1480, group=None):
+    """Permutation p-values over n_nulls nulls sharded by null index.  Nulls come in short chains (chain_len) that
+    start from burnt-in pool states (Engine.set_burn_in), so every null is a draw from the stationary distribution —
+    what the reference gets from its single long chain — and there are enough chains to fill every GPU.  Streams and
+    pool are keyed on global indices: the counts do not depend on the number of ranks.
+    Returns dict(n_ge, p, z_obs, n_nulls)."""
     rank, world = _world(group)
-    lo, hi = shard_range(n_nulls, rank, world)
+    lo, hi = shard_chains(n_nulls, chain_len, rank, world)
+    engine.set_burn_in(burn, pool_size)
     if z_obs is None:
         z_obs = engine.null_pvalue(seed, 0, 0, modules, n_trades=n_trades, stat=stat)["z_obs"]     # same on every rank
-    res = engine.null_pvalue(seed, null0 + lo, hi - lo, modules, n_trades=n_trades, chain_len=1, stat=stat, z_obs=z_obs)
+    res = engine.null_pvalue(seed, null0 + lo, hi - lo, modules, n_trades=n_trades, chain_len=chain_len, stat=stat, z_obs=z_obs)
     n_ge = allreduce_sum_int64(res["n_ge"], group)
     return {"n_ge": n_ge, "p": n_ge / float(max(n_nulls, 1)), "z_obs": np.asarray(z_obs), "n_nulls": int(n_nulls)}
 

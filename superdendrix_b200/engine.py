@@ -56,7 +56,7 @@ class Engine:
         """Run on a caller-owned CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
         self._check(self._lib.sdx_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)))
 
-    def set_burn_in(self, burn_rounds: int, pool_size: int = 1024):
+    def set_burn_in(self, burn_rounds: int, pool_size: int = 1480):
         """Chains start from one of ``pool_size`` states that have already seen ``burn_rounds`` rounds of trades
         (0 = start from the observed matrix, as a single reference chain does at null 0)."""
         self._check(self._lib.sdx_set_burn_in(self._ctx, int(burn_rounds), int(pool_size)))

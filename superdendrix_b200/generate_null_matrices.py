@@ -5,8 +5,11 @@
 
 Reference flags kept: -m -min_f -max_f -pf -gf -M -o -p -pre -v -rs
 (src/generate_null_matrices.py:16-33).  Added, non-breaking:
-  --mode chained|restart   chained (default) = the reference's single Markov chain per process
-                           (src/generate_null_matrices.py:71-74); restart = independent nulls
+  --mode chained|parallel|restart
+                           chained (default) = the reference's single Markov chain per process
+                           (src/generate_null_matrices.py:71-74); parallel = chains of 16 nulls from burnt-in pool
+                           states (--burn-in rounds; stationary, many chains); restart = every null from the observed
+                           matrix (not mixed for dense features)
   --device N               CUDA device
   --packed FILE.npz        also dump the packed nulls (no TSV parsing needed downstream)
   --no-tsv                 skip the TSV files (with --packed)
@@ -44,7 +47,8 @@ def get_parser():
     parser.add_argument("-pre", "--prefix", type=int, default=0, help="index offset of the output files")
     parser.add_argument("-v", "--verbosity", default=logging.INFO, type=int, help="Flag verbose output")
     parser.add_argument("-rs", "--random_seed", default=1764, type=int, help="Seed for random number generator")
-    parser.add_argument("--mode", default="chained", choices=["chained", "restart"])
+    parser.add_argument("--mode", default="chained", choices=["chained", "parallel", "restart"])
+    parser.add_argument("--burn-in", type=int, default=32, help="burn-in rounds of the pool states (parallel mode)")
     parser.add_argument("--device", type=int, default=0)
     parser.add_argument("--packed", default=None, help="write the packed nulls to this .npz")
     parser.add_argument("--no-tsv", action="store_true")
@@ -52,14 +56,15 @@ def get_parser():
     return parser
 
 
-def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None):
+def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None, burn_in=32):
     """Yields (first global null index, packed feature rows (n, F, ceil(S/32)) uint32) per device batch."""
     S, F = dense.shape
     eng = engine or Engine(device)
     try:
         eng.upload_dense(dense)
         R, L, wpr, rows_are_samples = eng.trade_shape()
-        chain_len = max(int(n_nulls), 1) if mode == "chained" else 1
+        chain_len = {"chained": max(int(n_nulls), 1), "parallel": 16, "restart": 1}[mode]
+        eng.set_burn_in(burn_in if mode == "parallel" else 0, 1480)
         # a chain starts at a multiple of chain_len: with prefix a multiple of n_nulls every process owns one chain
         done = 0
         while done < n_nulls:
@@ -75,10 +80,10 @@ def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, ba
             eng.close()
 
 
-def generate(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None):
+def generate(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None, burn_in=32):
     """Yields (global null index, S x F uint8 matrix) for n_nulls nulls of ``dense`` (S x F)."""
     S = dense.shape[0]
-    for first, rows in generate_packed(dense, n_nulls, seed, prefix, mode, device, batch, engine):
+    for first, rows in generate_packed(dense, n_nulls, seed, prefix, mode, device, batch, engine, burn_in):
         bits = bitpack.unpack_rows(rows, S)           # (n, F, S)
         for i in range(len(rows)):
             yield first + i, bits[i].T
@@ -99,7 +104,7 @@ def main(argv=None):
     dense = dense_matrix(genes, samples, samples_to_genes)
     print(len(samples), len(genes))
     packed, ids = [], []
-    for first, rows in generate_packed(dense, max(args.p_val_it, 0), args.random_seed, args.prefix, args.mode, args.device, args.batch):
+    for first, rows in generate_packed(dense, max(args.p_val_it, 0), args.random_seed, args.prefix, args.mode, args.device, args.batch, burn_in=args.burn_in):
         if not args.no_tsv:
             write_nulls_tsv(args.output_file, first, rows, samples, genes)      # multi-threaded C++ writer, reference format
         if args.packed:

@@ -19,7 +19,11 @@ Added, non-breaking flags:
                             reference's per-null ILP computes, :191).  Default max_k for k <= 3.
   --null-source generate|files   generate: nulls are produced and scored on the GPU, no files;
                             files: read ``<-nm><i>.tsv`` as the reference does (:186).
-  --mode chained|restart    Markov-chain semantics of generated nulls (see generate_null_matrices)
+  --mode parallel|chained|restart   generated nulls: parallel (default) = chains of 16 nulls that start from burnt-in
+                            pool states (32 rounds) — stationary like the reference's long chain and enough chains to
+                            fill the GPUs; chained = ONE chain from the observed matrix, exactly the reference's
+                            semantics (src/generate_null_matrices.py:71-74); restart = every null 5*min(S,F) trades from
+                            the observed matrix (src/curveball_main.py:136; NOT mixed for dense features)
   --device N
 """
 from __future__ import annotations
@@ -91,7 +95,8 @@ def get_parser():
     parser.add_argument("-t", "--threads", type=int, default=-1, help="Number of threads to use ([-1] = all).")
     parser.add_argument("--null-stat", default=None, choices=["fixed", "max_k"])
     parser.add_argument("--null-source", default=None, choices=["generate", "files"])
-    parser.add_argument("--mode", default="restart", choices=["chained", "restart"])
+    parser.add_argument("--mode", default="parallel", choices=["parallel", "chained", "restart"])
+    parser.add_argument("--burn-in", type=int, default=32, help="burn-in rounds of the pool states (parallel mode)")
     parser.add_argument("--device", type=int, default=0)
     return parser
 
@@ -225,7 +230,8 @@ def null_loop(genes, samples, profile, events_to_samples, module, zP, args, logg
         eng.upload_matrix(pack_features(genes, samples, events_to_samples), len(samples))
         eng.upload_weights(w_vec)
         mod = np.array([[gidx[g] for g in module] + [-1] * (max(k, 1) - k)], dtype=np.int32)
-        chain = n if args.mode == "chained" else 1
+        chain, burn = {"parallel": (16, args.burn_in), "chained": (max(n, 1), 0), "restart": (1, 0)}[args.mode]
+        eng.set_burn_in(burn, 1480)
         res = eng.null_pvalue(args.random_seed, 0, n, mod, chain_len=chain, stat=stat, z_obs=np.array([zP]), want_scores=True)
         return int(res["n_ge"][0]), n, res["null_scores"][0]
     # files: <-nm><i>.tsv, restricted to the profiled samples as src/superdendrix.py:186 does.  Read in batches by the

@@ -30,7 +30,7 @@ def _worker(rank, world, port, out_dir):
     from superdendrix_b200 import dist
     dense, w, modules = _inputs()
     eng = OracleEngine(dense, w)
-    pv = dist.null_pvalue(eng, seed=7, n_nulls=37, modules=modules)
+    pv = dist.null_pvalue(eng, seed=7, n_nulls=37, modules=modules, chain_len=4, burn=3, pool_size=5)
     sc = dist.scan(eng, profile=0, k=3, topn=6)
     jobs = np.array([[0, 3, 5], [1, 2, -1], [4, -1, -1], [0, 1, 2], [6, 7, -1]], dtype=np.int32)
     pj = np.array([0, 1, 1, 0, 1], dtype=np.int32)
@@ -50,7 +50,7 @@ def test_two_ranks_reduce_to_the_single_process_result(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     dense, w, modules = _inputs()
     eng = OracleEngine(dense, w)
-    one = dist.null_pvalue(eng, seed=7, n_nulls=37, modules=modules)              # world = 1 path
+    one = dist.null_pvalue(eng, seed=7, n_nulls=37, modules=modules, chain_len=4, burn=3, pool_size=5)      # world = 1 path
     sc1 = eng.scan(0, 3, 6)
     jobs = np.array([[0, 3, 5], [1, 2, -1], [4, -1, -1], [0, 1, 2], [6, 7, -1]], dtype=np.int32)
     pj = np.array([0, 1, 1, 0, 1], dtype=np.int32)

@@ -97,6 +97,13 @@ def test_shard_ranges_cover_and_balance():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_chains_keeps_chains_whole():
+    for n, L, world in ((100, 32, 3), (100000, 32, 8), (5, 32, 4), (64, 1, 2), (0, 16, 2)):
+        r = [dist.shard_chains(n, L, k, world) for k in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(a % L == 0 or a == n for a, _ in r)
+
+
 def test_scan_feature_ranges_balance_work():
     F = 2000
     for world in (1, 2, 4, 8):

@@ -21,7 +21,7 @@ with Engine(local) as eng:
     eng.upload_dense(dense)
     eng.upload_weights(w)
     pv = dist.null_pvalue(eng, 1764, 20001, mods)
-    one = eng.null_pvalue(1764, 0, 20001, mods)["n_ge"]
+    one = eng.null_pvalue(1764, 0, 20001, mods, chain_len=16)["n_ge"]          # dist.null_pvalue has set the same burn-in pool
     assert np.array_equal(pv["n_ge"], one), (pv["n_ge"], one)
     sc = dist.scan(eng, 1, 3, 8)
     whole = eng.scan(1, 3, 8)
