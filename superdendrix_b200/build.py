@@ -22,6 +22,8 @@ UNITS = ["sdx_api", "sdx_score", "sdx_curveball", "sdx_scan", "sdx_stats"]
 HOST_UNITS = ["sdx_io"]          # plain C++ (the host-side format path), compiled by the host compiler through nvcc
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wno-format-truncation", "-Xptxas", "-v"]
+if os.environ.get("SDX_BUILD_DEFINES"):          # debugging only, e.g. SDX_BUILD_DEFINES="-DSDX_SM_DEBUG"
+    NVCC_FLAGS += os.environ["SDX_BUILD_DEFINES"].split()
 
 
 def _nvcc() -> str:

@@ -229,10 +229,12 @@ static __device__ __noinline__ SetScore score_module_call(const uint32_t *rows, 
     return score_module(rows, RS, rows_are_samples, mod, k, w, mask, S, lane);
 }
 
-// LB selects the launch bounds: 0 = (512, 1), 1 = (128, 5), 2 = (256, 5), 3 = (256, 4), 4 = (192, 5), 5 = (256, 3) — all but 0 bound the
-// registers so that five CTAs (five nulls) stay resident per SM when the matrix fits five times in shared memory.
+// LB selects the launch bounds: 0 = (512, 1), 1 = (128, 5), 2 = (256, 5), 3 = (256, 4), 4 = (192, 5), 5 = (256, 3), 6 = (64, 5), 7 = (96, 5) — all
+// but 0 bound the registers so that five CTAs (five nulls) stay resident per SM when the matrix fits five times in shared memory.
+constexpr int lb_threads(int lb) { return lb == 0 ? 512 : (lb == 1 ? 128 : (lb == 4 ? 192 : (lb == 6 ? 64 : (lb == 7 ? 96 : 256)))); }
+constexpr int lb_blocks(int lb) { return lb == 0 ? 1 : (lb == 3 ? 4 : (lb == 5 ? 3 : 5)); }
 template <int G, int V, bool SMEM, int LB>
-__global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : (LB == 4 ? 192 : 256)), LB == 0 ? 1 : (LB == 3 ? 4 : (LB == 5 ? 3 : 5))) k_trade(const __grid_constant__ TradeArgs p) {
+__global__ void __launch_bounds__(lb_threads(LB), lb_blocks(LB)) k_trade(const __grid_constant__ TradeArgs p) {
     extern __shared__ __align__(16) uint32_t smem_rows[];
     __shared__ unsigned int s_applied;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NW = blockDim.x >> 5;
@@ -322,6 +324,250 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : (LB == 1 ? 128 : (LB == 4 ? 19
                 reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(rows)[i];
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Persistent variant (experimental, SDX_TRADE_PERSIST=1; needs the matrix to fit shared memory at least twice): ONE CTA per SM owns NS null
+// slots and its 20 warps pull ROUNDS — the 32/G trades one warp runs in lock step, all of one level of one slot — from
+// a ring queue in shared memory.  A slot publishes the rounds of level l+1 when the last round of level l reports
+// back, so the only thing that ever waits is a slot, never a warp: where k_trade parks a warp at the level barrier of
+// its null, this kernel hands it a round of another null.  Epilogue work (scoring, row output) is queued the same way.
+// Trades, streams and outputs are those of k_trade: results are bit-identical.
+// ---------------------------------------------------------------------------
+#define SM_MAX_SLOTS 8
+#define SM_OFFS_CAP 1024             // staged level offsets per slot (u16): schedules of up to 511 levels
+#define SM_EPI_ROUNDS 4              // epilogue rounds per null
+#define SM_RING 512                  // ring entries (power of two); the host checks that all outstanding rounds fit
+#define SM_THREADS 640
+#ifdef SDX_SM_DEBUG
+#define SM_DBG(...) do { if (lane == 0 && blockIdx.x == 0) printf(__VA_ARGS__); } while (0)
+#else
+#define SM_DBG(...) do { } while (0)
+#endif
+
+struct SmSlot {
+    unsigned int pending;            // rounds of the current level still running or queued
+    unsigned int applied;
+    int level;                       // current level; level == D is the epilogue
+    int D;                           // trade levels of the current null
+    int seq;                         // very deep schedule: one trade per level, in plan order
+    int unit, j, emit;
+    long long local;                 // launch-local null index
+    unsigned long long null_id;
+};
+
+struct SmShared {
+    SmSlot slot[SM_MAX_SLOTS];
+    unsigned long long ring[SM_RING];         // (ticket = index + 1) << 32 | payload
+    unsigned int head, reserve, n_finished;
+};
+
+// payload: slot (bits 0-2) | epilogue flag (bit 3) | trades in the round (bits 4-9) | first plan entry or epilogue round (bits 10-25)
+__device__ __forceinline__ unsigned int sm_payload(int s, int epi, int cnt, int base) {
+    return (unsigned)s | ((unsigned)epi << 3) | ((unsigned)cnt << 4) | ((unsigned)base << 10);
+}
+
+// D, seq: the slot's constants for the current null, read by the caller BEFORE any lane may change the slot (lanes of
+// a warp are not in lock step: a lane that lags must not see what lane 0 writes further down).
+template <int G>
+__device__ __forceinline__ void sm_push_level(SmShared &sh, const uint16_t *of_s, int s, int lv, int D, int seq, int lane) {
+    constexpr int GPW = 32 / G;
+    SmSlot &sl = sh.slot[s];
+    const bool epi = lv == D;
+    int base = 0, e = SM_EPI_ROUNDS * GPW;
+    if (!epi) {
+        base = seq ? lv : (int)of_s[2 * lv];
+        e = seq ? lv + 1 : (int)of_s[2 * lv + 2];
+    }
+    const int nr = (e - base + GPW - 1) / GPW;
+    __syncwarp();
+    unsigned int t0 = 0;
+    if (lane == 0) {
+        sl.level = lv;
+        sl.pending = (unsigned)nr;
+        __threadfence_block();
+        t0 = atomicAdd(&sh.reserve, (unsigned)nr);
+    }
+    t0 = __shfl_sync(0xffffffffu, t0, 0);
+    SM_DBG("push s=%d lv=%d D=%d epi=%d base=%d e=%d nr=%d t0=%u\n", s, lv, D, (int)epi, base, e, nr, t0);
+    for (int i = lane; i < nr; i += 32) {
+        const int b = base + i * GPW;
+        const int cnt = e - b < GPW ? e - b : GPW;
+        const unsigned int pay = epi ? sm_payload(s, 1, 0, i) : sm_payload(s, 0, cnt, b);
+        const unsigned int idx = t0 + (unsigned)i;
+        *reinterpret_cast<volatile unsigned long long *>(&sh.ring[idx & (SM_RING - 1)]) = ((unsigned long long)(idx + 1u) << 32) | pay;
+    }
+    __syncwarp();          // every entry is in the ring before any lane of this warp starts polling it (a lane spinning
+                           // on an entry that a sibling lane still has to write would starve that lane)
+}
+
+// Moves slot s to its next null (or retires it) and queues the first rounds.  One warp, all lanes.
+template <int G>
+__device__ __noinline__ void sm_next_null(const TradeArgs &p, SmShared &sh, uint32_t *rows, uint16_t *of_s, int s, int NS, bool first, int lane) {
+    SmSlot &sl = sh.slot[s];
+    const int R = p.R, RS = p.RS, T = p.T;
+    const int nvec = R * RS / 4;
+    int unit = sl.unit, j = first ? 0 : sl.j + 1;
+    __syncwarp();                      // every lane has read the slot before lane 0 rewrites it below
+    for (;;) {
+        bool have = unit < p.n_units && j < p.ix.seg_len;
+        long long local = 0;
+        unsigned long long null_id = 0;
+        if (have) {
+            local = (long long)unit * p.ix.seg_len + j;
+            null_id = p.ix.id(local);
+            have = null_id < p.ix.null_hi;
+        }
+        if (!have) {
+            if (unit < p.n_units && p.save_carry && !(first && j == 0)) {
+                uint4 *dst = reinterpret_cast<uint4 *>(p.carry + (size_t)unit * R * RS);
+                for (int i = lane; i < nvec; i += 32) dst[i] = reinterpret_cast<const uint4 *>(rows)[i];
+            }
+            if (unit < p.n_units) unit += NS * (int)gridDim.x;
+            j = 0;
+            first = true;
+            if (unit >= p.n_units) {
+                if (lane == 0) { sl.unit = unit; __threadfence_block(); atomicAdd(&sh.n_finished, 1u); }
+                return;
+            }
+            continue;
+        }
+        const bool restart = (null_id % (unsigned long long)p.ix.chain_len) == 0;
+        if (restart || j == 0) {
+            const uint32_t *src = p.carry + (size_t)unit * R * RS;
+            if (restart) src = p.pool ? p.pool + (size_t)((null_id / (unsigned long long)p.ix.chain_len) % (unsigned long long)p.pool_size) * R * RS : p.observed;
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+            uint4 *d4 = reinterpret_cast<uint4 *>(rows);
+            int i = lane;
+            for (; i + 96 < nvec; i += 128) {                  // four loads in flight per lane
+                const uint4 a = s4[i], b = s4[i + 32], c = s4[i + 64], d = s4[i + 96];
+                d4[i] = a; d4[i + 32] = b; d4[i + 64] = c; d4[i + 96] = d;
+            }
+            for (; i < nvec; i += 32) d4[i] = s4[i];
+        }
+        int D = T > 0 ? p.depth[local] : 0;
+        const int seq = D >= p.dcap;
+        if (seq) D = T;
+        else {
+            const uint16_t *of = p.offs + (size_t)local * p.offs_stride;
+            for (int i = lane; i <= 2 * D; i += 32) of_s[i] = of[i];
+        }
+        const int emit = null_id >= p.ix.null_lo;
+        SM_DBG("null s=%d unit=%d j=%d local=%lld id=%llu D=%d seq=%d emit=%d restart=%d\n", s, unit, j, local, null_id, D, seq, emit, (int)restart);
+        if (lane == 0) {
+            sl.unit = unit; sl.j = j; sl.local = local; sl.null_id = null_id; sl.D = D; sl.seq = seq; sl.applied = 0; sl.emit = emit;
+        }
+        __syncwarp();
+        __threadfence_block();
+        const bool has_epi = emit && (p.out_rows || p.sc.n_profiles > 0);
+        if (D > 0 || has_epi) {
+            sm_push_level<G>(sh, of_s, s, 0, D, seq, lane);    // level 0 == D means: epilogue only
+            return;
+        }
+        if (emit && p.applied && lane == 0) p.applied[null_id - p.ix.null_lo] = 0ull;
+        first = false;
+        ++j;
+    }
+}
+
+template <int G, int V>
+__global__ void __launch_bounds__(SM_THREADS, 1) k_trade_sm(const __grid_constant__ TradeArgs p, const int NS) {
+    extern __shared__ __align__(16) uint32_t smem_rows[];
+    __shared__ SmShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int GPW = 32 / G;
+    const int sub = lane & (G - 1), grp = lane / G;
+    const int R = p.R, RS = p.RS, T = p.T;
+    const size_t slot_words = (size_t)R * RS;
+    uint16_t *offs_all = reinterpret_cast<uint16_t *>(smem_rows + (size_t)NS * slot_words);
+
+    if (tid < SM_MAX_SLOTS) {
+        sh.slot[tid].pending = 0; sh.slot[tid].level = 0; sh.slot[tid].D = 0;
+        sh.slot[tid].unit = tid * (int)gridDim.x + (int)blockIdx.x;          // slot s starts with unit s * grid + b
+        sh.slot[tid].j = 0;
+    }
+    if (tid == 0) { sh.head = 0; sh.reserve = 0; sh.n_finished = 0; }
+    for (int i = tid; i < SM_RING; i += blockDim.x) sh.ring[i] = 0ull;
+    __syncthreads();
+    if (wid < NS) sm_next_null<G>(p, sh, smem_rows + (size_t)wid * slot_words, offs_all + (size_t)wid * SM_OFFS_CAP, wid, NS, true, lane);
+
+    for (;;) {
+        // ---- take a round from the queue (lane 0 polls) ---------------------------------------------------------
+        unsigned int pay = 0xffffffffu;
+        if (lane == 0) {
+            for (;;) {
+                const unsigned int h = *reinterpret_cast<volatile unsigned int *>(&sh.head);
+                const unsigned int rsv = *reinterpret_cast<volatile unsigned int *>(&sh.reserve);
+                if ((int)(rsv - h) > 0) {
+                    if (atomicCAS(&sh.head, h, h + 1u) != h) continue;
+                    unsigned long long e;
+                    do { e = *reinterpret_cast<volatile unsigned long long *>(&sh.ring[h & (SM_RING - 1)]); } while ((unsigned int)(e >> 32) != h + 1u);
+                    pay = (unsigned int)e;
+                    break;
+                }
+                if (*reinterpret_cast<volatile unsigned int *>(&sh.n_finished) >= (unsigned)NS) break;
+                __nanosleep(64);
+            }
+        }
+        pay = __shfl_sync(0xffffffffu, pay, 0);
+        if (pay == 0xffffffffu) break;
+        __threadfence_block();
+        const int s = (int)(pay & 7u), epi = (int)((pay >> 3) & 1u), cnt = (int)((pay >> 4) & 63u), base = (int)((pay >> 10) & 0xffffu);
+        SmSlot &sl = sh.slot[s];
+        uint32_t *rows = smem_rows + (size_t)s * slot_words;
+        SM_DBG("take w=%d s=%d epi=%d cnt=%d base=%d local=%lld\n", wid, s, epi, cnt, base, sl.local);
+        const long long local = sl.local;
+        const unsigned long long null_id = sl.null_id;
+
+        if (!epi) {
+            const uint2 *pl = reinterpret_cast<const uint2 *>(p.plan) + (size_t)local * T;
+            const bool act = grp < cnt;
+            const uint2 ent = act ? pl[base + grp] : make_uint2(0u, 0u);
+            const bool ap = trade_rows<G, V>(rows, RS, act, ent.x & 0xffffu, ent.x >> 16, ent.y, null_id, p.keys, sub);
+            if (p.applied) {
+                const unsigned int n_ap = __popc(__ballot_sync(0xffffffffu, ap && sub == 0));
+                if (lane == 0 && n_ap) atomicAdd(&sl.applied, n_ap);
+            }
+        } else if (sl.emit) {
+            const int r = base;                                   // epilogue round r of SM_EPI_ROUNDS
+            if (p.out_rows) {
+                uint32_t *dst = p.out_rows + (size_t)local * R * p.wprL;
+                for (int row = r; row < R; row += SM_EPI_ROUNDS)
+                    for (int c = lane; c < p.wprL; c += 32) dst[(size_t)row * p.wprL + c] = rows[(size_t)row * RS + c];
+            }
+            for (int pr = r; pr < p.sc.n_profiles; pr += SM_EPI_ROUNDS) {
+                SetScore sc = score_module_call(rows, RS, p.sc.rows_are_samples != 0, p.sc.modules + (size_t)pr * p.sc.k, p.sc.k,
+                                                p.sc.w + (size_t)pr * p.sc.S, p.sc.mask + (size_t)pr * p.sc.wprS, p.sc.S, lane);
+                if (lane == 0) {
+                    if (sc.W >= p.sc.z_obs[pr]) atomicAdd(&p.sc.n_ge[pr], 1ull);
+                    if (p.sc.null_scores) p.sc.null_scores[(size_t)pr * p.sc.n_total + (null_id - p.ix.null_lo)] = sc.W;
+                }
+            }
+        }
+
+        // ---- report back; the warp that completes a level moves the slot on ----------------------------------------
+        __syncwarp();
+        unsigned int left = 1;
+        if (lane == 0) { __threadfence_block(); left = atomicSub(&sl.pending, 1u) - 1u; }
+        left = __shfl_sync(0xffffffffu, left, 0);
+        SM_DBG("done w=%d s=%d left=%u\n", wid, s, left);
+        if (left == 0) {
+            __threadfence_block();
+            int st = 0, D = 0;                                   // lane 0 reads the slot, the others get copies
+            if (lane == 0) { st = sl.level | (sl.seq << 30) | (sl.emit << 29); D = sl.D; }
+            st = __shfl_sync(0xffffffffu, st, 0);
+            D = __shfl_sync(0xffffffffu, D, 0);
+            const int lv = st & 0xffffff, seq = (st >> 30) & 1, emit = (st >> 29) & 1;
+            const bool has_epi = emit && (p.out_rows || p.sc.n_profiles > 0);
+            uint16_t *of_s = offs_all + (size_t)s * SM_OFFS_CAP;
+            if (lv + 1 < D || (lv + 1 == D && has_epi)) {
+                sm_push_level<G>(sh, of_s, s, lv + 1, D, seq, lane);
+            } else {
+                if (emit && p.applied && lane == 0) p.applied[null_id - p.ix.null_lo] = sl.applied;
+                sm_next_null<G>(p, sh, rows, of_s, s, NS, false, lane);
+            }
+        }
     }
 }
 
@@ -530,6 +776,8 @@ struct TradeConfig {
     int threads;
     size_t smem_bytes;
     int grid_cap;      // max CTAs (global variant keeps the working set near L2 size)
+    int persist_slots; // k_trade_sm: null slots per SM (0 = not applicable)
+    size_t persist_smem;
 };
 
 static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
@@ -553,7 +801,23 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
     const size_t bytes = (size_t)c->R * c->RS * 4;
     const size_t budget = c->smem_optin > 2048 ? c->smem_optin - 1024 : 0;
     cfg->smem = bytes <= budget;
+    cfg->persist_slots = 0;
+    cfg->persist_smem = 0;
     if (cfg->smem) {
+        // persistent work-queue kernel: as many null slots as fit next to its control block, all outstanding rounds in the ring
+        const size_t per_slot = (bytes < 16 ? 16 : bytes) + SM_OFFS_CAP * sizeof(uint16_t);
+        const size_t avail = c->smem_optin > sizeof(SmShared) + 256 ? c->smem_optin - sizeof(SmShared) - 256 : 0;
+        int ns = (int)(avail / per_slot);
+        if (ns > SM_MAX_SLOTS) ns = SM_MAX_SLOTS;
+        const int gpw = 32 / cfg->G;
+        const int rounds_per_level = (c->R / 2 + gpw - 1) / gpw + SM_EPI_ROUNDS;
+        const char *pe = getenv("SDX_TRADE_PERSIST");
+        // EXPERIMENTAL (SDX_TRADE_PERSIST=1): bit-identical, but measured 37 % slower than k_trade on C1 — see
+        // profiles/r01_k_trade_ncu_summary.md ("work-queue kernel")
+        if (ns >= 2 && ns * rounds_per_level <= SM_RING - 32 && pe && atoi(pe) == 1) {
+            cfg->persist_slots = ns;
+            cfg->persist_smem = ns * per_slot;
+        }
         cfg->smem_bytes = bytes < 16 ? 16 : bytes;
         int per_sm = (int)((228 * 1024) / (cfg->smem_bytes + 1024 + 64));
         if (per_sm < 1) per_sm = 1;
@@ -566,7 +830,7 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
         cfg->LB = per_sm >= 4 ? (cfg->threads <= 128 ? 1 : (cfg->threads <= 256 ? 2 : 0)) : 0;
         if (const char *e = getenv("SDX_TRADE_LB")) {
             const int lb = atoi(e);
-            if (lb == 0 || (lb == 1 && cfg->threads <= 128) || ((lb == 2 || lb == 3 || lb == 5) && cfg->threads <= 256) || (lb == 4 && cfg->threads <= 192)) cfg->LB = lb;
+            if (lb >= 0 && lb <= 7 && cfg->threads <= lb_threads(lb)) cfg->LB = lb;
         }
         cfg->grid_cap = 1 << 30;
         {
@@ -592,9 +856,15 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
 }
 
 template <int G, int V>
-static cudaError_t launch_trade(const TradeConfig &cfg, int grid, cudaStream_t st, const TradeArgs &args) {
+static cudaError_t launch_trade(const TradeConfig &cfg, int grid, cudaStream_t st, const TradeArgs &args, bool persist) {
+    if (persist) {
+        cudaError_t e = cudaFuncSetAttribute(k_trade_sm<G, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.persist_smem);
+        if (e != cudaSuccess) return e;
+        k_trade_sm<G, V><<<grid, SM_THREADS, cfg.persist_smem, st>>>(args, cfg.persist_slots);
+        return cudaGetLastError();
+    }
     if (cfg.smem) {
-        auto kern = cfg.LB == 1 ? k_trade<G, V, true, 1> : (cfg.LB == 2 ? k_trade<G, V, true, 2> : (cfg.LB == 3 ? k_trade<G, V, true, 3> : (cfg.LB == 4 ? k_trade<G, V, true, 4> : (cfg.LB == 5 ? k_trade<G, V, true, 5> : k_trade<G, V, true, 0>))));
+        auto kern = cfg.LB == 1 ? k_trade<G, V, true, 1> : (cfg.LB == 2 ? k_trade<G, V, true, 2> : (cfg.LB == 3 ? k_trade<G, V, true, 3> : (cfg.LB == 4 ? k_trade<G, V, true, 4> : (cfg.LB == 5 ? k_trade<G, V, true, 5> : (cfg.LB == 6 ? k_trade<G, V, true, 6> : (cfg.LB == 7 ? k_trade<G, V, true, 7> : k_trade<G, V, true, 0>))))));
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;
         kern<<<grid, cfg.threads, cfg.smem_bytes, st>>>(args);
@@ -604,15 +874,15 @@ static cudaError_t launch_trade(const TradeConfig &cfg, int grid, cudaStream_t s
     return cudaGetLastError();
 }
 
-static cudaError_t dispatch_trade(const TradeConfig &cfg, int grid, cudaStream_t st, const TradeArgs &args) {
-    if (cfg.G == 2 && cfg.V == 16) return launch_trade<2, 16>(cfg, grid, st, args);
-    if (cfg.G == 4 && cfg.V == 8) return launch_trade<4, 8>(cfg, grid, st, args);
-    if (cfg.G == 8 && cfg.V == 4) return launch_trade<8, 4>(cfg, grid, st, args);
-    if (cfg.G == 8 && cfg.V == 8) return launch_trade<8, 8>(cfg, grid, st, args);
-    if (cfg.G == 16 && cfg.V == 4) return launch_trade<16, 4>(cfg, grid, st, args);
-    if (cfg.G == 32 && cfg.V == 4) return launch_trade<32, 4>(cfg, grid, st, args);
-    if (cfg.G == 32 && cfg.V == 5) return launch_trade<32, 5>(cfg, grid, st, args);
-    return launch_trade<32, 8>(cfg, grid, st, args);
+static cudaError_t dispatch_trade(const TradeConfig &cfg, int grid, cudaStream_t st, const TradeArgs &args, bool persist) {
+    if (cfg.G == 2 && cfg.V == 16) return launch_trade<2, 16>(cfg, grid, st, args, persist);
+    if (cfg.G == 4 && cfg.V == 8) return launch_trade<4, 8>(cfg, grid, st, args, persist);
+    if (cfg.G == 8 && cfg.V == 4) return launch_trade<8, 4>(cfg, grid, st, args, persist);
+    if (cfg.G == 8 && cfg.V == 8) return launch_trade<8, 8>(cfg, grid, st, args, persist);
+    if (cfg.G == 16 && cfg.V == 4) return launch_trade<16, 4>(cfg, grid, st, args, persist);
+    if (cfg.G == 32 && cfg.V == 4) return launch_trade<32, 4>(cfg, grid, st, args, persist);
+    if (cfg.G == 32 && cfg.V == 5) return launch_trade<32, 5>(cfg, grid, st, args, persist);
+    return launch_trade<32, 8>(cfg, grid, st, args, persist);
 }
 
 struct HostScore {               // optional fused scoring request
@@ -758,8 +1028,14 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
         const int64_t NB = 32768;                                   // nulls planned per launch
         const int seg_cap = (int)(chain_len < 256 ? chain_len : 256);
         int64_t chains_per_launch = NB / seg_cap;
+        // Expected depth of the level schedule is a small multiple of the trades per row (2T/R; C0: 10 -> depth ~41).
+        // dcap bounds the histogram of k_plan_sort; a null whose schedule is deeper runs in sequential order.
+        int dcap = (int)(16 * T / R) + 64;
+        if (dcap < 128) dcap = 128;
+        if (dcap > SDX_HCAP) dcap = SDX_HCAP;
+        const bool persist = !sparse && cfg.persist_slots > 0 && 2 * dcap <= SM_OFFS_CAP;
         {   // one CTA per chain and every chain of a launch does the same work: launch whole waves to avoid a ragged tail
-            const int64_t slots = sparse ? (int64_t)16 * c->sm_count : (int64_t)cfg.slots;
+            const int64_t slots = sparse ? (int64_t)16 * c->sm_count : (persist ? (int64_t)cfg.persist_slots * c->sm_count : (int64_t)cfg.slots);
             if (slots > 0 && chains_per_launch > slots) chains_per_launch = (chains_per_launch / slots) * slots;
         }
         if (chains_per_launch > n_chains) chains_per_launch = n_chains;
@@ -777,11 +1053,6 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
             SDX_CUDA(c, cudaFuncSetAttribute(k_plan_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem));
 
         void *p_lvl, *p_plan, *p_offs, *p_aux = nullptr, *p_carry = nullptr, *p_work = nullptr, *p_out = nullptr, *p_app = nullptr;
-        // Expected depth of the level schedule is a small multiple of the trades per row (2T/R; C0: 10 -> depth ~41).
-        // dcap bounds the histogram of k_plan_sort; a null whose schedule is deeper runs in sequential order.
-        int dcap = (int)(16 * T / R) + 64;
-        if (dcap < 128) dcap = 128;
-        if (dcap > SDX_HCAP) dcap = SDX_HCAP;
         const int offs_stride = (int)((2 * (T < dcap ? T : dcap) + 2 + 1) & ~1ll);
         const size_t sort_smem_warp = sizeof(uint32_t) * ((size_t)dcap * SDX_NCLS + 2);
         const int sort_warps = sort_smem_warp * 8 <= 40 * 1024 ? 8 : (sort_smem_warp * 4 <= 40 * 1024 ? 4 : 2);
@@ -852,8 +1123,10 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
                         k_trade_sparse<<<(unsigned)nch, 32, sp_smem, c->stream>>>(ta);
                         e = cudaGetLastError();
                     }
+                } else if (persist) {
+                    e = dispatch_trade(cfg, (int)(nch < c->sm_count ? nch : c->sm_count), c->stream, ta, true);
                 } else {
-                    e = dispatch_trade(cfg, grid, c->stream, ta);
+                    e = dispatch_trade(cfg, grid, c->stream, ta, false);
                 }
                 if (e != cudaSuccess) return sdx_fail(c, SDX_ERR_CUDA, std::string("trade kernel launch failed: ") + cudaGetErrorString(e));
                 timer.count();

@@ -605,6 +605,46 @@ def test_sparse_layout_kernel_is_bit_identical(monkeypatch):
                 assert res["n_ge"][p] == int((res["null_scores"][p] >= res["z_obs"][p]).sum())
 
 
+# ---------------------------------------------------------------- experimental work-queue kernel (SDX_TRADE_PERSIST=1)
+def test_work_queue_kernel_is_bit_identical(monkeypatch):
+    """k_trade_sm (one persistent CTA per SM, null slots in shared memory, warps pull rounds from a ring queue) must give
+    the same nulls, applied-trade counts, chains, burn-in pool states and scores as the oracle."""
+    monkeypatch.setenv("SDX_TRADE_PERSIST", "1")
+    cases, _ = curveball_cases()
+    rng = np.random.default_rng(8)
+    mats = {"c0_shape": cases["c0_shape"]["dense"],
+            "small": (rng.random((40, 17)) < 0.3).astype(np.uint8),
+            "wide_rows": (rng.random((1500, 30)) < 0.1).astype(np.uint8)}
+    with Engine(0) as e2:
+        for name, dense in mats.items():
+            S, F = dense.shape
+            upload_dense(e2, dense)
+            obs = rows_of(dense)
+            R = obs.shape[0]
+            for chain_len, null0, n, T in ((1, 0, 5, 5 * R), (3, 1, 7, 5 * R), (4, 0, 8, 0), (2, 3, 300, 7)):
+                want, want_ap = oracle.curveball_nulls(obs, 11, null0, n, T, chain_len)
+                got, got_ap = e2.curveball(11, null0, n, T, chain_len)
+                assert np.array_equal(got_ap, want_ap), name
+                assert np.array_equal(got, want), name
+            e2.set_burn_in(3, 7)
+            want, _ = oracle.curveball_nulls(obs, 5, 2, 20, 5 * R, 4, burn=3, pool_size=7)
+            got, _ = e2.curveball(5, 2, 20, -1, 4, want_applied=False)
+            assert np.array_equal(got, want), name
+            e2.set_burn_in(0)
+            w = synth.weights(S, 9, seed=S)
+            e2.upload_weights(w)
+            order = np.argsort(-dense.sum(0), kind="stable")
+            modules = np.stack([np.sort(order[i:i + 3]) for i in range(9)]).astype(np.int32)
+            res = e2.null_pvalue(3, 0, 40, modules, want_scores=True)
+            nulls, _ = oracle.curveball_nulls(obs, 3, 0, 40, 5 * R, 1)
+            frows = bitpack.pack_rows(dense.T)
+            for p in range(9):
+                ras = F >= S
+                want_sc = [oracle.score_set(bitpack.pack_rows(bitpack.unpack_rows(m, max(S, F)).T) if ras else m, S, modules[p], w[p])[0] for m in nulls]
+                assert np.allclose(res["null_scores"][p], want_sc, rtol=0, atol=1e-9 * np.abs(w[p]).sum()), name
+                assert res["n_ge"][p] == int((res["null_scores"][p] >= res["z_obs"][p]).sum())
+
+
 # ---------------------------------------------------------------- individual contributions
 def test_contributions_match_the_reference_arithmetic(eng):
     """utils/compute_individual_contribution_SELECT.py:69-85 restated with Python sets, against the GPU sums."""
