@@ -291,6 +291,7 @@ def run_ours(args):
         avg_launch_ms = trade_ms / trade_launches
         achieved = (bytes_per_null * (n / -(-n // 32768)) / 1e9) / (avg_launch_ms / 1e3)
         popc_per_null = T * 2 * wd
+        int_peaks = eng.measure_int_peaks()          # POPC / LOP3 rates measured on this box, outside the timed region
         line = {
             "metric": "curveball_nulls_scored_per_s", "value": value, "unit": "nulls/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -313,6 +314,8 @@ def run_ours(args):
                          "bytes_per_null": bytes_per_null, "avg_launch_ms": avg_launch_ms,
                          "kernel_share_of_step": trade_ms / ms, "plan_share_of_step": plan_ms / ms,
                          "popc_per_s": popc_per_null * value / world, "popc_frac_of_nominal": popc_per_null * value / world / POPC_PEAK_NOMINAL,
+                         "popc_peak_measured": int_peaks["popc_per_s"], "lop3_peak_measured": int_peaks["lop3_per_s"],
+                         "popc_frac_of_measured": popc_per_null * value / world / int_peaks["popc_per_s"],
                          "note": "working set is shared-memory resident: algorithmic bytes are SMEM row transfers; the only compulsory HBM traffic of the kernel is the trade plan (traffic)"},
             "clocks": sampler.summary(),
             "exceedances": int(counts.item()), "p_value": float(counts.item()) / total_nulls,
@@ -359,6 +362,7 @@ def secondary(eng, torch):
                 "ms": min(ts), "subsets_per_s": r["n_scored"] / (min(ts) / 1e3), "best_W": float(r["W"][0]),
                 "best": [int(x) for x in r["features"][0]],
                 "popc_roofline_frac_of_nominal": r["n_scored"] / (min(ts) / 1e3) * 32 / POPC_PEAK_NOMINAL,
+                "popc_roofline_frac_of_measured": r["n_scored"] / (min(ts) / 1e3) * 32 / eng.measure_int_peaks()["popc_per_s"],
                 "note": "inclusion-exclusion over a pair table does fewer word operations than the per-subset popc count the roofline "
                         "formula assumes (SURVEY 8d), so the fraction can exceed 1"}
 

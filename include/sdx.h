@@ -208,6 +208,10 @@ int sdx_read_nulls_tsv(const char *path_prefix, int64_t first_index, int64_t n_n
                        uint32_t *feature_rows, int64_t *n_unknown_events, int n_threads);
 const char *sdx_io_last_error(void);
 
+/* Measurement hook for bench.py ("popc/INT-pipe fraction against a peak measured on the box"): runs two
+ * register-only micro-kernels on the context's device and reports the sustained 32-bit POPC and LOP3 rates (ops/s). */
+int sdx_measure_int_peaks(sdx_ctx *ctx, double *popc_per_s, double *lop3_per_s);
+
 /* Self-test hooks used by tests/ (known-answer vectors of the random streams). */
 int sdx_test_philox(sdx_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, int n, uint32_t *out4);
 int sdx_test_trade_pairs(sdx_ctx *ctx, uint64_t seed, uint64_t null_id, int n_trades, int n_rows,

@@ -74,6 +74,7 @@ PROTOTYPES = {
     "sdx_read_nulls_tsv": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_char_p),
                                      C.POINTER(C.c_char_p), _u32p, _i64p, C.c_int]),
     "sdx_io_last_error": (C.c_char_p, []),
+    "sdx_measure_int_peaks": (C.c_int, [_ctx, _f64p, _f64p]),
     "sdx_test_philox": (C.c_int, [_ctx, _u32p, _u32p, C.c_int, _u32p]),
     "sdx_test_trade_pairs": (C.c_int, [_ctx, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _i32p, _i32p]),
 }

@@ -220,3 +220,54 @@ extern "C" int sdx_test_trade_pairs(sdx_ctx *c, uint64_t seed, uint64_t null_id,
     SDX_CUDA(c, cudaMemcpyAsync(b, d_b, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, c->stream));
     return timer.finish();
 }
+
+// ---------------------------------------------------------------------------
+// Integer-pipe peaks measured on the box (bench.py): register-only loops of eight independent chains
+// per thread, enough CTAs to fill every SM; the rates are what the XU (POPC) and ALU (LOP3) pipes sustain.
+// ---------------------------------------------------------------------------
+#define PEAK_CHAINS 8
+template <bool POPC>
+__global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, int iters, uint32_t salt) {
+    uint32_t a[PEAK_CHAINS], s[PEAK_CHAINS];
+#pragma unroll
+    for (int j = 0; j < PEAK_CHAINS; ++j) { a[j] = (threadIdx.x + 1u) * 2654435761u + j * salt; s[j] = j + salt; }
+    const uint32_t m0 = salt | 0x55555555u, m1 = ~salt ^ 0x0f0f0f0fu;
+#pragma unroll 8
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < PEAK_CHAINS; ++j) {
+            if (POPC) s[j] += __popc(a[j] ^ s[j]);               // one LOP3 + one POPC + one IADD per step: POPC is the slow pipe
+            else asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(a[j]) : "r"(m0), "r"(m1));      // one LOP3 (majority) per step
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int j = 0; j < PEAK_CHAINS; ++j) r ^= a[j] + s[j];
+    if (r == 0x12345678u) out[0] = r;                            // keeps the loops alive without a store per thread
+}
+
+extern "C" int sdx_measure_int_peaks(sdx_ctx *c, double *popc_per_s, double *lop3_per_s) {
+    if (!c || !popc_per_s || !lop3_per_s) return SDX_ERR_INVALID;
+    SDX_CUDA(c, cudaSetDevice(c->device));
+    void *p;
+    int rc;
+    if ((rc = sdx_scratch(c, 0, 64, &p))) return rc;
+    const int grid = c->sm_count * 8, threads = 256, iters = 4096;
+    float ms[2] = {0, 0};
+    for (int which = 0; which < 2; ++which) {
+        for (int rep = 0; rep < 3; ++rep) {                       // two warm-up launches, the third is timed
+            cudaEventRecord(c->ev[2], c->stream);
+            if (which == 0) k_int_peak<true><<<grid, threads, 0, c->stream>>>((uint32_t *)p, iters, 0x9e3779b9u + rep);
+            else k_int_peak<false><<<grid, threads, 0, c->stream>>>((uint32_t *)p, iters, 0x9e3779b9u + rep);
+            cudaEventRecord(c->ev[3], c->stream);
+            c->total_launches++;
+        }
+        SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+        SDX_CUDA(c, cudaGetLastError());
+        cudaEventElapsedTime(&ms[which], c->ev[2], c->ev[3]);
+    }
+    const double ops = (double)grid * threads * iters * PEAK_CHAINS;
+    *popc_per_s = ops / (ms[0] * 1e-3);
+    *lop3_per_s = ops / (ms[1] * 1e-3);
+    return SDX_OK;
+}

@@ -72,6 +72,12 @@ class Engine:
         self._check(self._lib.sdx_total_launches(self._ctx, C.byref(n)))
         return n.value
 
+    def measure_int_peaks(self) -> dict:
+        """Sustained 32-bit POPC and LOP3 rates of this GPU (ops/s), measured by two register-only micro-kernels."""
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self._lib.sdx_measure_int_peaks(self._ctx, C.byref(a), C.byref(b)))
+        return {"popc_per_s": a.value, "lop3_per_s": b.value}
+
     # -- uploads -------------------------------------------------------------
     def upload_matrix(self, feature_rows: np.ndarray, n_samples: int):
         """feature_rows: (F, ceil(S/32)) uint32 packed rows over samples."""

@@ -313,6 +313,24 @@ def test_scan_matches_golden_bruteforce(eng, name):
         assert abs(eng.scan(0, k, 1)["W"][0] - z[name + "__best_le_k"][k - 1]) < tol
 
 
+def test_scan_optimum_equals_the_reference_ilp_at_c0_size(eng):
+    """Pin G4 at F <= 400: the scan's optimum on the C0 matrix equals the optimum of the reference's ILP
+    (src/superdendrix.py:294-313) solved by HiGHS (oracle/milp.py), for k = 1, 2, 3 and for two weight vectors."""
+    from oracle import milp
+    dense, _, _ = synth.feature_matrix(770, 400)
+    S, F = dense.shape
+    upload_dense(eng, dense)
+    for seed in (3, 11):
+        w = synth.weights(S, 1, seed=seed)[0]
+        eng.upload_weights(w[None, :])
+        for k in (1, 2, 3):
+            z, feats, optimal = milp.ilp_optimum(dense, w, k, all_samples=False)
+            assert optimal
+            top = eng.scan(0, k, 1)
+            assert abs(max(float(top["W"][0]), 0.0) - z) <= 1e-7 * np.abs(w).sum(), (seed, k)
+            assert sorted(int(g) for g in top["features"][0] if g >= 0) == feats
+
+
 @pytest.mark.parametrize("S,F,density,k", [(200, 61, 0.05, 3), (130, 37, 0.5, 3), (64, 5, 0.3, 3), (40, 3, 0.4, 3),
                                            (40, 2, 0.4, 3), (33, 1, 0.5, 3), (300, 90, 0.02, 2), (300, 90, 0.02, 1),
                                            (1030, 70, 0.1, 3)])

@@ -10,7 +10,7 @@ import pytest
 
 import oracle
 from oracle import refport
-from superdendrix_b200 import bitpack
+from superdendrix_b200 import bitpack, synth
 
 from conftest import GOLDEN, curveball_cases, load_npz, rows_of
 
@@ -194,6 +194,29 @@ def test_scan_matches_bruteforce_over_reference_superw(name):
     for k in (1, 2, 3):
         bW, _, _, _ = oracle.scan(rows, S, w, k, topn=1)
         assert abs(bW[0] - z[name + "__best_le_k"][k - 1]) < 1e-9 * np.abs(w).sum()
+
+
+def test_scan_optimum_equals_the_reference_ilp_solved_by_highs():
+    """Pin G4: the integral optimum of the reference's ILP (src/superdendrix.py:294-313, objective :393-401,
+    restated for HiGHS in oracle/milp.py because Gurobi is not installed) equals the exhaustive-scan optimum, for every
+    cardinality bound, including instances where the empty module wins (z = 0)."""
+    from oracle import milp
+    for seed, S, F, dens in ((1, 90, 40, 0.12), (2, 120, 25, 0.3), (3, 60, 30, 0.05)):
+        rng = np.random.default_rng(seed)
+        dense = (rng.random((S, F)) < dens).astype(np.uint8)
+        w = synth.weights(S, 1, seed=seed)[0]
+        if seed == 3:
+            w = -np.abs(w)                                     # no feature can score > 0: the ILP selects nothing
+        rows = bitpack.pack_rows(dense.T)
+        for k in (1, 2, 3):
+            z, feats, optimal = milp.ilp_optimum(dense, w, k)
+            assert optimal
+            bW, bF, _, _ = oracle.scan(rows, S, w, k, topn=1)
+            best = max(float(bW[0]), 0.0)                      # the scan enumerates non-empty modules; M = {} scores 0
+            assert abs(z - best) <= 1e-7 * max(1.0, np.abs(w).sum()), (seed, k, z, best)
+            if best > 1e-6:
+                got = oracle.score_set(rows, S, np.array(feats, dtype=np.int32), w)[0]
+                assert abs(got - z) <= 1e-7 * np.abs(w).sum()    # the ILP's module really has that SuperW
 
 
 # ---------------------------------------------------------------- cond. permutation
