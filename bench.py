@@ -443,7 +443,72 @@ def secondary(eng, torch):
         return {"workload": "drop-in generator CLI: %d null TSV files of the C0 matrix written in the reference's format, then parsed back" % n,
                 "generate_and_write_s": t_gen, "files_per_s": n / t_gen, "parse_s": t_read, "parsed_files_per_s": n / t_read, "margins_ok": ok}
 
+    def cpu_secondary():
+        """SURVEY 8d CPU column for the secondary metrics: the reference's Python algorithm (oracle/refport.py) and
+        scipy.stats.ranksums on ONE host core, each on a bounded sample (about 2-5 s) of the same synthetic workload."""
+        import random
+
+        import scipy.stats
+
+        from oracle import refport
+        res = {"cores": 1, "kind": "port"}
+        # subsets/s: SuperW over random triples of the C2 matrix
+        dense, _, _ = synth.feature_matrix(1000, 2000, seed=20)
+        S, F = dense.shape
+        w = synth.weights(S, 1, seed=3)[0]
+        profile = {i: float(w[i]) for i in range(S)}
+        cases = [set(np.flatnonzero(dense[:, g]).tolist()) for g in range(F)]
+        rng = np.random.default_rng(5)
+        triples = rng.integers(0, F, size=(300000, 3))
+        t0 = time.perf_counter()
+        for a, b, c in triples:
+            refport.super_w([cases[a], cases[b], cases[c]], profile)
+        dt = time.perf_counter() - t0
+        res["superw_subsets_per_s"] = len(triples) / dt
+        res["superw_sample"] = "%d random triples of the C2 matrix in %.1f s (full scan: %.2e subsets)" % (len(triples), dt, F * (F - 1) * (F - 2) / 6)
+        # permuted scores/s and rank-sum profiles/s on the C0 matrix
+        dense, w1, module = workload()
+        S, F = dense.shape
+        samples = list(range(S))
+        ev = {int(g): set(np.flatnonzero(dense[:, g]).tolist()) for g in module}
+        profile = {i: float(w1[0, i]) for i in samples}
+        random.seed(1)
+        n_perm = 4000
+        t0 = time.perf_counter()
+        refport.conditional_permutation([int(g) for g in module], ev, profile, samples, n_perm)
+        dt = time.perf_counter() - t0
+        res["condperm_scores_per_s"] = len(module) * n_perm / dt
+        res["condperm_sample"] = "%d permutations x %d features of one C0 module in %.1f s" % (n_perm, len(module), dt)
+        ws = synth.weights(S, 3000, seed=11)
+        union = np.zeros(S, dtype=bool)
+        for g in module:
+            union |= dense[:, g] != 0
+        t0 = time.perf_counter()
+        for p_ in range(len(ws)):
+            scipy.stats.ranksums(ws[p_][union], ws[p_][~union])
+        dt = time.perf_counter() - t0
+        res["ranksum_profiles_per_s"] = len(ws) / dt
+        res["ranksum_sample"] = "scipy.stats.ranksums on %d profiles in %.2f s" % (len(ws), dt)
+        # generator rows + file writing (src/generate_null_matrices.py:75-86), 20 nulls
+        import tempfile
+        dense, samples_n, features = synth.feature_matrix(770, 400, seed=20)
+        random.seed(2)
+        lists = refport.presences(dense.astype(np.float64))
+        with tempfile.TemporaryDirectory(prefix="sdx_cpu_") as d:
+            t0 = time.perf_counter()
+            for i in range(60):
+                null = refport.curveball(dense.astype(np.float64), lists)
+                rows = refport.null_rows(null, samples_n, features)
+                with open(os.path.join(d, "%d.tsv" % i), "w") as fh:
+                    fh.write("#Samples\tEvents\n")
+                    fh.write("\n".join("\t".join(r) for r in rows))
+            dt = time.perf_counter() - t0
+        res["generator_files_per_s"] = 60 / dt
+        res["generator_sample"] = "60 chained nulls of the C0 matrix generated and written as TSV in %.1f s" % dt
+        return res
+
     guarded("scan_k3_2000", scan_c2)
+    guarded("cpu_secondary", cpu_secondary)
     guarded("generator_files_c0", files_c0)
     guarded("nulls_c3", nulls_c3)
     guarded("maxk_c0", maxk_c0)
