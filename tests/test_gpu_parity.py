@@ -779,7 +779,7 @@ def test_c4_slice_batched_model_selection_statistics(eng):
 
 # ---------------------------------------------------------------- the rare branch of Lemire's method
 # (half, sparse layout?, null indices of seed 4242 whose single trade enters the rejection zone; found by scanning the
-#  oracle: tools/find_lemire_cases.py.  The last index of each list also RE-DRAWS.)
+#  oracle: tests/tools/find_lemire_cases.py.  The last index of each list also RE-DRAWS.)
 LEMIRE_CASES = [
     (400, "0", [18883, 55949]),          # n = 800: general pick path (rank mask in the row's shared-memory storage)
     (32, "0", [314870, 16882340]),       # n = 64: register pick path

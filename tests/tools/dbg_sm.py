@@ -1,7 +1,7 @@
 """Debug driver for the persistent trade kernel: one small null against the oracle."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle
 from superdendrix_b200 import bitpack
 from superdendrix_b200.engine import Engine

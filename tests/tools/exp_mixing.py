@@ -2,7 +2,7 @@
 (5*min(S,F) trades each) from the observed matrix, C0 shape, canonical streams, CPU oracle.  Test infrastructure only."""
 import sys, os, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle
 from superdendrix_b200 import synth, bitpack
 

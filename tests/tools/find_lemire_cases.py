@@ -2,7 +2,7 @@
 zone of Lemire's method / re-draw, by scanning the oracle.  Used to pin tests/test_gpu_parity.py::LEMIRE_CASES."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle
 from superdendrix_b200 import bitpack
 
