@@ -213,6 +213,44 @@ def optimize_model(genes, samples, w, events_to_samples, samples_to_genes, args,
     return z, module, best_single, cov, act_cov, act_sample, None, None, None
 
 
+def mip_start(genes, samples, w, events_to_samples, k, logger=None):
+    """Certificate / warm start for the reference's Gurobi model (src/superdendrix.py:289-324).
+
+    k <= 3: the exhaustive scan IS the integral optimum, ``certified`` is True and the solve can be skipped.
+    k  > 3 (up to SDX_MAX_K = 8): the k=3 optimum is extended greedily, one feature at a time, each step scoring all F
+    candidate extensions with the set scorer; the result is a feasible module, i.e. a MIP start and a valid lower
+    bound (Gurobi ``Cutoff``) — the ILP itself stays the reference's.
+
+    Returns dict(module=[gene...], x_start={gene: 0/1}, lower_bound=z, certified=bool).  A maintainer adds, after
+    ``m.update()`` (src/superdendrix.py:315):  ``for g in genes: x[g].Start = hook["x_start"][g]`` and
+    ``m.params.Cutoff = hook["lower_bound"]``."""
+    if not 1 <= k <= 8:
+        raise ValueError("k must be in 1..8")
+    eng = _engine()
+    genes = list(genes)
+    samples = list(samples)
+    eng.upload_matrix(pack_features(genes, samples, events_to_samples), len(samples))
+    eng.upload_weights(np.array([w[s] for s in samples], dtype=np.float64))
+    hit = eng.scan(0, min(k, 3), 1)
+    z, feats = float(hit["W"][0]), [int(f) for f in hit["features"][0] if f >= 0]
+    if not feats or z < 0:
+        z, feats = 0.0, []
+    F = len(genes)
+    while feats and len(feats) < k:
+        cand = np.full((F, len(feats) + 1), -1, dtype=np.int32)
+        cand[:, :len(feats)] = feats
+        cand[:, -1] = np.arange(F)
+        W = eng.score_sets(cand)["W"]
+        W[feats] = -np.inf                                   # a repeated feature is not an extension
+        best = int(np.argmax(W))
+        if W[best] <= z:
+            break
+        z, feats = float(W[best]), feats + [best]
+    chosen = set(feats)
+    return {"module": [genes[f] for f in sorted(feats)], "x_start": {g: int(i in chosen) for i, g in enumerate(genes)},
+            "lower_bound": z, "certified": k <= 3}
+
+
 # ---------------------------------------------------------------------------
 def null_loop(genes, samples, profile, events_to_samples, module, zP, args, logger):
     """The permutation test of src/superdendrix.py:166-197 -> (no_better, n, null statistics)."""

@@ -80,6 +80,40 @@ def test_conditional_permutation_shim_agrees_with_reference_decisions():
             assert ev == c["worst"]
 
 
+def test_optimize_model_and_mip_start_hook_against_the_reference_ilp():
+    """optimize_model (src/superdendrix.py:267-357 return tuple) by exhaustive scan, and the warm-start hook of SURVEY 8f:
+    certified optimum for k <= 3 (equals the reference's ILP solved by HiGHS), feasible lower bound for k > 3."""
+    import types
+    from oracle import milp
+    dense, samples, features = synth.feature_matrix(300, 60, seed=9)
+    S, F = dense.shape
+    wv = synth.weights(S, 1, seed=4)[0]
+    w = {samples[i]: float(wv[i]) for i in range(S)}
+    e2s = {features[g]: set(samples[i] for i in np.flatnonzero(dense[:, g])) for g in range(F)}
+    s2g = {samples[i]: set(features[g] for g in np.flatnonzero(dense[i])) for i in range(S)}
+    for k in (1, 2, 3):
+        z_ilp, feats_ilp, optimal = milp.ilp_optimum(dense, wv, k)
+        assert optimal
+        z, module, best_single, cov, act_cov, act_sample, x, y, m = sd.optimize_model(features, samples, w, e2s, s2g, types.SimpleNamespace(cardinality=k))
+        assert abs(z - z_ilp) <= 1e-7 * np.abs(wv).sum() and (x, y, m) == (None, None, None)
+        assert sorted(module) == sorted(features[g] for g in feats_ilp)
+        assert cov == int(dense[:, feats_ilp].any(1).sum()) and act_sample == int((wv > 0).sum())
+        assert act_cov == int((dense[:, feats_ilp].any(1) & (wv > 0)).sum())
+        hook = sd.mip_start(features, samples, w, e2s, k)
+        assert hook["certified"] and abs(hook["lower_bound"] - z_ilp) <= 1e-7 * np.abs(wv).sum()
+        assert sum(hook["x_start"].values()) == len(module)
+    z3 = sd.mip_start(features, samples, w, e2s, 3)["lower_bound"]
+    for k in (4, 6):
+        hook = sd.mip_start(features, samples, w, e2s, k)
+        z_ilp, _, optimal = milp.ilp_optimum(dense, wv, k)
+        assert optimal and not hook["certified"]
+        assert z3 - 1e-9 <= hook["lower_bound"] <= z_ilp + 1e-7 * np.abs(wv).sum()      # feasible: never above the optimum
+        idx = [features.index(g) for g in hook["module"]]
+        rows = bitpack.pack_rows(dense.T)
+        assert abs(oracle.score_set(rows, S, np.array(idx, dtype=np.int32), wv)[0] - hook["lower_bound"]) <= 1e-9 * np.abs(wv).sum()
+        assert len(idx) <= k and sum(hook["x_start"].values()) == len(idx)
+
+
 # ---------------------------------------------------------------- generator CLI and file formats
 def test_generate_null_matrices_cli_writes_reference_format(tmp_path):
     gdir = os.path.join(GOLDEN, "generator")
