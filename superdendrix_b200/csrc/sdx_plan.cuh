@@ -1,0 +1,162 @@
+// sdx_plan.cuh — the trade plan of a batch of nulls: pairs (PAIR stream), level schedule, counting sort by (level, size class).
+// Included by sdx_curveball.cu only.
+#pragma once
+#include "sdx_trade.cuh"
+
+// ---------------------------------------------------------------------------
+struct NullIndexing {          // local null index (within a launch) -> global null id
+    uint64_t chain0;           // first chain of this launch
+    int64_t chain_len;
+    int64_t seg_off;           // chain-relative offset of the segment
+    int seg_len;               // nulls per chain in this launch
+    uint64_t null_lo, null_hi; // requested range [null_lo, null_hi)
+    __host__ __device__ uint64_t id(int64_t local) const {
+        return (chain0 + (uint64_t)(local / seg_len)) * (uint64_t)chain_len + (uint64_t)seg_off + (uint64_t)(local % seg_len);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// plan: levels
+// ---------------------------------------------------------------------------
+// pairs of every trade of every null of the launch, one thread per (null, trade): pairs[n][t] = a | b << 16
+__global__ void k_plan_pairs(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T, int Tp,
+                             uint32_t *__restrict__ pairs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = (int)(i / Tp), t = (int)(i - (int64_t)n * Tp);
+    if (n >= n_local) return;
+    uint32_t a = 0, b = 0;
+    if (t < T) trade_pair(keys, ix.id(n), (uint32_t)t, (uint32_t)R, a, b);
+    pairs[i] = a | (b << 16);
+}
+
+// One THREAD per null walks its trades in order; pairs come in and levels go out through shared-memory
+// tiles of PL_TT trades x PL_NT nulls so that every global access is a coalesced row segment.
+#define PL_NT 64
+#define PL_TT 32
+__global__ void __launch_bounds__(PL_NT) k_plan_levels(int n_local, int R, int T, int Tp, const uint32_t *__restrict__ pairs,
+                                                       uint16_t *__restrict__ lvl, int *__restrict__ depth,
+                                                       uint16_t *__restrict__ last_global) {
+    extern __shared__ __align__(16) uint16_t plan_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n0 = blockIdx.x * PL_NT, n = n0 + tid;
+    // layout: tile_p[PL_NT][PL_TT + 1] u32 | tile_l[PL_NT][PL_TT + 2] u16 | last[R][PL_NT] u16 (unless in global memory)
+    uint32_t *tile_p = reinterpret_cast<uint32_t *>(plan_smem);
+    uint16_t *tile_l = reinterpret_cast<uint16_t *>(tile_p + PL_NT * (PL_TT + 1));
+    uint16_t *last = last_global ? last_global + (size_t)blockIdx.x * PL_NT * R + tid : tile_l + PL_NT * (PL_TT + 2) + tid;
+    for (int r = 0; r < R; ++r) last[(size_t)r * PL_NT] = 0;
+    int d = 0;
+    constexpr int PER = PL_NT / (PL_NT / 32);                      // null rows each warp loads per tile
+    uint32_t nx[PER];                                              // next tile, in flight while the current one is processed
+    auto fetch = [&](int t0) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int i = wid + q * (PL_NT / 32);
+            nx[q] = (n0 + i < n_local && t0 + lane < Tp) ? pairs[(size_t)(n0 + i) * Tp + t0 + lane] : 0u;      // coalesced 128-byte segments
+        }
+    };
+    fetch(0);
+    for (int t0 = 0; t0 < T; t0 += PL_TT) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER; ++q) tile_p[(wid + q * (PL_NT / 32)) * (PL_TT + 1) + lane] = nx[q];
+        __syncthreads();
+        if (t0 + PL_TT < T) fetch(t0 + PL_TT);
+        const int cnt = T - t0 < PL_TT ? T - t0 : PL_TT;
+        for (int c = 0; c < cnt; ++c) {
+            const uint32_t e = tile_p[tid * (PL_TT + 1) + c];
+            const uint32_t a = e & 0xffffu, b = e >> 16;
+            const int la = last[(size_t)a * PL_NT], lb = last[(size_t)b * PL_NT];
+            const int l = (la > lb ? la : lb) + 1;
+            last[(size_t)a * PL_NT] = (uint16_t)l;
+            last[(size_t)b * PL_NT] = (uint16_t)l;
+            tile_l[tid * (PL_TT + 2) + c] = (uint16_t)l;
+            d = l > d ? l : d;
+        }
+        __syncthreads();
+        for (int i = wid; i < PL_NT; i += PL_NT / 32)
+            if (n0 + i < n_local && t0 + lane < T) lvl[(size_t)(n0 + i) * T + t0 + lane] = tile_l[i * (PL_TT + 2) + lane];
+    }
+    if (n < n_local) depth[n] = d;
+}
+
+// ---------------------------------------------------------------------------
+// plan: counting sort by level (one warp per null)
+// ---------------------------------------------------------------------------
+#define SDX_HCAP 1024          // upper bound of the deepest level schedule the plan kernels sort (see dcap below)
+#define SDX_NCLS 4             // trade size classes inside a level (largest first)
+
+// Row sizes never change (Curveball preserves them), so min(|a|, |b|) bounds the number of picks of a
+// trade and |a| + |b| bounds its symmetric difference.  Inside a level the plan lists the large
+// trades first and groups similar sizes, so the groups of one warp run loops of similar length and
+// the register fast path of trade_rows (n <= 64) is taken by whole warps.
+// With the sparse layout (ts >= 0: rows of at most ts carriers are index lists, sdx_sparse.cuh) classes 0 and 1 are
+// the trades that involve a bit-packed row and classes 2 and 3 the list x list trades (one per thread), split by the
+// total list length so that the threads of a warp walk lists of similar length.
+__device__ __forceinline__ int trade_class(int sa, int sb, int ts) {
+    const int kb = sa < sb ? sa : sb;
+    if (ts >= 0) {
+        if (sa > ts || sb > ts) return sa + sb > 64 ? 0 : 1;
+        return sa + sb > 12 ? 2 : 3;
+    }
+    if (sa + sb > 64) return 0;
+    return kb > 8 ? 1 : (kb > 3 ? 2 : 3);
+}
+
+__global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const uint32_t *__restrict__ pairs,
+                            const uint16_t *__restrict__ lvl, const int *__restrict__ depth, const int *__restrict__ rowsize,
+                            const uint32_t *__restrict__ desc, int ts, void *__restrict__ plan, uint16_t *__restrict__ offs,
+                            int offs_stride) {
+    extern __shared__ uint32_t hist_smem[];        // per warp: dcap * SDX_NCLS + 2 bins
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n = blockIdx.x * (blockDim.x >> 5) + wid;
+    if (n >= n_local) return;
+    const int D = depth[n];
+    uint32_t *hist = hist_smem + (size_t)wid * (dcap * SDX_NCLS + 2);
+    const uint16_t *lv = lvl + (size_t)n * T;
+    // plan entry: (a | b << 16, t) for k_trade; (a | b << 16, t, descriptor of a, descriptor of b) for k_trade_sparse
+    uint2 *out2 = reinterpret_cast<uint2 *>(plan) + (size_t)n * T;
+    uint4 *out4 = reinterpret_cast<uint4 *>(plan) + (size_t)n * T;
+    auto emit = [&](uint32_t pos, uint32_t e, uint32_t t) {
+        if (desc) out4[pos] = make_uint4(e, t, desc[e & 0xffffu], desc[e >> 16]);
+        else out2[pos] = make_uint2(e, t);
+    };
+    const uint32_t *pr = pairs + (size_t)n * Tp;
+    if (D >= dcap) {            // very deep schedule: fall back to the sequential order (always valid)
+        for (int t = lane; t < T; t += 32) emit((uint32_t)t, pr[t], (uint32_t)t);
+        return;                 // k_trade runs such a null one trade per level, in order
+    }
+    const int NB = D * SDX_NCLS;                       // bin = (level - 1) * NCLS + class
+    for (int i = lane; i <= NB; i += 32) hist[i] = 0;
+    __syncwarp();
+    for (int t = lane; t < T; t += 32) {
+        const uint32_t e = pr[t];
+        atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16], ts)], 1u);
+    }
+    __syncwarp();
+    // exclusive scan of the bins -> start offsets
+    uint32_t carry = 0;
+    for (int base = 0; base < NB; base += 32) {
+        const int i = base + lane;
+        const uint32_t c = (i < NB) ? hist[i] : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (i < NB) hist[i] = carry + inc - c;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    __syncwarp();
+    // of[2l] = first entry of level l+1, of[2l+1] = its first class-2 entry (list x list trades start there), of[2D] = T
+    uint16_t *of = offs + (size_t)n * offs_stride;
+    for (int l = lane; l < D; l += 32) { of[2 * l] = (uint16_t)hist[l * SDX_NCLS]; of[2 * l + 1] = (uint16_t)hist[l * SDX_NCLS + 2]; }
+    if (lane == 0) of[2 * D] = (uint16_t)T;
+    __syncwarp();
+    for (int t = lane; t < T; t += 32) {
+        const uint32_t e = pr[t];
+        uint32_t pos = atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16], ts)], 1u);
+        emit(pos, e, (uint32_t)t);
+    }
+}
+

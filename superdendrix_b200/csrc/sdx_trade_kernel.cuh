@@ -1,0 +1,150 @@
+// sdx_trade_kernel.cuh — k_trade: one CTA per chain, matrix in shared memory (or L2), trades level by level, fused scoring.
+// Included by sdx_curveball.cu only.
+#pragma once
+#include "sdx_plan.cuh"
+
+// ---------------------------------------------------------------------------
+// trade kernel
+// ---------------------------------------------------------------------------
+struct ScoreArgs {
+    int n_profiles, k;
+    const int32_t *modules;           // P x k
+    const double *w;                  // P x S
+    const uint32_t *mask;             // P x wprS
+    const double *z_obs;              // P
+    unsigned long long *n_ge;         // P
+    double *null_scores;              // P x n_total, or null
+    int64_t n_total;                  // row length of null_scores
+    int S, wprS;
+    int rows_are_samples;
+};
+
+struct TradeArgs {
+    PhiloxKeys keys;
+    NullIndexing ix;
+    const uint32_t *observed;         // R x RS
+    uint32_t *work;                   // gridDim.x x R x RS (global-resident variant only)
+    uint32_t *carry;                  // n_units x R x RS: chain state between launches (or null)
+    const void *plan;                 // n_local x T: uint2 (a | b << 16, t), or uint4 with the two row descriptors (sparse layout)
+    const uint16_t *offs;             // n_local x offs_stride level offsets
+    int dcap;                         // schedules at least this deep run in sequential order
+    const int *depth;                 // n_local
+    int offs_stride;
+    int n_units;                      // chain segments in this launch
+    int R, RS, T, wprL;
+    int save_carry;
+    uint32_t *out_rows;               // staging: rows of launch-local null l go to out_rows + l * R * wprL
+    unsigned long long *applied;      // (i - ix.null_lo)
+    ScoreArgs sc;
+    const uint32_t *pool;             // burn-in pool: pool_size start states in the kernel's state layout, or null
+    int pool_size;
+    // sparse layout (k_trade_sparse only)
+    const uint32_t *desc;             // R row descriptors
+    const uint32_t *obs_state;        // fp_words: observed matrix in the sparse layout
+    int n_dense, fp_words;
+};
+
+// out-of-line copy of the scorer for the trade kernel: keeps its registers out of the trade loop's budget
+static __device__ __noinline__ SetScore score_module_call(const uint32_t *rows, int RS, bool rows_are_samples, const int32_t *mod, int k,
+                                                          const double *w, const uint32_t *mask, int S, int lane) {
+    return score_module(rows, RS, rows_are_samples, mod, k, w, mask, S, lane);
+}
+
+// LB selects the launch bounds: 0 = (512, 1), 1 = (128, 5), 2 = (256, 5), 3 = (256, 4), 4 = (192, 5), 5 = (256, 3), 6 = (64, 5), 7 = (96, 5) — all
+// but 0 bound the registers so that five CTAs (five nulls) stay resident per SM when the matrix fits five times in shared memory.
+constexpr int lb_threads(int lb) { return lb == 0 ? 512 : (lb == 1 ? 128 : (lb == 4 ? 192 : (lb == 6 ? 64 : (lb == 7 ? 96 : 256)))); }
+constexpr int lb_blocks(int lb) { return lb == 0 ? 1 : (lb == 3 ? 4 : (lb == 5 ? 3 : 5)); }
+template <int G, int V, bool SMEM, int LB>
+__global__ void __launch_bounds__(lb_threads(LB), lb_blocks(LB)) k_trade(const __grid_constant__ TradeArgs p) {
+    extern __shared__ __align__(16) uint32_t smem_rows[];
+    __shared__ unsigned int s_applied;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NW = blockDim.x >> 5;
+    constexpr int GPW = 32 / G;                 // groups per warp
+    const int NG = NW * GPW;                    // groups per CTA
+    const int sub = lane & (G - 1);
+    const int myg = wid * GPW + (lane / G);
+    const int R = p.R, RS = p.RS, T = p.T;
+    const int nvec = R * RS / 4;
+    uint32_t *rows = SMEM ? smem_rows : p.work + (size_t)blockIdx.x * R * RS;
+
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        for (int j = 0; j < p.ix.seg_len; ++j) {
+            const int64_t local = (int64_t)u * p.ix.seg_len + j;
+            const uint64_t null_id = p.ix.id(local);
+            if (null_id >= p.ix.null_hi) break;
+            const bool restart = (null_id % (uint64_t)p.ix.chain_len) == 0;
+            if (restart || j == 0) {
+                const uint32_t *src = p.carry + (size_t)u * R * RS;
+                if (restart) src = p.pool ? p.pool + (size_t)((null_id / (uint64_t)p.ix.chain_len) % (uint64_t)p.pool_size) * R * RS : p.observed;
+                for (int i = tid; i < nvec; i += blockDim.x)
+                    reinterpret_cast<uint4 *>(rows)[i] = reinterpret_cast<const uint4 *>(src)[i];
+            }
+            if (tid == 0) s_applied = 0;
+            __syncthreads();
+
+            // ---- trades, level by level -------------------------------------
+            unsigned int my_applied = 0;
+            if (T > 0) {
+                const uint2 *pl = reinterpret_cast<const uint2 *>(p.plan) + (size_t)local * T;
+                const uint16_t *of = p.offs + (size_t)local * p.offs_stride;
+                int D = p.depth[local];
+                const bool seq = D >= p.dcap;            // very deep schedule: one trade per level, in order
+                if (seq) D = T;
+                // level l covers plan entries [OFF(l), OFF(l+1)); e2 = end of level l+1, fetched one level ahead
+                auto OFF = [&](int lv) -> int { return seq ? lv : (int)of[2 * lv]; };
+                int l = 0, base = OFF(0), e = OFF(1);
+                int e2 = (D >= 2) ? OFF(2) : e;
+                const uint2 none = make_uint2(0u, 0u);
+                uint2 ent_n = (base + myg < e) ? pl[base + myg] : none;
+                while (l < D) {
+                    const uint2 ent = ent_n;
+                    const bool act = base + myg < e;
+                    int nbase = base + NG, nl = l, ne = e;
+                    const bool level_end = nbase >= e;
+                    if (level_end) { nl = l + 1; nbase = e; ne = e2; }
+                    ent_n = (nl < D && nbase + myg < ne) ? pl[nbase + myg] : none;
+                    if (level_end) e2 = (nl + 2 <= D) ? OFF(nl + 2) : ne;
+                    const bool ap = trade_rows<G, V>(rows, RS, act, ent.x & 0xffffu, ent.x >> 16, ent.y, null_id, p.keys, sub);
+                    my_applied += (ap && sub == 0) ? 1u : 0u;
+                    if (level_end) __syncthreads();
+                    base = nbase; l = nl; e = ne;
+                }
+            }
+            __syncthreads();
+
+            // ---- outputs -----------------------------------------------------
+            const bool emit = null_id >= p.ix.null_lo;
+            if (emit && p.applied) {
+                my_applied = __reduce_add_sync(0xffffffffu, my_applied);
+                if (lane == 0 && my_applied) atomicAdd(&s_applied, my_applied);
+            }
+            if (emit && p.out_rows) {
+                uint32_t *dst = p.out_rows + (size_t)local * R * p.wprL;
+                for (int i = tid; i < R * p.wprL; i += blockDim.x) {
+                    int r = i / p.wprL, c = i - r * p.wprL;
+                    dst[i] = rows[(size_t)r * RS + c];
+                }
+            }
+            if (emit && p.sc.n_profiles > 0) {
+                for (int pr = wid; pr < p.sc.n_profiles; pr += NW) {
+                    SetScore sc = score_module_call(rows, RS, p.sc.rows_are_samples != 0, p.sc.modules + (size_t)pr * p.sc.k,
+                                                    p.sc.k, p.sc.w + (size_t)pr * p.sc.S, p.sc.mask + (size_t)pr * p.sc.wprS,
+                                                    p.sc.S, lane);
+                    if (lane == 0) {
+                        if (sc.W >= p.sc.z_obs[pr]) atomicAdd(&p.sc.n_ge[pr], 1ull);
+                        if (p.sc.null_scores) p.sc.null_scores[(size_t)pr * p.sc.n_total + (null_id - p.ix.null_lo)] = sc.W;
+                    }
+                }
+            }
+            __syncthreads();
+            if (emit && p.applied && tid == 0) p.applied[null_id - p.ix.null_lo] = s_applied;
+        }
+        if (p.save_carry) {
+            uint32_t *dst = p.carry + (size_t)u * R * RS;
+            for (int i = tid; i < nvec; i += blockDim.x)
+                reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(rows)[i];
+        }
+        __syncthreads();
+    }
+}
+
