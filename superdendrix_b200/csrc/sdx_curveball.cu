@@ -133,14 +133,14 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
         cfg->LB = per_sm >= 4 ? (cfg->threads <= 128 ? 1 : (cfg->threads <= 256 ? 2 : 0)) : 0;
         if (const char *e = getenv("SDX_TRADE_LB")) {
             const int lb = atoi(e);
-            if (lb >= 0 && lb <= 7 && cfg->threads <= lb_threads(lb)) cfg->LB = lb;
+            if (lb >= 0 && lb <= 9 && cfg->threads <= lb_threads(lb)) cfg->LB = lb;
         }
         cfg->grid_cap = 1 << 30;
         {
             int resident = per_sm;                                      // shared memory limit
             const int by_threads = 2048 / cfg->threads;
             if (resident > by_threads) resident = by_threads;
-            if (cfg->LB != 0 && resident > (cfg->LB == 3 ? 4 : (cfg->LB == 5 ? 3 : 5))) resident = cfg->LB == 3 ? 4 : (cfg->LB == 5 ? 3 : 5);
+            if (cfg->LB != 0 && resident > lb_blocks(cfg->LB)) resident = lb_blocks(cfg->LB);
             cfg->slots = resident * c->sm_count;
         }
     } else {
@@ -167,7 +167,7 @@ static cudaError_t launch_trade(const TradeConfig &cfg, int grid, cudaStream_t s
         return cudaGetLastError();
     }
     if (cfg.smem) {
-        auto kern = cfg.LB == 1 ? k_trade<G, V, true, 1> : (cfg.LB == 2 ? k_trade<G, V, true, 2> : (cfg.LB == 3 ? k_trade<G, V, true, 3> : (cfg.LB == 4 ? k_trade<G, V, true, 4> : (cfg.LB == 5 ? k_trade<G, V, true, 5> : (cfg.LB == 6 ? k_trade<G, V, true, 6> : (cfg.LB == 7 ? k_trade<G, V, true, 7> : k_trade<G, V, true, 0>))))));
+        auto kern = cfg.LB == 1 ? k_trade<G, V, true, 1> : (cfg.LB == 2 ? k_trade<G, V, true, 2> : (cfg.LB == 3 ? k_trade<G, V, true, 3> : (cfg.LB == 4 ? k_trade<G, V, true, 4> : (cfg.LB == 5 ? k_trade<G, V, true, 5> : (cfg.LB == 6 ? k_trade<G, V, true, 6> : (cfg.LB == 7 ? k_trade<G, V, true, 7> : (cfg.LB == 8 ? k_trade<G, V, true, 8> : (cfg.LB == 9 ? k_trade<G, V, true, 9> : k_trade<G, V, true, 0>))))))));
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;
         kern<<<grid, cfg.threads, cfg.smem_bytes, st>>>(args);
