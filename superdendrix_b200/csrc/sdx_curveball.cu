@@ -351,7 +351,18 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
         const size_t smem_cap = c->smem_optin > 4096 ? c->smem_optin - 2048 : 0;
         const size_t lv_tiles = sizeof(uint32_t) * PL_NT * (PL_TT + 1) + sizeof(uint16_t) * PL_NT * (PL_TT + 2);
         const bool last_in_smem = lv_tiles + (size_t)PL_NT * R * 2 <= smem_cap;
-        const size_t lv_smem = lv_tiles + (last_in_smem ? (size_t)PL_NT * R * 2 : 0);
+        // EXPERIMENTAL level capacity (k_plan_levels, SDX_PLAN_CAP=<trades per level>): with 32 (one round of the trade
+        // kernel's CTA per level) a C0 null needs 62 rounds instead of 79, but every round then ends in a barrier and the
+        // measured step is slower (trade 11.1 vs 10.8 ms per launch, plan kernels 8.8 % -> 14.7 % of the step); 64 gives
+        // trade 10.5 ms and the same plan cost.  Default: the earliest-level schedule (0).
+        int level_cap = 0;
+        if (T > 0 && !sparse) {
+            if (const char *e = getenv("SDX_PLAN_CAP")) level_cap = atoi(e);
+            if (level_cap < 0) level_cap = 0;
+            const size_t cnt_bytes = sizeof(uint16_t) * PL_NT * ((size_t)dcap + 1);
+            if (lv_tiles + (last_in_smem ? (size_t)PL_NT * R * 2 : 0) + cnt_bytes > smem_cap || level_cap > 65535) level_cap = 0;
+        }
+        const size_t lv_smem = lv_tiles + (last_in_smem ? (size_t)PL_NT * R * 2 : 0) + (level_cap > 0 ? sizeof(uint16_t) * PL_NT * ((size_t)dcap + 1) : 0);
         if (lv_smem > 48 * 1024)
             SDX_CUDA(c, cudaFuncSetAttribute(k_plan_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem));
 
@@ -398,7 +409,7 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
                 if (T > 0) {
                     k_plan_pairs<<<ceil_div((int64_t)n_local * Tp, 256), 256, 0, c->stream>>>(keys, ix, n_local, R, (int)T, Tp, (uint32_t *)p_pairs);
                     k_plan_levels<<<ceil_div(n_local, lv_threads), lv_threads, lv_smem, c->stream>>>(
-                        n_local, R, (int)T, Tp, (const uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux);
+                        n_local, R, (int)T, Tp, (const uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux, level_cap, dcap);
                     k_plan_sort<<<ceil_div(n_local, sort_warps), sort_warps * 32, sort_smem_warp * sort_warps, c->stream>>>(
                                                                           n_local, R, (int)T, Tp, dcap, (const uint32_t *)p_pairs,
                                                                           (const uint16_t *)p_lvl, d_depth, c->d_rowsize, sparse ? c->d_sp_desc : nullptr,

@@ -33,9 +33,15 @@ __global__ void k_plan_pairs(const __grid_constant__ PhiloxKeys keys, NullIndexi
 // tiles of PL_TT trades x PL_NT nulls so that every global access is a coalesced row segment.
 #define PL_NT 64
 #define PL_TT 32
+// cap > 0: at most `cap` trades per level (online first fit: the earliest level after both predecessors that still has
+// room).  With cap = the number of trades one CTA of the trade kernel runs at a time, every level is exactly one
+// round of that CTA, and the rounds per null drop from 79 (earliest-level schedule, half-empty second rounds) to 62
+// at C0 (ideal: T / cap = 60; tests/tools/exp_levels.py).  Any assignment that puts a trade after its two
+// predecessors is a valid schedule, so the nulls do not change.  A schedule that would need dcap levels or more is
+// reported as depth dcap (the trade kernel then runs that null in sequential order).
 __global__ void __launch_bounds__(PL_NT) k_plan_levels(int n_local, int R, int T, int Tp, const uint32_t *__restrict__ pairs,
                                                        uint16_t *__restrict__ lvl, int *__restrict__ depth,
-                                                       uint16_t *__restrict__ last_global) {
+                                                       uint16_t *__restrict__ last_global, int cap, int dcap) {
     extern __shared__ __align__(16) uint16_t plan_smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n0 = blockIdx.x * PL_NT, n = n0 + tid;
@@ -43,8 +49,12 @@ __global__ void __launch_bounds__(PL_NT) k_plan_levels(int n_local, int R, int T
     uint32_t *tile_p = reinterpret_cast<uint32_t *>(plan_smem);
     uint16_t *tile_l = reinterpret_cast<uint16_t *>(tile_p + PL_NT * (PL_TT + 1));
     uint16_t *last = last_global ? last_global + (size_t)blockIdx.x * PL_NT * R + tid : tile_l + PL_NT * (PL_TT + 2) + tid;
+    // fill[level][tid]: trades already assigned to a level (only with cap > 0); it follows last[] when that is in shared memory
+    uint16_t *fill = tile_l + PL_NT * (PL_TT + 2) + (last_global ? 0 : (size_t)PL_NT * R) + tid;
     for (int r = 0; r < R; ++r) last[(size_t)r * PL_NT] = 0;
-    int d = 0;
+    if (cap > 0)
+        for (int l = 0; l <= dcap; ++l) fill[(size_t)l * PL_NT] = 0;
+    int d = 0, lo = 1;                                             // lo: lowest level that still has room
     constexpr int PER = PL_NT / (PL_NT / 32);                      // null rows each warp loads per tile
     uint32_t nx[PER];                                              // next tile, in flight while the current one is processed
     auto fetch = [&](int t0) {
@@ -66,7 +76,14 @@ __global__ void __launch_bounds__(PL_NT) k_plan_levels(int n_local, int R, int T
             const uint32_t e = tile_p[tid * (PL_TT + 1) + c];
             const uint32_t a = e & 0xffffu, b = e >> 16;
             const int la = last[(size_t)a * PL_NT], lb = last[(size_t)b * PL_NT];
-            const int l = (la > lb ? la : lb) + 1;
+            int l = (la > lb ? la : lb) + 1;
+            if (cap > 0) {
+                if (l < lo) l = lo;
+                while (l < dcap && fill[(size_t)l * PL_NT] >= cap) ++l;
+                if (l > dcap) l = dcap;
+                ++fill[(size_t)l * PL_NT];
+                while (lo < dcap && fill[(size_t)lo * PL_NT] >= cap) ++lo;
+            }
             last[(size_t)a * PL_NT] = (uint16_t)l;
             last[(size_t)b * PL_NT] = (uint16_t)l;
             tile_l[tid * (PL_TT + 2) + c] = (uint16_t)l;
