@@ -151,6 +151,7 @@ static int condperm_run(sdx_ctx *c, const int32_t *prof, const int32_t *modules,
 extern "C" int sdx_condperm(sdx_ctx *c, int profile, const int32_t *module, int k, uint64_t seed, uint64_t perm_id0,
                             int64_t n_perm, int64_t *counts, double *real_W) {
     if (!c) return SDX_ERR_INVALID;
+    SDX_REQUIRE(c, c->d_feat && c->d_w, SDX_ERR_STATE, "matrix and weights must be uploaded first");
     SDX_REQUIRE(c, profile >= 0 && profile < c->P, SDX_ERR_INVALID, "profile index out of range");
     const int32_t pj = profile;
     return condperm_run(c, &pj, module, 1, k, seed, perm_id0, n_perm, counts, real_W);

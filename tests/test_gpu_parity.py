@@ -250,6 +250,67 @@ def test_null_pvalue_fixed_matches_oracle(eng, shape):
 
 
 # ---------------------------------------------------------------- error behaviour
+def test_c_abi_status_codes_through_ctypes():
+    """The boundary contract of include/sdx.h exercised without the Python wrapper: bad arguments, NULL handles and
+    calls in the wrong order return negative SDX_ERR_* codes with a message; nothing aborts and the context stays usable."""
+    import ctypes as C
+    from superdendrix_b200 import _capi
+    lib = _capi.load()
+    INVALID, STATE = -1, -3
+    ctx = C.c_void_p()
+    assert lib.sdx_create(99, C.byref(ctx)) == INVALID and not ctx.value
+    assert b"out of range" in lib.sdx_last_error(None)
+    assert lib.sdx_destroy(None) == INVALID
+    assert lib.sdx_create(0, C.byref(ctx)) == 0 and ctx.value
+    try:
+        i32p, i64p, f64p, u32p = (C.POINTER(t) for t in (C.c_int32, C.c_int64, C.c_double, C.c_uint32))
+        n64 = (C.c_int64 * 4)()
+        f64 = (C.c_double * 4)()
+        mod = (C.c_int32 * 3)(0, 1, 2)
+        hits = (_capi.Hit * 2)()
+        # nothing uploaded yet
+        assert lib.sdx_curveball(ctx, 1, 0, 1, -1, 1, None, None) == STATE
+        assert lib.sdx_score_sets(ctx, mod, None, 1, 3, f64, None, None, None) == STATE
+        assert lib.sdx_scan(ctx, 0, 3, 2, hits, n64) == STATE
+        assert lib.sdx_feature_scores(ctx, 0, f64, None, None, None) == STATE
+        assert lib.sdx_condperm(ctx, 0, mod, 3, 1, 0, 10, n64, f64) == STATE
+        assert lib.sdx_ranksum(ctx, mod, None, 1, 3, f64, f64, n64, None) == STATE
+        assert lib.sdx_null_pvalue(ctx, 1, 0, 4, -1, 1, 0, mod, 3, None, n64, None, f64) == STATE
+        assert len(lib.sdx_last_error(ctx)) > 0
+        # bad uploads
+        rows = np.zeros((4, 1), dtype=np.uint32)
+        rp = rows.ctypes.data_as(u32p)
+        assert lib.sdx_upload_matrix(ctx, None, 4, 20, 1) == INVALID
+        assert lib.sdx_upload_matrix(ctx, rp, 4, 20, 2) == INVALID                 # words_per_row must be ceil(S / 32)
+        assert lib.sdx_upload_matrix(ctx, rp, 0, 20, 1) == INVALID
+        assert lib.sdx_upload_weights(ctx, f64, None, 1, 4) == STATE              # matrix first
+        rows[:, 0] = [0b0111, 0b0011, 0b1000, 0b0101]
+        assert lib.sdx_upload_matrix(ctx, rp, 4, 20, 1) == 0
+        w = np.linspace(-1, 1, 20)
+        assert lib.sdx_upload_weights(ctx, w.ctypes.data_as(f64p), None, 1, 19) == INVALID
+        assert lib.sdx_upload_weights(ctx, None, None, 1, 20) == INVALID
+        w_nan = w.copy(); w_nan[3] = np.nan
+        assert lib.sdx_upload_weights(ctx, w_nan.ctypes.data_as(f64p), None, 1, 20) == INVALID
+        assert lib.sdx_upload_weights(ctx, w.ctypes.data_as(f64p), None, 1, 20) == 0
+        # bad calls on a ready context
+        assert lib.sdx_scan(ctx, 0, 4, 2, hits, n64) < 0                           # k > 3
+        assert lib.sdx_scan(ctx, 1, 3, 2, hits, n64) == INVALID                    # profile out of range
+        assert lib.sdx_score_sets(ctx, mod, None, 1, 9, f64, None, None, None) == INVALID      # k > SDX_MAX_K
+        bad = (C.c_int32 * 3)(0, 1, 4)
+        assert lib.sdx_score_sets(ctx, bad, None, 1, 3, f64, None, None, None) == INVALID      # feature index out of range
+        assert lib.sdx_curveball(ctx, 1, 0, -1, -1, 1, None, None) == INVALID
+        assert lib.sdx_set_burn_in(ctx, 1000, 4) == INVALID
+        assert lib.sdx_null_pvalue(ctx, 1, 0, 4, -1, 1, 7, mod, 3, None, n64, None, f64) == INVALID   # unknown statistic
+        # ... and it still works
+        assert lib.sdx_score_sets(ctx, mod, None, 1, 3, f64, None, None, None) == 0
+        cases = [set(np.flatnonzero([(int(rows[g, 0]) >> s_) & 1 for s_ in range(20)])) for g in range(3)]
+        union = set().union(*cases)
+        want = 2 * sum(w[s_] for s_ in union if w[s_] > 0) - sum(abs(w[s_]) for c_ in cases for s_ in c_)
+        assert abs(f64[0] - want) < 1e-12
+    finally:
+        assert lib.sdx_destroy(ctx) == 0
+
+
 def test_errors_are_reported_not_fatal(eng):
     dense, _, _ = synth.feature_matrix(100, 50)
     upload_dense(eng, dense)
