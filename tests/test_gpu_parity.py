@@ -724,6 +724,24 @@ def test_work_queue_kernel_is_bit_identical(monkeypatch):
                 assert res["n_ge"][p] == int((res["null_scores"][p] >= res["z_obs"][p]).sum())
 
 
+@pytest.mark.parametrize("cap", ["8", "32", "5"])
+def test_capacity_level_schedule_gives_the_same_nulls(monkeypatch, cap):
+    """SDX_PLAN_CAP: a first-fit level schedule with at most `cap` trades per level is another valid order of the same
+    trades, so nulls and applied-trade counts must not change (including when the schedule overflows into the
+    sequential fallback: cap = 5 needs more levels than dcap allows on the C0 shape)."""
+    monkeypatch.setenv("SDX_PLAN_CAP", cap)
+    cases, _ = curveball_cases()
+    with Engine(0) as e2:
+        for name in ("c0_shape", "square", "wide_small"):
+            dense = cases[name]["dense"]
+            upload_dense(e2, dense)
+            obs = rows_of(dense)
+            R = obs.shape[0]
+            want, want_ap = oracle.curveball_nulls(obs, 21, 0, 6, 5 * R, 3)
+            got, got_ap = e2.curveball(21, 0, 6, -1, 3)
+            assert np.array_equal(got_ap, want_ap) and np.array_equal(got, want), name
+
+
 # ---------------------------------------------------------------- individual contributions
 def test_contributions_match_the_reference_arithmetic(eng):
     """utils/compute_individual_contribution_SELECT.py:69-85 restated with Python sets, against the GPU sums."""
