@@ -356,7 +356,7 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
         // measured step is slower (trade 11.1 vs 10.8 ms per launch, plan kernels 8.8 % -> 14.7 % of the step); 64 gives
         // trade 10.5 ms and the same plan cost.  Default: the earliest-level schedule (0).
         int level_cap = 0;
-        if (T > 0 && !sparse) {
+        if (T > 0) {
             if (const char *e = getenv("SDX_PLAN_CAP")) level_cap = atoi(e);
             if (level_cap < 0) level_cap = 0;
             const size_t cnt_bytes = sizeof(uint16_t) * PL_NT * ((size_t)dcap + 1);
