@@ -122,6 +122,10 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
             cfg->persist_smem = ns * per_slot;
         }
         cfg->smem_bytes = bytes < 16 ? 16 : bytes;
+        if (const char *e = getenv("SDX_TRADE_PAD_SMEM")) {       // experiments only: fewer resident CTAs per SM
+            const size_t pad = (size_t)atol(e);
+            if (cfg->smem_bytes + pad <= budget) cfg->smem_bytes += pad;
+        }
         int per_sm = (int)((228 * 1024) / (cfg->smem_bytes + 1024 + 64));
         if (per_sm < 1) per_sm = 1;
         int warps = 40 / per_sm;                  // aim at ~40 resident warps per SM
