@@ -34,6 +34,8 @@ if ROOT not in sys.path:
 
 NULLS_PER_STEP = 100_000
 CHAIN_LEN, BURN_ROUNDS, POOL_SIZE = 16, 32, 1480      # short chains from a burnt-in pool: stationary nulls
+if os.environ.get("SDX_BENCH_CHAINS"):                # experiments only: "chain_len,burn,pool"
+    CHAIN_LEN, BURN_ROUNDS, POOL_SIZE = (int(x) for x in os.environ["SDX_BENCH_CHAINS"].split(","))
 SEED = 1764          # the reference's default -rs (src/generate_null_matrices.py:32)
 POPC_PEAK_NOMINAL = 148 * 16 * 1.965e9     # 32-bit popc/s
 NCU_DRAM_BYTES_PER_NULL = (62717952.0 + 299264.0) / 4000         # profiles/r01_k_trade_traffic_g.csv: the trade plan, 8 B per trade
@@ -237,7 +239,7 @@ def run_ours(args):
         barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         l0 = eng.total_launches()
-        kernel_ms, plan_ms, ge = 0.0, 0.0, 0
+        kernel_ms, plan_ms, ge, tl = 0.0, 0.0, 0, 0
         t0 = time.perf_counter()
         for i in range(steps):
             flush.zero_()                      # L2 flush between timed iterations (256 MiB > 126 MB L2)
@@ -247,20 +249,21 @@ def run_ours(args):
             tm = eng.timing()
             kernel_ms += tm["trade_ms"]
             plan_ms += tm["plan_ms"]
+            tl += tm["trade_launches"]
         barrier()
         wall = time.perf_counter() - t0
         ms = sum(a.elapsed_time(b) for a, b in ev)
         if os.environ.get("SDX_BENCH_DEBUG"):
             print("per-step ms:", [round(a.elapsed_time(b), 2) for a, b in ev], file=sys.stderr)
         launches = eng.total_launches() - l0
-        return ms, kernel_ms, plan_ms, launches, ge, wall
+        return ms, kernel_ms, plan_ms, launches, ge, wall, tl
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms, trade_ms, plan_ms, launches, ge, wall = timed(step_resident, args.steps, args.warmup, 0)
+    ms, trade_ms, plan_ms, launches, ge, wall, trade_launches = timed(step_resident, args.steps, args.warmup, 0)
     sampler.stop_flag.set()
     sampler.join()
-    ms_e2e, _, _, _, ge2, _ = timed(step_e2e, args.steps, max(args.warmup, 1), 10_000)
+    ms_e2e, _, _, _, ge2, _, _ = timed(step_e2e, args.steps, max(args.warmup, 1), 10_000)
 
     t = torch.tensor([ms, ms_e2e, trade_ms, plan_ms], dtype=torch.float64, device="cuda")
     counts[0] = ge
@@ -286,10 +289,10 @@ def run_ours(args):
         # algorithmic bytes per null: read observed + 4 row transfers per trade
         wd = wpr
         bytes_per_null = R * wd * 4 + T * 4 * wd * 4
-        per_launch_nulls = n                      # one k_trade launch covers the step's nulls (<= 32768 per launch, see below)
-        trade_launches = args.steps * -(-n // 32768)
+        trade_launches = max(int(trade_launches), 1)         # k_trade launches in the timed region (sdx_timing.trade_launches)
+        per_launch_nulls = n * args.steps / trade_launches   # whole waves of chains per launch
         avg_launch_ms = trade_ms / trade_launches
-        achieved = (bytes_per_null * (n / -(-n // 32768)) / 1e9) / (avg_launch_ms / 1e3)
+        achieved = (bytes_per_null * per_launch_nulls / 1e9) / (avg_launch_ms / 1e3)
         popc_per_null = T * 2 * wd
         int_peaks = eng.measure_int_peaks()          # POPC / LOP3 rates measured on this box, outside the timed region
         line = {
@@ -308,10 +311,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(8 + 8), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_trade", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_NULL * (n / -(-n // 32768)),
+                         "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_NULL * per_launch_nulls,
                          "traffic_source": "ncu capture profiles/r01_k_trade_traffic_g.csv (dram__bytes_read.sum + dram__bytes_write.sum of one 4000-null launch): per null x nulls per launch",
                          "peak_source": peaks_src,
-                         "bytes_per_null": bytes_per_null, "avg_launch_ms": avg_launch_ms,
+                         "bytes_per_null": bytes_per_null, "avg_launch_ms": avg_launch_ms, "nulls_per_launch": per_launch_nulls, "trade_launches": trade_launches,
                          "kernel_share_of_step": trade_ms / ms, "plan_share_of_step": plan_ms / ms,
                          "popc_per_s": popc_per_null * value / world, "popc_frac_of_nominal": popc_per_null * value / world / POPC_PEAK_NOMINAL,
                          "popc_peak_measured": int_peaks["popc_per_s"], "lop3_peak_measured": int_peaks["lop3_per_s"],

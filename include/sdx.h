@@ -59,7 +59,7 @@ typedef struct sdx_timing {
     float score_ms;    /* stand-alone scorer / scanner / perm / rank kernels */
     float total_ms;    /* first launch to last launch of the call           */
     int32_t launches;  /* kernels launched by the call                      */
-    int32_t reserved;
+    int32_t trade_launches; /* launches of the trade kernel among them (nulls per launch = n / trade_launches) */
 } sdx_timing;
 
 int sdx_version(void);

@@ -34,7 +34,7 @@ class Hit(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("plan_ms", C.c_float), ("trade_ms", C.c_float), ("score_ms", C.c_float),
-                ("total_ms", C.c_float), ("launches", C.c_int32), ("reserved", C.c_int32)]
+                ("total_ms", C.c_float), ("launches", C.c_int32), ("trade_launches", C.c_int32)]
 
 
 _u32p = C.POINTER(C.c_uint32)

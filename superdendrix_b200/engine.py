@@ -65,7 +65,7 @@ class Engine:
         t = _capi.Timing()
         self._check(self._lib.sdx_get_timing(self._ctx, C.byref(t)))
         return {"plan_ms": t.plan_ms, "trade_ms": t.trade_ms, "score_ms": t.score_ms, "total_ms": t.total_ms,
-                "launches": t.launches}
+                "launches": t.launches, "trade_launches": t.trade_launches}
 
     def total_launches(self) -> int:
         n = C.c_int64(0)
