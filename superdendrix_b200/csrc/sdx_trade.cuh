@@ -94,7 +94,7 @@ __device__ __forceinline__ bool trade_row_ptrs(uint32_t *row_a, uint32_t *row_b,
     // one reduction for both maxima: k <= n / 2 and n < 2^15, and the group with the largest n that trades has k > 0
     const uint32_t kmax = __reduce_max_sync(FULL, k);
     if (kmax == 0) return false;                        // warp-uniform
-    const uint32_t nmax = __reduce_max_sync(FULL, go ? n : 0u);
+    const uint32_t nmax = __any_sync(FULL, go && n > 64u) ? 65u : 0u;   // only "does any trade of the warp need the wide mask" matters
     uint32_t off = (inc - packed) >> 16;                // rank of this lane's first symmetric-difference element
     uint32_t pick[V];
 

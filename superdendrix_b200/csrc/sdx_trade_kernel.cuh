@@ -104,7 +104,10 @@ __global__ void __launch_bounds__(lb_threads(LB), lb_blocks(LB)) k_trade(const _
                     if (level_end) { nl = l + 1; nbase = e; ne = e2; }
                     ent_n = (nl < D && nbase + myg < ne) ? pl[nbase + myg] : none;
                     if (level_end) e2 = (nl + 2 <= D) ? OFF(nl + 2) : ne;
-                    const bool ap = trade_rows<G, V>(rows, RS, act, ent.x & 0xffffu, ent.x >> 16, ent.y, null_id, p.keys, sub);
+                    // a warp without a trade in this round (the half-empty last round of a level) skips the call
+                    bool ap = false;
+                    if (__any_sync(0xffffffffu, act))
+                        ap = trade_rows<G, V>(rows, RS, act, ent.x & 0xffffu, ent.x >> 16, ent.y, null_id, p.keys, sub);
                     my_applied += (ap && sub == 0) ? 1u : 0u;
                     if (level_end) __syncthreads();
                     base = nbase; l = nl; e = ne;
