@@ -149,16 +149,19 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
         }
     } else {
         cfg->smem_bytes = 0;
-        cfg->LB = 0;
+        // Rows live in global memory / L2.  16 warps per CTA (one trade per warp at G = 32), two CTAs per SM at 64 registers
+        // (launch bounds (512, 2)): C3 slice 53.9 -> 44.6 ms per 4 096 nulls against one CTA of 128 registers per SM.
+        cfg->LB = cfg->V <= 5 ? 10 : 0;          // 8 words per lane spill too much at 64 registers
+        if (const char *e = getenv("SDX_TRADE_LB")) { cfg->LB = atoi(e) == 10 ? 10 : 0; }
         int warps = 16;
         if (warps_env >= 1 && warps_env <= 16) warps = warps_env;
         cfg->threads = warps * 32;
         size_t per = bytes;
-        // One CTA of 16 warps x 128 registers fills an SM, so the grid is a whole number of CTAs per SM: 150 CTAs on 148 SMs
-        // ran as two waves (C3: 22.2 ms per 1 024 nulls against 13.4 ms with 148 or 296).  The working set of one wave
-        // (148 x 640 KB at C3) stays close to the L2 size.
-        int cap = (int)((size_t)96 * 1024 * 1024 / per);
-        cap = cap < c->sm_count ? c->sm_count : (cap / c->sm_count) * c->sm_count;
+        // The grid is a whole number of resident CTAs per SM (150 CTAs on 148 SMs ran as two waves: 22.2 ms per 1 024 C3
+        // nulls against 13.4 ms); the working set of a wave stays within a small multiple of the L2 size.
+        const int per_wave = (cfg->LB == 10 ? 2 : 1) * c->sm_count;
+        int cap = (int)((size_t)192 * 1024 * 1024 / per);
+        cap = cap < per_wave ? per_wave : (cap / per_wave) * per_wave;
         if (const char *e = getenv("SDX_TRADE_GRID_CAP")) { const int v = atoi(e); if (v >= 1) cap = v; }   // experiments only
         cfg->grid_cap = cap;
         cfg->slots = cap;
@@ -180,7 +183,8 @@ static cudaError_t launch_trade(const TradeConfig &cfg, int grid, cudaStream_t s
         if (e != cudaSuccess) return e;
         kern<<<grid, cfg.threads, cfg.smem_bytes, st>>>(args);
     } else {
-        k_trade<G, V, false, 0><<<grid, cfg.threads, 0, st>>>(args);
+        if (cfg.LB == 10) k_trade<G, V, false, 10><<<grid, cfg.threads, 0, st>>>(args);
+        else k_trade<G, V, false, 0><<<grid, cfg.threads, 0, st>>>(args);
     }
     return cudaGetLastError();
 }

@@ -50,10 +50,10 @@ static __device__ __noinline__ SetScore score_module_call(const uint32_t *rows, 
     return score_module(rows, RS, rows_are_samples, mod, k, w, mask, S, lane);
 }
 
-// LB selects the launch bounds: 0 = (512, 1), 1 = (128, 5), 2 = (256, 5), 3 = (256, 4), 4 = (192, 5), 5 = (256, 3), 6 = (64, 5), 7 = (96, 5), 8 = (192, 4), 9 = (160, 4) — all
+// LB selects the launch bounds: 0 = (512, 1), 1 = (128, 5), 2 = (256, 5), 3 = (256, 4), 4 = (192, 5), 5 = (256, 3), 6 = (64, 5), 7 = (96, 5), 8 = (192, 4), 9 = (160, 4), 10 = (512, 2; global-memory variant) — all
 // but 0 bound the registers so that five CTAs (five nulls) stay resident per SM when the matrix fits five times in shared memory.
-constexpr int lb_threads(int lb) { return lb == 0 ? 512 : (lb == 1 ? 128 : ((lb == 4 || lb == 8) ? 192 : (lb == 6 ? 64 : (lb == 7 ? 96 : (lb == 9 ? 160 : 256))))); }
-constexpr int lb_blocks(int lb) { return lb == 0 ? 1 : ((lb == 3 || lb == 8 || lb == 9) ? 4 : (lb == 5 ? 3 : 5)); }
+constexpr int lb_threads(int lb) { return (lb == 0 || lb == 10) ? 512 : (lb == 1 ? 128 : ((lb == 4 || lb == 8) ? 192 : (lb == 6 ? 64 : (lb == 7 ? 96 : (lb == 9 ? 160 : 256))))); }
+constexpr int lb_blocks(int lb) { return lb == 0 ? 1 : (lb == 10 ? 2 : ((lb == 3 || lb == 8 || lb == 9) ? 4 : (lb == 5 ? 3 : 5))); }
 template <int G, int V, bool SMEM, int LB>
 __global__ void __launch_bounds__(lb_threads(LB), lb_blocks(LB)) k_trade(const __grid_constant__ TradeArgs p) {
     extern __shared__ __align__(16) uint32_t smem_rows[];
