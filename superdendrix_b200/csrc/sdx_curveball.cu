@@ -183,8 +183,9 @@ static cudaError_t launch_trade(const TradeConfig &cfg, int grid, cudaStream_t s
         if (e != cudaSuccess) return e;
         kern<<<grid, cfg.threads, cfg.smem_bytes, st>>>(args);
     } else {
-        if (cfg.LB == 10) k_trade<G, V, false, 10><<<grid, cfg.threads, 0, st>>>(args);
-        else k_trade<G, V, false, 0><<<grid, cfg.threads, 0, st>>>(args);
+        const size_t cols = sizeof(uint32_t) * (size_t)args.sc.n_ufeat * args.sc.wprS;      // column cache of the scorer (<= 48 KB)
+        if (cfg.LB == 10) k_trade<G, V, false, 10><<<grid, cfg.threads, cols, st>>>(args);
+        else k_trade<G, V, false, 0><<<grid, cfg.threads, cols, st>>>(args);
     }
     return cudaGetLastError();
 }
@@ -312,7 +313,21 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
         for (int64_t i = 0; i < (int64_t)c->P * hs->k; ++i)
             SDX_REQUIRE(c, hs->modules[i] >= -1 && hs->modules[i] < c->F, SDX_ERR_INVALID, "module feature index out of range");
         void *pm, *pz, *ps = nullptr;
-        if ((rc = sdx_scratch(c, SL_MOD, sizeof(int32_t) * c->P * hs->k + 16, &pm))) return rc;
+        const size_t n_mod = (size_t)c->P * hs->k;
+        // column cache of the fused scorer (global-memory variant with samples as rows): distinct module features + remapped modules
+        std::vector<int32_t> ufeat, umod;
+        if (c->rows_are_samples && !cfg.smem && !sparse) {
+            std::vector<int32_t> slot((size_t)c->F, -1);
+            umod.assign(n_mod, -1);
+            for (size_t i = 0; i < n_mod; ++i) {
+                const int32_t g = hs->modules[i];
+                if (g < 0) continue;
+                if (slot[g] < 0) { slot[g] = (int32_t)ufeat.size(); ufeat.push_back(g); }
+                umod[i] = slot[g];
+            }
+            if (ufeat.empty() || sizeof(uint32_t) * ufeat.size() * c->wprS > 48 * 1024) { ufeat.clear(); umod.clear(); }
+        }
+        if ((rc = sdx_scratch(c, SL_MOD, sizeof(int32_t) * (2 * n_mod + ufeat.size()) + 16, &pm))) return rc;
         if ((rc = sdx_scratch(c, SL_Z, (sizeof(double) + sizeof(unsigned long long)) * c->P + 16, &pz))) return rc;
         d_zobs = (double *)pz;
         d_nge = (unsigned long long *)((char *)pz + sizeof(double) * c->P);
@@ -325,6 +340,13 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
         sc.n_profiles = c->P; sc.k = hs->k; sc.modules = (const int32_t *)pm; sc.w = c->d_w; sc.mask = c->d_mask;
         sc.z_obs = d_zobs; sc.n_ge = d_nge; sc.null_scores = d_scores; sc.n_total = n_nulls;
         sc.S = c->S; sc.wprS = c->wprS; sc.rows_are_samples = c->rows_are_samples;
+        if (!ufeat.empty()) {
+            int32_t *d_umod = (int32_t *)pm + n_mod, *d_ufeat = d_umod + n_mod;
+            SDX_CUDA(c, cudaMemcpyAsync(d_umod, umod.data(), sizeof(int32_t) * n_mod, cudaMemcpyHostToDevice, c->stream));
+            SDX_CUDA(c, cudaMemcpyAsync(d_ufeat, ufeat.data(), sizeof(int32_t) * ufeat.size(), cudaMemcpyHostToDevice, c->stream));
+            SDX_CUDA(c, cudaStreamSynchronize(c->stream));          // the host vectors go out of scope before the launch
+            sc.umod = d_umod; sc.ufeat = d_ufeat; sc.n_ufeat = (int)ufeat.size();
+        }
         if (hs->z_obs) {
             SDX_CUDA(c, cudaMemcpyAsync(d_zobs, hs->z_obs, sizeof(double) * c->P, cudaMemcpyHostToDevice, c->stream));
         } else {

@@ -295,18 +295,26 @@ __device__ __forceinline__ SetScore score_module(const uint32_t *__restrict__ ro
             }
         }
     } else {
-        for (int s = lane; s < S; s += 32) {
-            if (!((mask[s >> 5] >> (s & 31)) & 1u)) continue;
-            int mult = 0;
+        // lane <- the 32 samples of mask word wi, in ascending order: the same partition and order of the fp64 sums as
+        // the branch above, so both orientations (and the column cache of k_trade) give bit-identical W for equal sets
+        const int nw = (S + 31) >> 5;
+        for (int wi = lane; wi < nw; wi += 32) {
+            uint32_t m = mask[wi];
+            while (m) {
+                const int bp = __ffs(m) - 1;
+                m &= m - 1;
+                const int s = wi * 32 + bp;
+                int mult = 0;
 #pragma unroll
-            for (int j = 0; j < SDX_MAX_K; ++j)
-                if (g[j] >= 0) mult += (rows[(size_t)s * RS + (g[j] >> 5)] >> (g[j] & 31)) & 1u;
-            if (mult) {
-                const double ws = w[s];
-                ++cov; tot += mult;
-                if (ws > 0.0) { pos += ws; ++act; }
-                neg += (double)mult * fabs(ws);
-                sw += ws;
+                for (int j = 0; j < SDX_MAX_K; ++j)
+                    if (g[j] >= 0) mult += (rows[(size_t)s * RS + (g[j] >> 5)] >> (g[j] & 31)) & 1u;
+                if (mult) {
+                    const double ws = w[s];
+                    ++cov; tot += mult;
+                    if (ws > 0.0) { pos += ws; ++act; }
+                    neg += (double)mult * fabs(ws);
+                    sw += ws;
+                }
             }
         }
     }

@@ -17,6 +17,11 @@ struct ScoreArgs {
     int64_t n_total;                  // row length of null_scores
     int S, wprS;
     int rows_are_samples;
+    // column cache (k_trade, global-memory variant, rows are samples): the distinct features of all modules, and the
+    // modules as indices into that list.  n_ufeat = 0: not used.
+    const int32_t *ufeat;             // n_ufeat
+    const int32_t *umod;              // P x k
+    int n_ufeat;
 };
 
 struct TradeArgs {
@@ -128,7 +133,31 @@ __global__ void __launch_bounds__(lb_threads(LB), lb_blocks(LB)) k_trade(const _
                     dst[i] = rows[(size_t)r * RS + c];
                 }
             }
-            if (emit && p.sc.n_profiles > 0) {
+            if (!SMEM && emit && p.sc.n_profiles > 0 && p.sc.n_ufeat > 0) {
+                // Rows are samples and the module features are columns: gather the columns of the distinct module features
+                // ONCE per null into shared memory (n_ufeat x wprS words, one ballot per 32 samples and feature) and score
+                // every profile from there like a features-as-rows matrix, instead of walking all sample rows per profile.
+                uint32_t *cols = smem_rows;
+                const int wprS = p.sc.wprS;
+                for (int sb = wid; sb < wprS; sb += NW) {
+                    const int s = sb * 32 + lane;
+                    for (int d = 0; d < p.sc.n_ufeat; ++d) {
+                        const int g = p.sc.ufeat[d];
+                        const uint32_t bit = s < p.sc.S ? (rows[(size_t)s * RS + (g >> 5)] >> (g & 31)) & 1u : 0u;
+                        const uint32_t word = __ballot_sync(0xffffffffu, bit != 0);
+                        if (lane == 0) cols[(size_t)d * wprS + sb] = word;
+                    }
+                }
+                __syncthreads();
+                for (int pr = wid; pr < p.sc.n_profiles; pr += NW) {
+                    SetScore sc = score_module_call(cols, wprS, false, p.sc.umod + (size_t)pr * p.sc.k, p.sc.k,
+                                                    p.sc.w + (size_t)pr * p.sc.S, p.sc.mask + (size_t)pr * p.sc.wprS, p.sc.S, lane);
+                    if (lane == 0) {
+                        if (sc.W >= p.sc.z_obs[pr]) atomicAdd(&p.sc.n_ge[pr], 1ull);
+                        if (p.sc.null_scores) p.sc.null_scores[(size_t)pr * p.sc.n_total + (null_id - p.ix.null_lo)] = sc.W;
+                    }
+                }
+            } else if (emit && p.sc.n_profiles > 0) {
                 for (int pr = wid; pr < p.sc.n_profiles; pr += NW) {
                     SetScore sc = score_module_call(rows, RS, p.sc.rows_are_samples != 0, p.sc.modules + (size_t)pr * p.sc.k,
                                                     p.sc.k, p.sc.w + (size_t)pr * p.sc.S, p.sc.mask + (size_t)pr * p.sc.wprS,

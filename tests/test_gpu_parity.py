@@ -827,6 +827,11 @@ def test_c3_shape_global_memory_variant(eng):
         fr = bitpack.pack_rows(bitpack.unpack_rows(nulls[i], L).T)
         for p in range(P):
             assert abs(res["null_scores"][p, i] - oracle.score_set(fr, S, mods[p], w[p])[0]) <= 1e-9 * np.abs(w[p]).sum()
+    # ties count (src/superdendrix.py:192 uses >=): a null that equals the observed matrix must score EXACTLY z_obs although the
+    # nulls are scored from the column cache and the observed matrix from its sample rows
+    same = eng.null_pvalue(7, 0, 5, mods, n_trades=0, want_scores=True)
+    assert np.array_equal(same["null_scores"], np.repeat(same["z_obs"][:, None], 5, axis=1))
+    assert np.array_equal(same["n_ge"], np.full(P, 5))
 
 
 def test_c4_slice_batched_model_selection_statistics(eng):
