@@ -96,7 +96,7 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
     int warps_env = 0;
     if (const char *e = getenv("SDX_TRADE_G")) {
         const int g = atoi(e);
-        static const int gv[][2] = {{2, 16}, {4, 8}, {8, 4}, {8, 8}, {16, 4}, {32, 4}, {32, 5}, {32, 8}};
+        static const int gv[][2] = {{2, 16}, {4, 8}, {8, 4}, {8, 8}, {8, 20}, {16, 4}, {32, 4}, {32, 5}, {32, 8}};
         for (auto &q : gv)
             if (q[0] == g && q[0] * q[1] >= c->RS) { cfg->G = q[0]; cfg->V = q[1]; break; }
     }
@@ -149,17 +149,23 @@ static int pick_config(sdx_ctx *c, TradeConfig *cfg) {
         }
     } else {
         cfg->smem_bytes = 0;
-        // Rows live in global memory / L2.  16 warps per CTA (one trade per warp at G = 32), two CTAs per SM at 64 registers
-        // (launch bounds (512, 2)): C3 slice 53.9 -> 44.6 ms per 4 096 nulls against one CTA of 128 registers per SM.
-        cfg->LB = cfg->V <= 5 ? 10 : 0;          // 8 words per lane spill too much at 64 registers
+        // Rows live in global memory / L2 (C3: 1 000 rows of 157 words).  Measured on the C3 slice, 4 096 nulls, trade kernel only:
+        //   G = 32, V = 5, 16 warps, 1 CTA / SM (128 registers), 150 CTAs on 148 SMs      53.9 ms  (two waves: the first version)
+        //   the same with a grid of whole waves (148 CTAs)                                 32.1 ms
+        //   G = 32, V = 5, 16 warps, 2 CTAs / SM at 64 registers (launch bounds (512, 2))  29.6 ms
+        //   G = 8, V = 20, 4 warps, 4 CTAs / SM at 128 registers                           18.7 ms  <- rows of 129..160 words
+        // Fewer lanes per trade means more trades per instruction for the serial parts (Philox block, Floyd loop), and
+        // the grid is always a whole number of resident CTAs per SM.
+        int warps = 16, ctas_per_sm = 1;
+        if (c->RS > 128 && c->RS <= 160 && !getenv("SDX_TRADE_G")) { cfg->G = 8; cfg->V = 20; }
+        if (cfg->G == 8 && cfg->V == 20) { cfg->LB = 0; warps = 4; ctas_per_sm = 4; }
+        else if (cfg->V <= 5) { cfg->LB = 10; ctas_per_sm = 2; }      // 8 words per lane spill too much at 64 registers
+        else cfg->LB = 0;
         if (const char *e = getenv("SDX_TRADE_LB")) { cfg->LB = atoi(e) == 10 ? 10 : 0; }
-        int warps = 16;
         if (warps_env >= 1 && warps_env <= 16) warps = warps_env;
         cfg->threads = warps * 32;
         size_t per = bytes;
-        // The grid is a whole number of resident CTAs per SM (150 CTAs on 148 SMs ran as two waves: 22.2 ms per 1 024 C3
-        // nulls against 13.4 ms); the working set of a wave stays within a small multiple of the L2 size.
-        const int per_wave = (cfg->LB == 10 ? 2 : 1) * c->sm_count;
+        const int per_wave = ctas_per_sm * c->sm_count;
         int cap = (int)((size_t)192 * 1024 * 1024 / per);
         cap = cap < per_wave ? per_wave : (cap / per_wave) * per_wave;
         if (const char *e = getenv("SDX_TRADE_GRID_CAP")) { const int v = atoi(e); if (v >= 1) cap = v; }   // experiments only
@@ -196,6 +202,7 @@ static cudaError_t dispatch_trade(const TradeConfig &cfg, int grid, cudaStream_t
     if (cfg.G == 8 && cfg.V == 4) return launch_trade<8, 4>(cfg, grid, st, args, persist);
     if (cfg.G == 8 && cfg.V == 8) return launch_trade<8, 8>(cfg, grid, st, args, persist);
     if (cfg.G == 16 && cfg.V == 4) return launch_trade<16, 4>(cfg, grid, st, args, persist);
+    if (cfg.G == 8 && cfg.V == 20) return launch_trade<8, 20>(cfg, grid, st, args, persist);
     if (cfg.G == 32 && cfg.V == 4) return launch_trade<32, 4>(cfg, grid, st, args, persist);
     if (cfg.G == 32 && cfg.V == 5) return launch_trade<32, 5>(cfg, grid, st, args, persist);
     return launch_trade<32, 8>(cfg, grid, st, args, persist);
