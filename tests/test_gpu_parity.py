@@ -392,6 +392,33 @@ def test_scan_optimum_equals_the_reference_ilp_at_c0_size(eng):
             assert sorted(int(g) for g in top["features"][0] if g >= 0) == feats
 
 
+def test_maxk_null_statistic_equals_the_reference_ilp_on_every_null(eng):
+    """The reference's p-value compares the observed optimum with the ILP optimum of EVERY null (src/superdendrix.py:173-192).
+    The max_k statistic of the GPU path (per-null exhaustive scan) must equal that ILP — solved here by HiGHS on the
+    oracle's nulls of the C0 matrix — null by null, so exceedance counts are the reference's by construction."""
+    from oracle import milp
+    dense, _, _ = synth.feature_matrix(770, 400)
+    S, F = dense.shape
+    w = synth.weights(S, 1, seed=3)
+    upload_dense(eng, dense)
+    eng.upload_weights(w)
+    module = synth.pick_module(dense, 3)[None, :].astype(np.int32)
+    n = 24
+    res = eng.null_pvalue(1764, 0, n, module, stat=SDX_STAT_MAXK, want_scores=True)
+    z_ilp, _, optimal = milp.ilp_optimum(dense, w[0], 3, all_samples=False)
+    assert optimal and abs(res["z_obs"][0] - z_ilp) <= 1e-7 * np.abs(w).sum()
+    R, L, wpr, ras = eng.trade_shape()
+    nulls, _ = oracle.curveball_nulls(rows_of(dense), 1764, 0, n, 5 * R, 1)
+    want = []
+    for m in nulls:
+        d = bitpack.unpack_rows(m, L)
+        z, _, optimal = milp.ilp_optimum(d if ras else d.T, w[0], 3, all_samples=False)
+        assert optimal
+        want.append(z)
+    assert np.allclose(res["null_scores"][0], want, rtol=0, atol=1e-7 * np.abs(w).sum())
+    assert res["n_ge"][0] == int((np.array(want) >= z_ilp - 1e-9).sum())
+
+
 @pytest.mark.parametrize("S,F,density,k", [(200, 61, 0.05, 3), (130, 37, 0.5, 3), (64, 5, 0.3, 3), (40, 3, 0.4, 3),
                                            (40, 2, 0.4, 3), (33, 1, 0.5, 3), (300, 90, 0.02, 2), (300, 90, 0.02, 1),
                                            (1030, 70, 0.1, 3)])
