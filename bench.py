@@ -512,7 +512,7 @@ def secondary(eng, torch):
         w0 = synth.weights(770, 1, seed=3)[0]
         random.seed(3)
         lists2 = refport.presences(dense.astype(np.float64))
-        t_ilp, n_ilp = 0.0, 40
+        t_ilp, n_ilp = 0.0, 12
         for _ in range(n_ilp):
             null = refport.curveball(dense.astype(np.float64), lists2)
             t1 = time.perf_counter()
