@@ -62,7 +62,7 @@ struct sdx_ctx {
     int *d_nsamp = nullptr;       // P: popcount of the mask
 
     // reusable scratch
-    DevBuf scratch[16];
+    DevBuf scratch[20];
     // capacities (bytes) of the grow-only matrix / weight / pool buffers: re-uploads of the same shape never touch the allocator
     size_t cap_feat = 0, cap_samp = 0, cap_obs = 0, cap_rowsize = 0, cap_pool = 0, cap_w = 0, cap_mask = 0, cap_nsamp = 0;
 };

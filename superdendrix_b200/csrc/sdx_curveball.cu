@@ -217,7 +217,7 @@ struct HostScore {               // optional fused scoring request
     double *z_obs_out = nullptr;        // host out, P (or null)
 };
 
-enum { SL_LVL = 0, SL_PLAN, SL_AUX, SL_MOD, SL_Z, SL_SCORES, SL_CARRY, SL_OUT, SL_APPLIED, SL_WORK, SL_OFFS = 12, SL_PAIRS = 13 };
+enum { SL_LVL = 0, SL_PLAN, SL_AUX, SL_MOD, SL_Z, SL_SCORES, SL_CARRY, SL_OUT, SL_APPLIED, SL_WORK, SL_OFFS = 12, SL_PAIRS = 13, SL_RT = 16 };      // 10, 11, 14, 15: sdx_scan.cu
 
 // Builds (once per uploaded matrix) the sparse layout of the trade rows: rows of at most SP_TS carriers become
 // index lists, the others stay bit-packed.  Applicable when the rows are features, fit 32 words, the lists are the
@@ -372,11 +372,11 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
         const int64_t n_chains = (int64_t)(chain_last - chain_first + 1);
         // Nulls planned per launch.  A launch ends with a ragged tail (its slowest chains), so fewer, larger launches are
         // faster: 100 000 C1 nulls in chains of 16 run at 2.10 M/s with 32 768 per launch and 2.31 M/s with 131 072
-        // (one launch).  Bounded by ~4 GB of plan scratch (14 bytes per trade) and, when the nulls themselves are
+        // (one launch).  Bounded by ~4 GB of plan scratch (18 bytes per trade) and, when the nulls themselves are
         // returned, by the staging buffer.
         int64_t NB = 131072;
         {
-            const int64_t by_mem = ((int64_t)4 << 30) / (14 * (T > 0 ? T : 1));
+            const int64_t by_mem = ((int64_t)4 << 30) / (18 * (T > 0 ? T : 1));
             if (NB > by_mem) NB = by_mem;
             if (out_rows && NB > 32768) NB = 32768;
             if (NB < 1024) NB = 1024;
@@ -428,6 +428,15 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
         if ((rc = sdx_scratch(c, SL_LVL, lvl_bytes + sizeof(int) * n_local_max + 64, &p_lvl))) return rc;
         int *d_depth = (int *)((char *)p_lvl + lvl_bytes);
         if ((rc = sdx_scratch(c, SL_PLAN, (sparse ? sizeof(uint4) : sizeof(uint2)) * (size_t)n_local_max * Tn, &p_plan))) return rc;
+        // round table of k_trade (k_plan_sort): at most one round per trade
+        void *p_rt = nullptr;
+        const int rt_stride = (Tn + 4) & ~3;
+        const int per_round = (cfg.threads / 32) * (32 / cfg.G);
+        int *d_nrounds = nullptr;
+        if (!sparse) {
+            if ((rc = sdx_scratch(c, SL_RT, sizeof(uint32_t) * (size_t)n_local_max * rt_stride + sizeof(int) * (size_t)n_local_max + 64, &p_rt))) return rc;
+            d_nrounds = (int *)((uint32_t *)p_rt + (size_t)n_local_max * rt_stride);
+        }
         void *p_pairs;
         const int Tp = (Tn + 3) & ~3;                       // pairs row length: 16-byte aligned rows
         if ((rc = sdx_scratch(c, SL_PAIRS, sizeof(uint32_t) * (size_t)n_local_max * Tp + 64, &p_pairs))) return rc;
@@ -467,7 +476,7 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
                                                                           n_local, R, (int)T, Tp, dcap, (const uint32_t *)p_pairs,
                                                                           (const uint16_t *)p_lvl, d_depth, c->d_rowsize, sparse ? c->d_sp_desc : nullptr,
                                                                           sparse ? SP_TS : -1, p_plan,
-                                                                          (uint16_t *)p_offs, offs_stride);
+                                                                          (uint16_t *)p_offs, offs_stride, (uint32_t *)p_rt, rt_stride, d_nrounds, per_round);
                     timer.count(3);
                 }
                 cudaEventRecord(c->ev[3], c->stream);
@@ -475,6 +484,7 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
                 ta.keys = keys; ta.ix = ix; ta.observed = c->d_trade_obs; ta.work = (uint32_t *)p_work;
                 ta.carry = (uint32_t *)p_carry; ta.plan = p_plan; ta.n_units = (int)nch;
                 ta.offs = (const uint16_t *)p_offs; ta.depth = d_depth; ta.offs_stride = offs_stride; ta.dcap = dcap;
+                ta.rt = (const uint32_t *)p_rt; ta.nrounds = d_nrounds; ta.rt_stride = rt_stride;
                 ta.R = R; ta.RS = RS; ta.T = (int)T; ta.wprL = c->wprL;
                 ta.save_carry = need_carry && sg + 1 < n_segs;
                 if (save_states) { ta.carry = save_states + (size_t)cb * mat_words; ta.save_carry = 1; }

@@ -119,10 +119,13 @@ __device__ __forceinline__ int trade_class(int sa, int sb, int ts) {
     return kb > 8 ? 1 : (kb > 3 ? 2 : 3);
 }
 
+// Round table (k_trade): one u32 per round = the `ng` trades a CTA of the trade kernel runs at a time:
+//   bits 0-15 first plan entry, bits 16-30 number of trades, bit 31 last round of its level (barrier after it).
+// The kernel then needs no level bookkeeping at all.  rt == nullptr: not written (sparse / work-queue kernels use offs).
 __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const uint32_t *__restrict__ pairs,
                             const uint16_t *__restrict__ lvl, const int *__restrict__ depth, const int *__restrict__ rowsize,
                             const uint32_t *__restrict__ desc, int ts, void *__restrict__ plan, uint16_t *__restrict__ offs,
-                            int offs_stride) {
+                            int offs_stride, uint32_t *__restrict__ rt, int rt_stride, int *__restrict__ nrounds, int ng) {
     extern __shared__ uint32_t hist_smem[];        // per warp: dcap * SDX_NCLS + 2 bins
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n = blockIdx.x * (blockDim.x >> 5) + wid;
@@ -138,8 +141,13 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
         else out2[pos] = make_uint2(e, t);
     };
     const uint32_t *pr = pairs + (size_t)n * Tp;
+    uint32_t *rtn = rt ? rt + (size_t)n * rt_stride : nullptr;
     if (D >= dcap) {            // very deep schedule: fall back to the sequential order (always valid)
-        for (int t = lane; t < T; t += 32) emit((uint32_t)t, pr[t], (uint32_t)t);
+        for (int t = lane; t < T; t += 32) {
+            emit((uint32_t)t, pr[t], (uint32_t)t);
+            if (rtn) rtn[t] = (uint32_t)t | (1u << 16) | (1u << 31);       // one trade per round, a barrier after each
+        }
+        if (rtn && lane == 0) nrounds[n] = T;
         return;                 // k_trade runs such a null one trade per level, in order
     }
     const int NB = D * SDX_NCLS;                       // bin = (level - 1) * NCLS + class
@@ -169,6 +177,32 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
     uint16_t *of = offs + (size_t)n * offs_stride;
     for (int l = lane; l < D; l += 32) { of[2 * l] = (uint16_t)hist[l * SDX_NCLS]; of[2 * l + 1] = (uint16_t)hist[l * SDX_NCLS + 2]; }
     if (lane == 0) of[2 * D] = (uint16_t)T;
+    if (rtn) {
+        // rounds of level l: ceil(n_l / ng); their positions in the table = prefix sum over the levels
+        uint32_t rcarry = 0;
+        for (int base = 0; base < D; base += 32) {
+            const int l = base + lane;
+            uint32_t s0 = 0, nl = 0;
+            if (l < D) {
+                s0 = hist[l * SDX_NCLS];
+                nl = (l + 1 < D ? hist[(l + 1) * SDX_NCLS] : (uint32_t)T) - s0;
+            }
+            const uint32_t nr = (nl + ng - 1) / ng;
+            uint32_t inc = nr;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            uint32_t pos = rcarry + inc - nr;
+            for (uint32_t q = 0; q < nr; ++q) {
+                const uint32_t left = nl - q * ng;
+                rtn[pos + q] = (s0 + q * ng) | ((left < (uint32_t)ng ? left : (uint32_t)ng) << 16) | (q + 1 == nr ? 1u << 31 : 0u);
+            }
+            rcarry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) nrounds[n] = (int)rcarry;
+    }
     __syncwarp();
     for (int t = lane; t < T; t += 32) {
         const uint32_t e = pr[t];

@@ -31,7 +31,10 @@ struct TradeArgs {
     uint32_t *work;                   // gridDim.x x R x RS (global-resident variant only)
     uint32_t *carry;                  // n_units x R x RS: chain state between launches (or null)
     const void *plan;                 // n_local x T: uint2 (a | b << 16, t), or uint4 with the two row descriptors (sparse layout)
-    const uint16_t *offs;             // n_local x offs_stride level offsets
+    const uint16_t *offs;             // n_local x offs_stride level offsets (sparse / work-queue kernels)
+    const uint32_t *rt;               // n_local x rt_stride round table (k_trade), see k_plan_sort
+    const int *nrounds;               // n_local
+    int rt_stride;
     int dcap;                         // schedules at least this deep run in sequential order
     const int *depth;                 // n_local
     int offs_stride;
@@ -90,32 +93,28 @@ __global__ void __launch_bounds__(lb_threads(LB), lb_blocks(LB)) k_trade(const _
             // ---- trades, level by level -------------------------------------
             unsigned int my_applied = 0;
             if (T > 0) {
+                // One table entry per round (k_plan_sort): first plan entry, number of trades, "last round of its level".
+                // The next round's trade and the descriptor after that are in flight while the current trades run.
                 const uint2 *pl = reinterpret_cast<const uint2 *>(p.plan) + (size_t)local * T;
-                const uint16_t *of = p.offs + (size_t)local * p.offs_stride;
-                int D = p.depth[local];
-                const bool seq = D >= p.dcap;            // very deep schedule: one trade per level, in order
-                if (seq) D = T;
-                // level l covers plan entries [OFF(l), OFF(l+1)); e2 = end of level l+1, fetched one level ahead
-                auto OFF = [&](int lv) -> int { return seq ? lv : (int)of[2 * lv]; };
-                int l = 0, base = OFF(0), e = OFF(1);
-                int e2 = (D >= 2) ? OFF(2) : e;
+                const uint32_t *rt = p.rt + (size_t)local * p.rt_stride;
+                const int NR = p.nrounds[local];
                 const uint2 none = make_uint2(0u, 0u);
-                uint2 ent_n = (base + myg < e) ? pl[base + myg] : none;
-                while (l < D) {
+                uint32_t q = NR > 0 ? rt[0] : 0u;
+                uint32_t q_n = NR > 1 ? rt[1] : 0u;
+                uint2 ent_n = myg < (int)((q >> 16) & 0x7fffu) ? pl[(q & 0xffffu) + myg] : none;
+                for (int r = 0; r < NR; ++r) {
                     const uint2 ent = ent_n;
-                    const bool act = base + myg < e;
-                    int nbase = base + NG, nl = l, ne = e;
-                    const bool level_end = nbase >= e;
-                    if (level_end) { nl = l + 1; nbase = e; ne = e2; }
-                    ent_n = (nl < D && nbase + myg < ne) ? pl[nbase + myg] : none;
-                    if (level_end) e2 = (nl + 2 <= D) ? OFF(nl + 2) : ne;
+                    const bool act = myg < (int)((q >> 16) & 0x7fffu);
+                    const bool level_end = (q >> 31) != 0;
+                    q = q_n;
+                    ent_n = myg < (int)((q >> 16) & 0x7fffu) ? pl[(q & 0xffffu) + myg] : none;
+                    q_n = r + 2 < NR ? rt[r + 2] : 0u;
                     // a warp without a trade in this round (the half-empty last round of a level) skips the call
                     bool ap = false;
                     if (__any_sync(0xffffffffu, act))
                         ap = trade_rows<G, V>(rows, RS, act, ent.x & 0xffffu, ent.x >> 16, ent.y, null_id, p.keys, sub);
                     my_applied += (ap && sub == 0) ? 1u : 0u;
                     if (level_end) __syncthreads();
-                    base = nbase; l = nl; e = ne;
                 }
             }
             __syncthreads();
