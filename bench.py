@@ -38,7 +38,7 @@ if os.environ.get("SDX_BENCH_CHAINS"):                # experiments only: "chain
     CHAIN_LEN, BURN_ROUNDS, POOL_SIZE = (int(x) for x in os.environ["SDX_BENCH_CHAINS"].split(","))
 SEED = 1764          # the reference's default -rs (src/generate_null_matrices.py:32)
 POPC_PEAK_NOMINAL = 148 * 16 * 1.965e9     # 32-bit popc/s
-NCU_DRAM_BYTES_PER_NULL = (434623488.0 + 5162240.0) / 23680     # profiles/r01_k_trade_j.ncu-rep: plan (8 B per trade) + one 43 KB pool state per chain of 16
+NCU_DRAM_BYTES_PER_NULL = (439615744.0 + 6422784.0) / 23680     # profiles/r01_k_trade_k.ncu-rep: plan (8 B per trade) + one 43 KB pool state per chain of 16
 
 
 def workload():
@@ -312,7 +312,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_trade", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_NULL * per_launch_nulls,
-                         "traffic_source": "ncu --set full capture profiles/r01_k_trade_j.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum of one 23680-null launch of this configuration): per null x nulls per launch",
+                         "traffic_source": "ncu --set full capture profiles/r01_k_trade_k.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum of one 23680-null launch of this configuration): per null x nulls per launch",
                          "peak_source": peaks_src,
                          "bytes_per_null": bytes_per_null, "avg_launch_ms": avg_launch_ms, "nulls_per_launch": per_launch_nulls, "trade_launches": trade_launches,
                          "kernel_share_of_step": trade_ms / ms, "plan_share_of_step": plan_ms / ms,
