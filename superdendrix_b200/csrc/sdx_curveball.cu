@@ -421,7 +421,9 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
 
         void *p_lvl, *p_plan, *p_offs, *p_aux = nullptr, *p_carry = nullptr, *p_work = nullptr, *p_out = nullptr, *p_app = nullptr;
         const int offs_stride = (int)((2 * (T < dcap ? T : dcap) + 2 + 1) & ~1ll);
-        const size_t sort_smem_warp = sizeof(uint32_t) * ((size_t)dcap * SDX_NCLS + 2);
+        const size_t sort_bins = sizeof(uint32_t) * ((size_t)dcap * SDX_NCLS + 2);
+        const int cache_bins = sort_bins + 2 * (size_t)Tn + 4 <= 20 * 1024;                     // + one u16 per trade when two warps still fit
+        const size_t sort_smem_warp = sort_bins + (cache_bins ? sizeof(uint32_t) * (size_t)((Tn + 1) / 2) : 0);
         const int sort_warps = sort_smem_warp * 8 <= 40 * 1024 ? 8 : (sort_smem_warp * 4 <= 40 * 1024 ? 4 : 2);
         if ((rc = sdx_scratch(c, SL_OFFS, sizeof(uint16_t) * (size_t)n_local_max * offs_stride + 64, &p_offs))) return rc;
         const size_t lvl_bytes = ((sizeof(uint16_t) * (size_t)n_local_max * Tn + 15) / 16) * 16;
@@ -476,7 +478,7 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
                                                                           n_local, R, (int)T, Tp, dcap, (const uint32_t *)p_pairs,
                                                                           (const uint16_t *)p_lvl, d_depth, c->d_rowsize, sparse ? c->d_sp_desc : nullptr,
                                                                           sparse ? SP_TS : -1, p_plan,
-                                                                          (uint16_t *)p_offs, offs_stride, (uint32_t *)p_rt, rt_stride, d_nrounds, per_round);
+                                                                          (uint16_t *)p_offs, offs_stride, (uint32_t *)p_rt, rt_stride, d_nrounds, per_round, cache_bins);
                     timer.count(3);
                 }
                 cudaEventRecord(c->ev[3], c->stream);

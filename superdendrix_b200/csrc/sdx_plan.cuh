@@ -125,13 +125,17 @@ __device__ __forceinline__ int trade_class(int sa, int sb, int ts) {
 __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const uint32_t *__restrict__ pairs,
                             const uint16_t *__restrict__ lvl, const int *__restrict__ depth, const int *__restrict__ rowsize,
                             const uint32_t *__restrict__ desc, int ts, void *__restrict__ plan, uint16_t *__restrict__ offs,
-                            int offs_stride, uint32_t *__restrict__ rt, int rt_stride, int *__restrict__ nrounds, int ng) {
-    extern __shared__ uint32_t hist_smem[];        // per warp: dcap * SDX_NCLS + 2 bins
+                            int offs_stride, uint32_t *__restrict__ rt, int rt_stride, int *__restrict__ nrounds, int ng, int cache_bins) {
+    extern __shared__ uint32_t hist_smem[];        // per warp: dcap * SDX_NCLS + 2 bins + T u16 trade bins
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n = blockIdx.x * (blockDim.x >> 5) + wid;
     if (n >= n_local) return;
     const int D = depth[n];
-    uint32_t *hist = hist_smem + (size_t)wid * (dcap * SDX_NCLS + 2);
+    // per warp: dcap * NCLS + 2 bins, then the bin of every trade (u16) so that the second pass does not look it up again
+    // (cache_bins = 0 when T is too large for that: the second pass then recomputes the bin)
+    const size_t per_warp = (size_t)(dcap * SDX_NCLS + 2) + (cache_bins ? (size_t)((T + 1) / 2) : 0);
+    uint32_t *hist = hist_smem + (size_t)wid * per_warp;
+    uint16_t *bin = reinterpret_cast<uint16_t *>(hist + (dcap * SDX_NCLS + 2));
     const uint16_t *lv = lvl + (size_t)n * T;
     // plan entry: (a | b << 16, t) for k_trade; (a | b << 16, t, descriptor of a, descriptor of b) for k_trade_sparse
     uint2 *out2 = reinterpret_cast<uint2 *>(plan) + (size_t)n * T;
@@ -155,7 +159,9 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
     __syncwarp();
     for (int t = lane; t < T; t += 32) {
         const uint32_t e = pr[t];
-        atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16], ts)], 1u);
+        const int b = (lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16], ts);
+        if (cache_bins) bin[t] = (uint16_t)b;
+        atomicAdd(&hist[b], 1u);
     }
     __syncwarp();
     // exclusive scan of the bins -> start offsets
@@ -206,7 +212,8 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
     __syncwarp();
     for (int t = lane; t < T; t += 32) {
         const uint32_t e = pr[t];
-        uint32_t pos = atomicAdd(&hist[(lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16], ts)], 1u);
+        const int b = cache_bins ? (int)bin[t] : (lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16], ts);
+        const uint32_t pos = atomicAdd(&hist[b], 1u);
         emit(pos, e, (uint32_t)t);
     }
 }
