@@ -6,8 +6,8 @@
 //   src/superdendrix.py:166-197       the null loop / exceedance count (stat = fixed)
 //
 // Pipeline per batch of nulls (all on the ctx stream):
-//   k_plan_pairs    one thread per (null, trade): the trade's row pair (PAIR stream)       [sdx_plan.cuh]
-//   k_plan_levels   one THREAD per null walks its trades in order and assigns each the level
+//   k_plan_levels   [sdx_plan.cuh] one THREAD per null draws the row pair of each of its trades (PAIR stream), walks them in
+//                   order and assigns each the level
 //                   1 + max(level of the last trade that touched row a, row b).
 //                   Trades of one level touch pairwise disjoint rows, and every
 //                   earlier trade on those rows is in a lower level, so running
@@ -471,15 +471,14 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
                 const int n_local = (int)(nch * ix.seg_len);
                 cudaEventRecord(c->ev[2], c->stream);
                 if (T > 0) {
-                    k_plan_pairs<<<ceil_div((int64_t)n_local * Tp, 256), 256, 0, c->stream>>>(keys, ix, n_local, R, (int)T, Tp, (uint32_t *)p_pairs);
                     k_plan_levels<<<ceil_div(n_local, lv_threads), lv_threads, lv_smem, c->stream>>>(
-                        n_local, R, (int)T, Tp, (const uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux, level_cap, dcap);
+                        keys, ix, n_local, R, (int)T, Tp, (uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux, level_cap, dcap);
                     k_plan_sort<<<ceil_div(n_local, sort_warps), sort_warps * 32, sort_smem_warp * sort_warps, c->stream>>>(
                                                                           n_local, R, (int)T, Tp, dcap, (const uint32_t *)p_pairs,
                                                                           (const uint16_t *)p_lvl, d_depth, c->d_rowsize, sparse ? c->d_sp_desc : nullptr,
                                                                           sparse ? SP_TS : -1, p_plan,
                                                                           (uint16_t *)p_offs, offs_stride, (uint32_t *)p_rt, rt_stride, d_nrounds, per_round, cache_bins);
-                    timer.count(3);
+                    timer.count(2);
                 }
                 cudaEventRecord(c->ev[3], c->stream);
                 TradeArgs ta{};

@@ -18,18 +18,7 @@ struct NullIndexing {          // local null index (within a launch) -> global n
 // ---------------------------------------------------------------------------
 // plan: levels
 // ---------------------------------------------------------------------------
-// pairs of every trade of every null of the launch, one thread per (null, trade): pairs[n][t] = a | b << 16
-__global__ void k_plan_pairs(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T, int Tp,
-                             uint32_t *__restrict__ pairs) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = (int)(i / Tp), t = (int)(i - (int64_t)n * Tp);
-    if (n >= n_local) return;
-    uint32_t a = 0, b = 0;
-    if (t < T) trade_pair(keys, ix.id(n), (uint32_t)t, (uint32_t)R, a, b);
-    pairs[i] = a | (b << 16);
-}
-
-// One THREAD per null walks its trades in order; pairs come in and levels go out through shared-memory
+// One THREAD per null draws and walks its trades in order; pairs and levels go out through shared-memory
 // tiles of PL_TT trades x PL_NT nulls so that every global access is a coalesced row segment.
 #define PL_NT 64
 #define PL_TT 32
@@ -39,9 +28,9 @@ __global__ void k_plan_pairs(const __grid_constant__ PhiloxKeys keys, NullIndexi
 // at C0 (ideal: T / cap = 60; tests/tools/exp_levels.py).  Any assignment that puts a trade after its two
 // predecessors is a valid schedule, so the nulls do not change.  A schedule that would need dcap levels or more is
 // reported as depth dcap (the trade kernel then runs that null in sequential order).
-__global__ void __launch_bounds__(PL_NT) k_plan_levels(int n_local, int R, int T, int Tp, const uint32_t *__restrict__ pairs,
-                                                       uint16_t *__restrict__ lvl, int *__restrict__ depth,
-                                                       uint16_t *__restrict__ last_global, int cap, int dcap) {
+__global__ void __launch_bounds__(PL_NT) k_plan_levels(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T,
+                                                       int Tp, uint32_t *__restrict__ pairs, uint16_t *__restrict__ lvl,
+                                                       int *__restrict__ depth, uint16_t *__restrict__ last_global, int cap, int dcap) {
     extern __shared__ __align__(16) uint16_t plan_smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n0 = blockIdx.x * PL_NT, n = n0 + tid;
@@ -55,26 +44,15 @@ __global__ void __launch_bounds__(PL_NT) k_plan_levels(int n_local, int R, int T
     if (cap > 0)
         for (int l = 0; l <= dcap; ++l) fill[(size_t)l * PL_NT] = 0;
     int d = 0, lo = 1;                                             // lo: lowest level that still has room
-    constexpr int PER = PL_NT / (PL_NT / 32);                      // null rows each warp loads per tile
-    uint32_t nx[PER];                                              // next tile, in flight while the current one is processed
-    auto fetch = [&](int t0) {
-#pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            const int i = wid + q * (PL_NT / 32);
-            nx[q] = (n0 + i < n_local && t0 + lane < Tp) ? pairs[(size_t)(n0 + i) * Tp + t0 + lane] : 0u;      // coalesced 128-byte segments
-        }
-    };
-    fetch(0);
+    // The thread draws the row pair of each of its trades itself (PAIR stream): the Philox arithmetic is independent of the
+    // shared-memory chain of the level walk and fills its latency.  Pairs and levels leave through the tiles, coalesced.
+    const uint64_t null_id = ix.id(n < n_local ? n : 0);
     for (int t0 = 0; t0 < T; t0 += PL_TT) {
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < PER; ++q) tile_p[(wid + q * (PL_NT / 32)) * (PL_TT + 1) + lane] = nx[q];
-        __syncthreads();
-        if (t0 + PL_TT < T) fetch(t0 + PL_TT);
         const int cnt = T - t0 < PL_TT ? T - t0 : PL_TT;
         for (int c = 0; c < cnt; ++c) {
-            const uint32_t e = tile_p[tid * (PL_TT + 1) + c];
-            const uint32_t a = e & 0xffffu, b = e >> 16;
+            uint32_t a, b;
+            trade_pair(keys, null_id, (uint32_t)(t0 + c), (uint32_t)R, a, b);
+            tile_p[tid * (PL_TT + 1) + c] = a | (b << 16);
             const int la = last[(size_t)a * PL_NT], lb = last[(size_t)b * PL_NT];
             int l = (la > lb ? la : lb) + 1;
             if (cap > 0) {
@@ -91,7 +69,11 @@ __global__ void __launch_bounds__(PL_NT) k_plan_levels(int n_local, int R, int T
         }
         __syncthreads();
         for (int i = wid; i < PL_NT; i += PL_NT / 32)
-            if (n0 + i < n_local && t0 + lane < T) lvl[(size_t)(n0 + i) * T + t0 + lane] = tile_l[i * (PL_TT + 2) + lane];
+            if (n0 + i < n_local && t0 + lane < T) {
+                lvl[(size_t)(n0 + i) * T + t0 + lane] = tile_l[i * (PL_TT + 2) + lane];
+                pairs[(size_t)(n0 + i) * Tp + t0 + lane] = tile_p[i * (PL_TT + 1) + lane];
+            }
+        __syncthreads();
     }
     if (n < n_local) depth[n] = d;
 }
