@@ -403,7 +403,9 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
         const int lv_threads = PL_NT;
         const size_t smem_cap = c->smem_optin > 4096 ? c->smem_optin - 2048 : 0;
         const size_t lv_tiles = sizeof(uint32_t) * PL_NT * (PL_TT + 1) + sizeof(uint16_t) * PL_NT * (PL_TT + 2);
-        const bool last_in_smem = lv_tiles + (size_t)PL_NT * R * 2 <= smem_cap;
+        const size_t lt = dcap <= 255 ? 1 : 2;                          // bytes per entry of the last-level table (k_plan_levels<LT>)
+        const size_t last_bytes = (((size_t)PL_NT * R * lt + 1) / 2) * 2;
+        const bool last_in_smem = lv_tiles + last_bytes <= smem_cap;
         // EXPERIMENTAL level capacity (k_plan_levels, SDX_PLAN_CAP=<trades per level>): with 32 (one round of the trade
         // kernel's CTA per level) a C0 null needs 62 rounds instead of 79, but every round then ends in a barrier and the
         // measured step is slower (trade 11.1 vs 10.8 ms per launch, plan kernels 8.8 % -> 14.7 % of the step); 64 gives
@@ -413,11 +415,13 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
             if (const char *e = getenv("SDX_PLAN_CAP")) level_cap = atoi(e);
             if (level_cap < 0) level_cap = 0;
             const size_t cnt_bytes = sizeof(uint16_t) * PL_NT * ((size_t)dcap + 1);
-            if (lv_tiles + (last_in_smem ? (size_t)PL_NT * R * 2 : 0) + cnt_bytes > smem_cap || level_cap > 65535) level_cap = 0;
+            if (lv_tiles + (last_in_smem ? last_bytes : 0) + cnt_bytes > smem_cap || level_cap > 65535) level_cap = 0;
         }
-        const size_t lv_smem = lv_tiles + (last_in_smem ? (size_t)PL_NT * R * 2 : 0) + (level_cap > 0 ? sizeof(uint16_t) * PL_NT * ((size_t)dcap + 1) : 0);
-        if (lv_smem > 48 * 1024)
-            SDX_CUDA(c, cudaFuncSetAttribute(k_plan_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem));
+        const size_t lv_smem = lv_tiles + (last_in_smem ? last_bytes : 0) + (level_cap > 0 ? sizeof(uint16_t) * PL_NT * ((size_t)dcap + 1) : 0);
+        if (lv_smem > 48 * 1024) {
+            if (lt == 1) SDX_CUDA(c, cudaFuncSetAttribute(k_plan_levels<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem));
+            else SDX_CUDA(c, cudaFuncSetAttribute(k_plan_levels<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lv_smem));
+        }
 
         void *p_lvl, *p_plan, *p_offs, *p_aux = nullptr, *p_carry = nullptr, *p_work = nullptr, *p_out = nullptr, *p_app = nullptr;
         const int offs_stride = (int)((2 * (T < dcap ? T : dcap) + 2 + 1) & ~1ll);
@@ -444,7 +448,7 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
         if ((rc = sdx_scratch(c, SL_PAIRS, sizeof(uint32_t) * (size_t)n_local_max * Tp + 64, &p_pairs))) return rc;
         if (!last_in_smem) {
             const size_t nb = (size_t)ceil_div(n_local_max, lv_threads) * lv_threads;
-            if ((rc = sdx_scratch(c, SL_AUX, sizeof(uint16_t) * nb * R, &p_aux))) return rc;
+            if ((rc = sdx_scratch(c, SL_AUX, lt * nb * R, &p_aux))) return rc;
         }
         const bool need_carry = n_segs > 1;
         SDX_REQUIRE(c, !save_states || n_segs == 1, SDX_ERR_INVALID, "burn-in chains must fit one segment");
@@ -471,8 +475,12 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
                 const int n_local = (int)(nch * ix.seg_len);
                 cudaEventRecord(c->ev[2], c->stream);
                 if (T > 0) {
-                    k_plan_levels<<<ceil_div(n_local, lv_threads), lv_threads, lv_smem, c->stream>>>(
-                        keys, ix, n_local, R, (int)T, Tp, (uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux, level_cap, dcap);
+                    if (lt == 1)
+                        k_plan_levels<uint8_t><<<ceil_div(n_local, lv_threads), lv_threads, lv_smem, c->stream>>>(
+                            keys, ix, n_local, R, (int)T, Tp, (uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint8_t *)p_aux, level_cap, dcap);
+                    else
+                        k_plan_levels<uint16_t><<<ceil_div(n_local, lv_threads), lv_threads, lv_smem, c->stream>>>(
+                            keys, ix, n_local, R, (int)T, Tp, (uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux, level_cap, dcap);
                     k_plan_sort<<<ceil_div(n_local, sort_warps), sort_warps * 32, sort_smem_warp * sort_warps, c->stream>>>(
                                                                           n_local, R, (int)T, Tp, dcap, (const uint32_t *)p_pairs,
                                                                           (const uint16_t *)p_lvl, d_depth, c->d_rowsize, sparse ? c->d_sp_desc : nullptr,

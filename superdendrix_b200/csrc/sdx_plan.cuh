@@ -28,18 +28,22 @@ struct NullIndexing {          // local null index (within a launch) -> global n
 // at C0 (ideal: T / cap = 60; tests/tools/exp_levels.py).  Any assignment that puts a trade after its two
 // predecessors is a valid schedule, so the nulls do not change.  A schedule that would need dcap levels or more is
 // reported as depth dcap (the trade kernel then runs that null in sequential order).
+// LT: type of the per-row "level of the last trade" table — u8 when dcap <= 255 (half the shared memory, twice the resident
+// CTAs), else u16.  Levels are clamped to dcap (a null that reaches it runs in sequential order anyway).
+template <typename LT>
 __global__ void __launch_bounds__(PL_NT) k_plan_levels(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T,
                                                        int Tp, uint32_t *__restrict__ pairs, uint16_t *__restrict__ lvl,
-                                                       int *__restrict__ depth, uint16_t *__restrict__ last_global, int cap, int dcap) {
+                                                       int *__restrict__ depth, LT *__restrict__ last_global, int cap, int dcap) {
     extern __shared__ __align__(16) uint16_t plan_smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n0 = blockIdx.x * PL_NT, n = n0 + tid;
-    // layout: tile_p[PL_NT][PL_TT + 1] u32 | tile_l[PL_NT][PL_TT + 2] u16 | last[R][PL_NT] u16 (unless in global memory)
+    // layout: tile_p[PL_NT][PL_TT + 1] u32 | tile_l[PL_NT][PL_TT + 2] u16 | last[R][PL_NT] LT (unless in global memory)
     uint32_t *tile_p = reinterpret_cast<uint32_t *>(plan_smem);
     uint16_t *tile_l = reinterpret_cast<uint16_t *>(tile_p + PL_NT * (PL_TT + 1));
-    uint16_t *last = last_global ? last_global + (size_t)blockIdx.x * PL_NT * R + tid : tile_l + PL_NT * (PL_TT + 2) + tid;
+    uint16_t *after_tiles = tile_l + PL_NT * (PL_TT + 2);
+    LT *last = last_global ? last_global + (size_t)blockIdx.x * PL_NT * R + tid : reinterpret_cast<LT *>(after_tiles) + tid;
     // fill[level][tid]: trades already assigned to a level (only with cap > 0); it follows last[] when that is in shared memory
-    uint16_t *fill = tile_l + PL_NT * (PL_TT + 2) + (last_global ? 0 : (size_t)PL_NT * R) + tid;
+    uint16_t *fill = after_tiles + (last_global ? 0 : ((size_t)PL_NT * R * sizeof(LT) + 1) / 2) + tid;
     for (int r = 0; r < R; ++r) last[(size_t)r * PL_NT] = 0;
     if (cap > 0)
         for (int l = 0; l <= dcap; ++l) fill[(size_t)l * PL_NT] = 0;
@@ -62,8 +66,9 @@ __global__ void __launch_bounds__(PL_NT) k_plan_levels(const __grid_constant__ P
                 ++fill[(size_t)l * PL_NT];
                 while (lo < dcap && fill[(size_t)lo * PL_NT] >= cap) ++lo;
             }
-            last[(size_t)a * PL_NT] = (uint16_t)l;
-            last[(size_t)b * PL_NT] = (uint16_t)l;
+            if (l > dcap) l = dcap;
+            last[(size_t)a * PL_NT] = (LT)l;
+            last[(size_t)b * PL_NT] = (LT)l;
             tile_l[tid * (PL_TT + 2) + c] = (uint16_t)l;
             d = l > d ? l : d;
         }
