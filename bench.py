@@ -33,7 +33,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 NULLS_PER_STEP = 100_000
-CHAIN_LEN, BURN_ROUNDS, POOL_SIZE = 16, 32, 1480      # short chains from a burnt-in pool: stationary nulls
+CHAIN_LEN, BURN_ROUNDS, POOL_SIZE = 16, 6, 1480       # short chains from a burnt-in pool: stationary nulls
 if os.environ.get("SDX_BENCH_CHAINS"):                # experiments only: "chain_len,burn,pool"
     CHAIN_LEN, BURN_ROUNDS, POOL_SIZE = (int(x) for x in os.environ["SDX_BENCH_CHAINS"].split(","))
 SEED = 1764          # the reference's default -rs (src/generate_null_matrices.py:32)

@@ -127,7 +127,10 @@ int sdx_curveball(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, 
  * stationary only because null i has already seen (i+1) rounds (src/generate_null_matrices.py:73-74).  With
  * burn_rounds > 0 every chain starts, instead of from the observed matrix, from one of pool_size start states:
  * state j = the observed matrix after burn_rounds rounds of n_trades trades drawn from reserved stream ids
- * ((2^61 / burn_rounds + j) * burn_rounds + r, r < burn_rounds); chain c uses state c % pool_size.  Null i keeps the
+ * ((2^61 / burn_rounds + j) * burn_rounds + r, r < burn_rounds); chain c uses state c % pool_size.  A burn-in trade
+ * takes both rows from the max(2, ceil(R / 10)) densest rows with probability 1/4 and a uniform pair otherwise (a fixed
+ * pair distribution: the stationary distribution stays uniform, and the dense rows forget the observed matrix in
+ * ~3 rounds instead of ~30; the high-level paths use burn_rounds = 6).  Null indices must stay below 2^61 - 256.  Null i keeps the
  * stream id i, so results still depend only on (seed, i, chain_len, burn_rounds, pool_size) and not on batching or
  * on the GPU count.  The pool is built on first use and cached until the matrix, the seed or n_trades change.
  * burn_rounds = 0 (default) starts every chain from the observed matrix. */

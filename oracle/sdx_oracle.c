@@ -231,6 +231,62 @@ static int trade_canonical(uint32_t *ra, uint32_t *rb, int wpr, uint64_t seed, u
     return 1;
 }
 
+/* Pair of a BURN-IN trade: with probability 1/4 both rows come from the K densest rows (top[], by size
+ * descending, index ascending), otherwise the pair is uniform as in sdxo_trade_pair.  Row sizes are invariants of the
+ * chain, so this is a fixed pair distribution and the stationary distribution stays uniform; dense x dense trades move
+ * ~100 elements at once, which is what makes the dense rows forget the observed matrix in 3 rounds instead of 30. */
+static void trade_pair_burn(uint64_t seed, uint64_t null_id, uint32_t t, uint32_t R, const uint16_t *top, uint32_t K,
+                            uint32_t *a, uint32_t *b) {
+    stream_t s;
+    stream_init(&s, seed, STREAM_PAIR, null_id, t);
+    uint32_t u = stream_next(&s);
+    if (K >= 2 && u < 0x40000000u) {
+        uint32_t i = stream_below(&s, K), j = stream_below(&s, K - 1);
+        if (j >= i) j++;
+        *a = top[i]; *b = top[j];
+    } else {
+        uint32_t x = stream_below(&s, R), y = stream_below(&s, R - 1);
+        if (y >= x) y++;
+        *a = x; *b = y;
+    }
+}
+
+static int64_t curveball_burn_round(uint32_t *rows, int R, int wpr, uint64_t seed, uint64_t null_id, int64_t n_trades,
+                                    const uint16_t *top, uint32_t K) {
+    uint32_t *chosen = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)wpr + 1));
+    int64_t applied = 0;
+    for (int64_t t = 0; t < n_trades; ++t) {
+        uint32_t a, b;
+        trade_pair_burn(seed, null_id, (uint32_t)t, (uint32_t)R, top, K, &a, &b);
+        applied += trade_canonical(rows + (size_t)a * wpr, rows + (size_t)b * wpr, wpr, seed, null_id, (uint32_t)t, chosen);
+    }
+    free(chosen);
+    return applied;
+}
+
+/* the K = max(2, ceil(R / 10)) densest rows, by size descending then index ascending */
+static uint32_t dense_rows(const uint32_t *rows, int R, int wpr, uint16_t *top) {
+    uint32_t K = (uint32_t)((R + 9) / 10);
+    if (K < 2) K = 2;
+    if (K > (uint32_t)R) K = (uint32_t)R;
+    int *size = (int *)malloc(sizeof(int) * (size_t)R);
+    char *used = (char *)calloc((size_t)R, 1);
+    for (int r = 0; r < R; ++r) {
+        int c = 0;
+        for (int i = 0; i < wpr; ++i) c += __builtin_popcount(rows[(size_t)r * wpr + i]);
+        size[r] = c;
+    }
+    for (uint32_t q = 0; q < K; ++q) {
+        int best = -1;
+        for (int r = 0; r < R; ++r)
+            if (!used[r] && (best < 0 || size[r] > size[best])) best = r;
+        used[best] = 1;
+        top[q] = (uint16_t)best;
+    }
+    free(size); free(used);
+    return K;
+}
+
 /* curve_ball(input_matrix, r_hp, num_iterations) — src/curveball.py:17-40 —
  * on the packed form of r_hp (R rows over the longer dimension), in place,
  * for null index `null_id`.  Returns the number of applied trades. */
@@ -262,7 +318,13 @@ SDXO_API void sdxo_curveball_nulls_burn(const uint32_t *observed, int R, int wpr
     size_t msz = (size_t)R * wpr;
     uint32_t *cur = (uint32_t *)malloc(sizeof(uint32_t) * msz);
     uint32_t **pool = NULL;
-    if (burn > 0) pool = (uint32_t **)calloc((size_t)pool_size, sizeof(uint32_t *));
+    uint16_t *top = NULL;
+    uint32_t K = 0;
+    if (burn > 0) {
+        pool = (uint32_t **)calloc((size_t)pool_size, sizeof(uint32_t *));
+        top = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)R);
+        K = dense_rows(observed, R, wpr, top);
+    }
     for (int64_t i = 0; i < n; ++i) {
         uint64_t id = null0 + (uint64_t)i;
         if (i == 0 || id % (uint64_t)chain_len == 0) {
@@ -273,7 +335,7 @@ SDXO_API void sdxo_curveball_nulls_burn(const uint32_t *observed, int R, int wpr
                     pool[j] = (uint32_t *)malloc(sizeof(uint32_t) * msz);
                     memcpy(pool[j], observed, sizeof(uint32_t) * msz);
                     uint64_t base = ((1ull << 61) / (uint64_t)burn + (uint64_t)j) * (uint64_t)burn;
-                    for (int64_t r = 0; r < burn; ++r) sdxo_curveball(pool[j], R, wpr, seed, base + (uint64_t)r, n_trades);
+                    for (int64_t r = 0; r < burn; ++r) curveball_burn_round(pool[j], R, wpr, seed, base + (uint64_t)r, n_trades, top, K);
                 }
                 memcpy(cur, pool[j], sizeof(uint32_t) * msz);
             } else {
@@ -291,6 +353,7 @@ SDXO_API void sdxo_curveball_nulls_burn(const uint32_t *observed, int R, int wpr
         for (int j = 0; j < pool_size; ++j) free(pool[j]);
         free(pool);
     }
+    free(top);
     free(cur);
 }
 

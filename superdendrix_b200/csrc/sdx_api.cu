@@ -69,6 +69,8 @@ static void free_matrix(sdx_ctx *c) {
     if (c->d_pool) cudaFree(c->d_pool);
     c->d_pool = nullptr;
     c->pool_valid = false;
+    if (c->d_top) cudaFree(c->d_top);
+    c->d_top = nullptr; c->cap_top = 0; c->top_K = 0;
     c->cap_feat = c->cap_samp = c->cap_obs = c->cap_rowsize = c->cap_pool = 0;
 }
 
@@ -79,6 +81,7 @@ static void invalidate_matrix(sdx_ctx *c) {
     c->d_sp_desc = c->d_sp_obs = nullptr;
     c->sp_state = 0;
     c->pool_valid = false;
+    c->top_K = 0;
 }
 
 static void free_weights(sdx_ctx *c) {

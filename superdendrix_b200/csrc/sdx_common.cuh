@@ -54,6 +54,9 @@ struct sdx_ctx {
     bool pool_valid = false;
     uint64_t pool_seed = 0;
     int64_t pool_T = 0;
+    uint16_t *d_top = nullptr;    // the top_K densest trade rows (size descending, index ascending): pair set of the burn-in trades
+    size_t cap_top = 0;
+    int top_K = 0;
 
     // weights
     int P = 0;
@@ -213,6 +216,27 @@ __device__ __forceinline__ void trade_pair(const PhiloxKeys &k, uint64_t null_id
     b = s.below(R - 1);
     if (b >= a) b++;
 }
+
+// Pair of a BURN-IN trade (oracle: trade_pair_burn): with probability 1/4 both rows come from the K densest
+// rows (top[]), otherwise the pair is uniform.  A fixed pair distribution (row sizes never change), so the stationary
+// distribution stays uniform, and dense x dense trades make the dense rows forget the observed matrix in ~3 rounds.
+__device__ __forceinline__ void trade_pair_burn(const PhiloxKeys &k, uint64_t null_id, uint32_t t, uint32_t R,
+                                                const uint16_t *__restrict__ top, uint32_t K, uint32_t &a, uint32_t &b) {
+    ThreadStream s(k, SDX_STREAM_PAIR, null_id, t);
+    const uint32_t u = s.next();
+    if (K >= 2 && u < 0x40000000u) {
+        const uint32_t i = s.below(K);
+        uint32_t j = s.below(K - 1);
+        if (j >= i) j++;
+        a = top[i]; b = top[j];
+    } else {
+        a = s.below(R);
+        b = s.below(R - 1);
+        if (b >= a) b++;
+    }
+}
+#define SDX_POOL_BASE (1ull << 61)      // stream ids of the burn-in rounds start at floor(2^61 / burn) * burn > 2^61 - burn ...
+#define SDX_BURN_ID_MIN (SDX_POOL_BASE - 256)   // ... so (burn <= 256) every id from here on is a burn-in round; null indices stay below
 
 // ---------------------------------------------------------------------------
 // small device helpers

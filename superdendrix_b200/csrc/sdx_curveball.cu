@@ -260,7 +260,6 @@ static int sparse_layout(sdx_ctx *c) {
 static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
                           uint32_t *out_rows, int64_t *applied, const HostScore *hs, uint32_t *save_states, bool use_pool);
 
-#define SDX_POOL_BASE (1ull << 61)      // stream ids of the burn-in rounds live above every null index
 
 // The burn-in pool of sdx_set_burn_in: pool_size chains of `burn` rounds from the observed matrix; their final states
 // (in the trade kernel's own state layout) are the start states of the real chains.  Cached per (seed, T).
@@ -269,6 +268,22 @@ static int ensure_pool(sdx_ctx *c, uint64_t seed, int64_t T, size_t state_words)
     if (c->pool_valid && c->pool_seed == seed && c->pool_T == T && c->pool_state_words == state_words) return SDX_OK;
     c->pool_valid = false;
     SDX_TRY(sdx_reserve(c, c->d_pool, c->cap_pool, sizeof(uint32_t) * state_words * (size_t)c->pool_size));
+    {   // pair set of the burn-in trades: the max(2, ceil(R / 10)) densest rows, size descending, index ascending
+        const int R = c->R;
+        std::vector<int> size((size_t)R);
+        SDX_CUDA(c, cudaMemcpyAsync(size.data(), c->d_rowsize, sizeof(int) * R, cudaMemcpyDeviceToHost, c->stream));
+        SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+        std::vector<uint16_t> top((size_t)R);
+        for (int r = 0; r < R; ++r) top[r] = (uint16_t)r;
+        std::stable_sort(top.begin(), top.end(), [&](uint16_t x, uint16_t y) { return size[x] > size[y]; });
+        int K = (R + 9) / 10;
+        if (K < 2) K = 2;
+        if (K > R) K = R;
+        SDX_TRY(sdx_reserve(c, c->d_top, c->cap_top, sizeof(uint16_t) * (size_t)R));
+        SDX_CUDA(c, cudaMemcpyAsync(c->d_top, top.data(), sizeof(uint16_t) * K, cudaMemcpyHostToDevice, c->stream));
+        SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->top_K = K;
+    }
     const uint64_t base_chain = SDX_POOL_BASE / (uint64_t)c->burn;
     int rc = run_nulls_impl(c, seed, base_chain * (uint64_t)c->burn, (int64_t)c->pool_size * c->burn, T, c->burn, nullptr, nullptr, nullptr,
                             c->d_pool, false);
@@ -287,7 +302,7 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
     SDX_REQUIRE(c, c->d_trade_obs, SDX_ERR_STATE, "sdx_upload_matrix has not been called");
     SDX_REQUIRE(c, n_nulls >= 0 && chain_len >= 1, SDX_ERR_INVALID, "n_nulls must be >= 0 and chain_len >= 1");
     SDX_REQUIRE(c, c->R >= 2, SDX_ERR_INVALID, "Curveball needs at least two trade rows");
-    SDX_REQUIRE(c, null0 + (uint64_t)n_nulls < (1ull << 62) && (!use_pool || null0 + (uint64_t)n_nulls <= SDX_POOL_BASE), SDX_ERR_INVALID,
+    SDX_REQUIRE(c, null0 + (uint64_t)n_nulls < (1ull << 62) && (!use_pool || null0 + (uint64_t)n_nulls <= SDX_BURN_ID_MIN), SDX_ERR_INVALID,
                 "null index out of range");
     const int64_t T = n_trades < 0 ? 5 * (int64_t)(c->S < c->F ? c->S : c->F) : n_trades;
     SDX_REQUIRE(c, T <= 60000, SDX_ERR_UNSUPPORTED, "more than 60000 trades per null are not supported");
@@ -477,10 +492,10 @@ static int run_nulls_impl(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_n
                 if (T > 0) {
                     if (lt == 1)
                         k_plan_levels<uint8_t><<<ceil_div(n_local, lv_threads), lv_threads, lv_smem, c->stream>>>(
-                            keys, ix, n_local, R, (int)T, Tp, (uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint8_t *)p_aux, level_cap, dcap);
+                            keys, ix, n_local, R, (int)T, Tp, (uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint8_t *)p_aux, level_cap, dcap, c->d_top, c->top_K);
                     else
                         k_plan_levels<uint16_t><<<ceil_div(n_local, lv_threads), lv_threads, lv_smem, c->stream>>>(
-                            keys, ix, n_local, R, (int)T, Tp, (uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux, level_cap, dcap);
+                            keys, ix, n_local, R, (int)T, Tp, (uint32_t *)p_pairs, (uint16_t *)p_lvl, d_depth, (uint16_t *)p_aux, level_cap, dcap, c->d_top, c->top_K);
                     k_plan_sort<<<ceil_div(n_local, sort_warps), sort_warps * 32, sort_smem_warp * sort_warps, c->stream>>>(
                                                                           n_local, R, (int)T, Tp, dcap, (const uint32_t *)p_pairs,
                                                                           (const uint16_t *)p_lvl, d_depth, c->d_rowsize, sparse ? c->d_sp_desc : nullptr,

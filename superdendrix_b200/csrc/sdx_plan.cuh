@@ -33,7 +33,8 @@ struct NullIndexing {          // local null index (within a launch) -> global n
 template <typename LT>
 __global__ void __launch_bounds__(PL_NT) k_plan_levels(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T,
                                                        int Tp, uint32_t *__restrict__ pairs, uint16_t *__restrict__ lvl,
-                                                       int *__restrict__ depth, LT *__restrict__ last_global, int cap, int dcap) {
+                                                       int *__restrict__ depth, LT *__restrict__ last_global, int cap, int dcap,
+                                                       const uint16_t *__restrict__ top, int top_K) {
     extern __shared__ __align__(16) uint16_t plan_smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n0 = blockIdx.x * PL_NT, n = n0 + tid;
@@ -51,11 +52,13 @@ __global__ void __launch_bounds__(PL_NT) k_plan_levels(const __grid_constant__ P
     // The thread draws the row pair of each of its trades itself (PAIR stream): the Philox arithmetic is independent of the
     // shared-memory chain of the level walk and fills its latency.  Pairs and levels leave through the tiles, coalesced.
     const uint64_t null_id = ix.id(n < n_local ? n : 0);
+    const bool burn = top_K >= 2 && null_id >= SDX_BURN_ID_MIN;     // burn-in rounds of the pool (the whole launch or none of it)
     for (int t0 = 0; t0 < T; t0 += PL_TT) {
         const int cnt = T - t0 < PL_TT ? T - t0 : PL_TT;
         for (int c = 0; c < cnt; ++c) {
             uint32_t a, b;
-            trade_pair(keys, null_id, (uint32_t)(t0 + c), (uint32_t)R, a, b);
+            if (burn) trade_pair_burn(keys, null_id, (uint32_t)(t0 + c), (uint32_t)R, top, (uint32_t)top_K, a, b);
+            else trade_pair(keys, null_id, (uint32_t)(t0 + c), (uint32_t)R, a, b);
             tile_p[tid * (PL_TT + 1) + c] = a | (b << 16);
             const int la = last[(size_t)a * PL_NT], lb = last[(size_t)b * PL_NT];
             int l = (la > lb ? la : lb) + 1;

@@ -122,7 +122,7 @@ def shard_chains(n, chain_len, rank, world):
     return min(c_lo * chain_len, n), min(c_hi * chain_len, n)
 
 
-def null_pvalue(engine, seed, n_nulls, modules, null0=0, n_trades=-1, stat=0, z_obs=None, chain_len=16, burn=32,
+def null_pvalue(engine, seed, n_nulls, modules, null0=0, n_trades=-1, stat=0, z_obs=None, chain_len=16, burn=6,
                 pool_size=1480, group=None):
     """Permutation p-values over n_nulls nulls sharded by null index.  Nulls come in short chains (chain_len) that
     start from burnt-in pool states (Engine.set_burn_in), so every null is a draw from the stationary distribution —

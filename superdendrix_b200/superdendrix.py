@@ -20,7 +20,7 @@ Added, non-breaking flags:
   --null-source generate|files   generate: nulls are produced and scored on the GPU, no files;
                             files: read ``<-nm><i>.tsv`` as the reference does (:186).
   --mode parallel|chained|restart   generated nulls: parallel (default) = chains of 16 nulls that start from burnt-in
-                            pool states (32 rounds) — stationary like the reference's long chain and enough chains to
+                            pool states (6 dense-favouring rounds) — stationary like the reference's long chain and enough chains to
                             fill the GPUs; chained = ONE chain from the observed matrix, exactly the reference's
                             semantics (src/generate_null_matrices.py:71-74); restart = every null 5*min(S,F) trades from
                             the observed matrix (src/curveball_main.py:136; NOT mixed for dense features)
@@ -96,7 +96,7 @@ def get_parser():
     parser.add_argument("--null-stat", default=None, choices=["fixed", "max_k"])
     parser.add_argument("--null-source", default=None, choices=["generate", "files"])
     parser.add_argument("--mode", default="parallel", choices=["parallel", "chained", "restart"])
-    parser.add_argument("--burn-in", type=int, default=32, help="burn-in rounds of the pool states (parallel mode)")
+    parser.add_argument("--burn-in", type=int, default=6, help="burn-in rounds of the pool states (parallel mode)")
     parser.add_argument("--device", type=int, default=0)
     return parser
 

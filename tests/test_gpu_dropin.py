@@ -204,7 +204,7 @@ def test_driver_end_to_end_against_oracle(tmp_path, stat):
     assert abs(last["zP"] - zP) <= 1e-9 * np.abs(wv).sum()
     # null loop: same nulls through the oracle
     obs = rows_of(d)
-    nulls, _ = oracle.curveball_nulls(obs, 9, 0, 64, 5 * obs.shape[0], 16, burn=32, pool_size=1480)     # --mode parallel (default)
+    nulls, _ = oracle.curveball_nulls(obs, 9, 0, 64, 5 * obs.shape[0], 16, burn=6, pool_size=1480)     # --mode parallel (default)
     ras = d.shape[1] >= d.shape[0]
     sc = []
     for m in nulls:
@@ -298,7 +298,7 @@ def test_batched_screen_equals_per_profile_pipeline(tmp_path):
         res = scr.screen(eng, rows, S, w, mask, k=3, cond_it=cond_it, n_nulls=n_nulls, seed=seed, stat="fixed")
     obs = rows_of(dense)
     ras = F >= S
-    nulls, _ = oracle.curveball_nulls(obs, seed, 0, n_nulls, 5 * obs.shape[0], 16, burn=32, pool_size=1480)
+    nulls, _ = oracle.curveball_nulls(obs, seed, 0, n_nulls, 5 * obs.shape[0], 16, burn=6, pool_size=1480)
     for p in range(P):
         wm = np.where(mask[p], w[p], 0.0)
         mk = bitpack.pack_mask(np.nonzero(mask[p])[0], S)

@@ -9,7 +9,7 @@ w = synth.weights(770, 1)
 module = synth.pick_module(dense, 3)[None, :]
 rows = bitpack.pack_rows(dense.T)
 with Engine(0) as eng:
-    eng.set_burn_in(32, 1480)
+    eng.set_burn_in(6, 1480)
     for it in range(4):
         t0 = time.perf_counter(); eng.upload_matrix(rows, 770)
         t1 = time.perf_counter(); eng.upload_weights(w)

@@ -10,7 +10,7 @@ rows = bitpack.pack_rows(dense.T)
 torch.cuda.set_device(0)
 eng = Engine(0)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); eng.set_stream(stream.cuda_stream)
-eng.set_burn_in(32, 1480)
+eng.set_burn_in(6, 1480)
 flush = torch.empty(256*1024*1024, dtype=torch.uint8, device="cuda")
 for it in range(4):
     flush.zero_()
