@@ -136,6 +136,18 @@ int sdx_curveball(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, 
  * burn_rounds = 0 (default) starts every chain from the observed matrix. */
 int sdx_set_burn_in(sdx_ctx *ctx, int64_t burn_rounds, int pool_size);
 
+/* How the PAIR stream (which two rows trade t exchanges) is shared between nulls.  pair_group = 1 (default): every
+ * null draws its own pairs, stream id = its null index.  pair_group = 32: the chains of an aligned block of 32
+ * consecutive chains (chain c = null index / chain_len) walk the SAME schedule of row pairs — round j of chain c draws
+ * its pairs from the stream of round j of chain c - c % 32 — while every null keeps its own DEAL stream (who gets
+ * which element).  Each null on its own is still curve_ball with uniformly random pairs (src/curveball.py:22); given the
+ * pairs the 32 chains are independent, and the uniform distribution is stationary for every fixed pair sequence, so
+ * nulls that start from independent stationary states stay independent.  What it buys: the two rows of a trade have
+ * the same sizes in all 32 nulls (row sums are invariants), so one warp runs 32 nulls in lock step without
+ * divergence — the layout of k_trade_lanes, ~5x fewer instructions per null.  Results depend on
+ * (seed, null index, chain_len, burn-in, pair_group) only — not on batching, kernel choice or the GPU count. */
+int sdx_set_pair_group(sdx_ctx *ctx, int pair_group);
+
 /* Replay of a recorded schedule (parity with the reference under its own
  * random draws): trade t exchanges rows a[t], b[t]; to_a[t] (words_per_row
  * words) holds the symmetric-difference elements given to row a, i.e.

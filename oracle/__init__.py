@@ -99,18 +99,30 @@ def trade_pair(seed, null_id, t, R):
     return a.value, b.value
 
 
-def curveball_nulls(observed, seed, null0, n, n_trades, chain_len=1, want_matrices=True, burn=0, pool_size=1024):
+def curveball_nulls(observed, seed, null0, n, n_trades, chain_len=1, want_matrices=True, burn=0, pool_size=1024, pair_group=1):
     """observed: (R, wpr) uint32 packed rows over the longer dimension.
     burn > 0: chains start from the burn-in pool (see sdx_oracle.c).
+    pair_group > 1: aligned blocks of that many chains draw their row pairs from the stream of the block's first chain.
     Returns (nulls (n, R, wpr) or None, applied (n,))."""
     obs = _u32(observed)
     R, wpr = obs.shape
     out = np.zeros((n, R, wpr), dtype=np.uint32) if want_matrices else None
     applied = np.zeros(n, dtype=np.int64)
-    lib().sdxo_curveball_nulls_burn(_p(obs, C.c_uint32), C.c_int(R), C.c_int(wpr), C.c_uint64(seed),
-                                    C.c_uint64(null0), C.c_int64(n), C.c_int64(n_trades), C.c_int64(chain_len),
-                                    C.c_int64(burn), C.c_int(pool_size), _p(out, C.c_uint32), _p(applied, C.c_int64))
+    lib().sdxo_curveball_nulls_group(_p(obs, C.c_uint32), C.c_int(R), C.c_int(wpr), C.c_uint64(seed),
+                                     C.c_uint64(null0), C.c_int64(n), C.c_int64(n_trades), C.c_int64(chain_len),
+                                     C.c_int64(burn), C.c_int(pool_size), C.c_int(pair_group), _p(out, C.c_uint32),
+                                     _p(applied, C.c_int64))
     return out, applied
+
+
+def pool_state(observed, seed, n_trades, burn, j):
+    """start state j of the burn-in pool: the observed matrix after `burn` dense-favouring rounds on reserved streams"""
+    obs = _u32(observed)
+    R, wpr = obs.shape
+    out = np.zeros_like(obs)
+    lib().sdxo_pool_state(_p(obs, C.c_uint32), C.c_int(R), C.c_int(wpr), C.c_uint64(seed), C.c_int64(n_trades),
+                          C.c_int64(burn), C.c_int(j), _p(out, C.c_uint32))
+    return out
 
 
 def curveball_replay(rows, a, b, to_a):

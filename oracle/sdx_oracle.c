@@ -290,16 +290,30 @@ static uint32_t dense_rows(const uint32_t *rows, int R, int wpr, uint16_t *top) 
 /* curve_ball(input_matrix, r_hp, num_iterations) — src/curveball.py:17-40 —
  * on the packed form of r_hp (R rows over the longer dimension), in place,
  * for null index `null_id`.  Returns the number of applied trades. */
-SDXO_API int64_t sdxo_curveball(uint32_t *rows, int R, int wpr, uint64_t seed, uint64_t null_id, int64_t n_trades) {
+/* pair_id: the stream the row pairs are drawn from — the null's own index, or, when blocks of chains
+ * share their schedule of row pairs (pair_group > 1), the index of the same round of the block's first chain.  The
+ * elements are always dealt from the null's own DEAL stream. */
+static int64_t curveball_round(uint32_t *rows, int R, int wpr, uint64_t seed, uint64_t null_id, uint64_t pair_id, int64_t n_trades) {
     uint32_t *chosen = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)wpr + 1));
     int64_t applied = 0;
     for (int64_t t = 0; t < n_trades; ++t) {
         uint32_t a, b;
-        sdxo_trade_pair(seed, null_id, (uint32_t)t, (uint32_t)R, &a, &b);
+        sdxo_trade_pair(seed, pair_id, (uint32_t)t, (uint32_t)R, &a, &b);
         applied += trade_canonical(rows + (size_t)a * wpr, rows + (size_t)b * wpr, wpr, seed, null_id, (uint32_t)t, chosen);
     }
     free(chosen);
     return applied;
+}
+
+SDXO_API int64_t sdxo_curveball(uint32_t *rows, int R, int wpr, uint64_t seed, uint64_t null_id, int64_t n_trades) {
+    return curveball_round(rows, R, wpr, seed, null_id, null_id, n_trades);
+}
+
+/* stream id of the row pairs of null `id`: round j of chain c uses the pairs of round j of chain c - c % pair_group */
+static uint64_t pair_stream_id(uint64_t id, int64_t chain_len, int pair_group) {
+    if (pair_group <= 1) return id;
+    uint64_t c = id / (uint64_t)chain_len, j = id % (uint64_t)chain_len;
+    return (c - c % (uint64_t)pair_group) * (uint64_t)chain_len + j;
 }
 
 /* The null-driver loop of src/generate_null_matrices.py:71-74: nulls
@@ -312,9 +326,9 @@ SDXO_API int64_t sdxo_curveball(uint32_t *rows, int R, int wpr, uint64_t seed, u
  * where state j = the observed matrix after `burn` rounds drawn from the
  * reserved stream ids ((2^61 / burn + j) * burn + r), r < burn.
  * out = n packed matrices (may be NULL); applied[n] optional. */
-SDXO_API void sdxo_curveball_nulls_burn(const uint32_t *observed, int R, int wpr, uint64_t seed,
-                                        uint64_t null0, int64_t n, int64_t n_trades, int64_t chain_len,
-                                        int64_t burn, int pool_size, uint32_t *out, int64_t *applied) {
+SDXO_API void sdxo_curveball_nulls_group(const uint32_t *observed, int R, int wpr, uint64_t seed,
+                                         uint64_t null0, int64_t n, int64_t n_trades, int64_t chain_len,
+                                         int64_t burn, int pool_size, int pair_group, uint32_t *out, int64_t *applied) {
     size_t msz = (size_t)R * wpr;
     uint32_t *cur = (uint32_t *)malloc(sizeof(uint32_t) * msz);
     uint32_t **pool = NULL;
@@ -343,9 +357,9 @@ SDXO_API void sdxo_curveball_nulls_burn(const uint32_t *observed, int R, int wpr
             }
             /* a shard that starts inside a chain replays the chain prefix */
             for (uint64_t q = chain * (uint64_t)chain_len; q < id; ++q)
-                sdxo_curveball(cur, R, wpr, seed, q, n_trades);
+                curveball_round(cur, R, wpr, seed, q, pair_stream_id(q, chain_len, pair_group), n_trades);
         }
-        int64_t ap = sdxo_curveball(cur, R, wpr, seed, id, n_trades);
+        int64_t ap = curveball_round(cur, R, wpr, seed, id, pair_stream_id(id, chain_len, pair_group), n_trades);
         if (applied) applied[i] = ap;
         if (out) memcpy(out + (size_t)i * msz, cur, sizeof(uint32_t) * msz);
     }
@@ -355,6 +369,23 @@ SDXO_API void sdxo_curveball_nulls_burn(const uint32_t *observed, int R, int wpr
     }
     free(top);
     free(cur);
+}
+
+/* start state j of the burn-in pool, as the chains of sdxo_curveball_nulls_group use it */
+SDXO_API void sdxo_pool_state(const uint32_t *observed, int R, int wpr, uint64_t seed, int64_t n_trades, int64_t burn, int j,
+                              uint32_t *out) {
+    uint16_t *top = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)R);
+    uint32_t K = dense_rows(observed, R, wpr, top);
+    memcpy(out, observed, sizeof(uint32_t) * (size_t)R * wpr);
+    uint64_t base = ((1ull << 61) / (uint64_t)burn + (uint64_t)j) * (uint64_t)burn;
+    for (int64_t r = 0; r < burn; ++r) curveball_burn_round(out, R, wpr, seed, base + (uint64_t)r, n_trades, top, K);
+    free(top);
+}
+
+SDXO_API void sdxo_curveball_nulls_burn(const uint32_t *observed, int R, int wpr, uint64_t seed,
+                                        uint64_t null0, int64_t n, int64_t n_trades, int64_t chain_len,
+                                        int64_t burn, int pool_size, uint32_t *out, int64_t *applied) {
+    sdxo_curveball_nulls_group(observed, R, wpr, seed, null0, n, n_trades, chain_len, burn, pool_size, 1, out, applied);
 }
 
 SDXO_API void sdxo_curveball_nulls(const uint32_t *observed, int R, int wpr, uint64_t seed,

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "sdx_trade_shape": (C.c_int, [_ctx, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sdx_curveball": (C.c_int, [_ctx, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, _u32p, _i64p]),
     "sdx_set_burn_in": (C.c_int, [_ctx, C.c_int64, C.c_int]),
+    "sdx_set_pair_group": (C.c_int, [_ctx, C.c_int]),
     "sdx_curveball_replay": (C.c_int, [_ctx, _u32p, _i32p, _i32p, _u32p, C.c_int64, _u32p, _i64p]),
     "sdx_null_pvalue": (C.c_int, [_ctx, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _i32p,
                                   C.c_int, _f64p, _i64p, _f64p, _f64p]),

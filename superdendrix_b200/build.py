@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libsdx.so")
-UNITS = ["sdx_api", "sdx_score", "sdx_curveball", "sdx_scan", "sdx_stats"]
+UNITS = ["sdx_api", "sdx_score", "sdx_curveball", "sdx_lanes", "sdx_scan", "sdx_stats"]
 HOST_UNITS = ["sdx_io"]          # plain C++ (the host-side format path), compiled by the host compiler through nvcc
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wno-format-truncation", "-Xptxas", "-v"]

@@ -1,4 +1,6 @@
 // sdx_api.cu — context lifecycle, uploads and layout kernels of libsdx.so.
+#include <stdlib.h>
+
 #include "sdx_common.cuh"
 
 std::string g_sdx_create_error;
@@ -51,6 +53,20 @@ extern "C" int sdx_create(int device, sdx_ctx **out) {
     }
     c->stream = c->own_stream;
     for (auto &ev : c->ev) cudaEventCreate(&ev);
+    {   // tuning knobs (benchmarks and tests only): read here, once, never on the call path
+        auto geti = [](const char *n, long dflt) { const char *e = getenv(n); return e && *e ? atol(e) : dflt; };
+        c->knobs.trade_g = (int)geti("SDX_TRADE_G", 0);
+        c->knobs.trade_warps = (int)geti("SDX_TRADE_WARPS", 0);
+        c->knobs.trade_lb = (int)geti("SDX_TRADE_LB", -1);
+        c->knobs.plan_cap = (int)geti("SDX_PLAN_CAP", 0);
+        c->knobs.grid_cap = (int)geti("SDX_TRADE_GRID_CAP", 0);
+        c->knobs.nulls_per_launch = geti("SDX_NULLS_PER_LAUNCH", 0);
+        c->knobs.pad_smem = geti("SDX_TRADE_PAD_SMEM", 0);
+        c->knobs.lanes = (int)geti("SDX_LANES", 1);
+        c->knobs.lane_ts = (int)geti("SDX_LANE_TS", 0);
+        c->knobs.lane_wpc = (int)geti("SDX_LANE_WPC", 0);
+        c->knobs.lane_min_chains = (int)geti("SDX_LANE_MIN_CHAINS", 0);
+    }
     *out = c;
     return SDX_OK;
 }
@@ -60,12 +76,13 @@ static void free_matrix(sdx_ctx *c) {
     if (c->d_samp) cudaFree(c->d_samp);
     if (c->d_trade_obs) cudaFree(c->d_trade_obs);
     if (c->d_rowsize) cudaFree(c->d_rowsize);
-    if (c->d_sp_desc) cudaFree(c->d_sp_desc);
-    if (c->d_sp_obs) cudaFree(c->d_sp_obs);
+    if (c->d_ln_desc) cudaFree(c->d_ln_desc);
+    if (c->d_ln_obs) cudaFree(c->d_ln_obs);
+    if (c->d_ln_pool) cudaFree(c->d_ln_pool);
     c->d_feat = c->d_samp = c->d_trade_obs = nullptr;
     c->d_rowsize = nullptr;
-    c->d_sp_desc = c->d_sp_obs = nullptr;
-    c->sp_state = 0;
+    c->d_ln_desc = nullptr; c->d_ln_obs = nullptr; c->d_ln_pool = nullptr; c->cap_ln_pool = 0;
+    c->ln_state = 0; c->ln_pool_valid = false;
     if (c->d_pool) cudaFree(c->d_pool);
     c->d_pool = nullptr;
     c->pool_valid = false;
@@ -76,10 +93,8 @@ static void free_matrix(sdx_ctx *c) {
 
 // a new matrix invalidates everything derived from the old one; the buffers themselves are kept and reused
 static void invalidate_matrix(sdx_ctx *c) {
-    if (c->d_sp_desc) cudaFree(c->d_sp_desc);
-    if (c->d_sp_obs) cudaFree(c->d_sp_obs);
-    c->d_sp_desc = c->d_sp_obs = nullptr;
-    c->sp_state = 0;
+    c->ln_state = 0;                  // the lane layout (row kinds and offsets) is rebuilt on first use
+    c->ln_pool_valid = false;
     c->pool_valid = false;
     c->top_K = 0;
 }
@@ -117,9 +132,17 @@ extern "C" int sdx_set_burn_in(sdx_ctx *c, int64_t burn_rounds, int pool_size) {
     if (!c) return SDX_ERR_INVALID;
     SDX_REQUIRE(c, burn_rounds >= 0 && burn_rounds <= 256, SDX_ERR_INVALID, "burn_rounds must be in 0..256");
     SDX_REQUIRE(c, burn_rounds == 0 || (pool_size >= 1 && pool_size <= 65536), SDX_ERR_INVALID, "pool_size must be in 1..65536");
-    if (burn_rounds != c->burn || pool_size != c->pool_size) c->pool_valid = false;
+    if (burn_rounds != c->burn || pool_size != c->pool_size) { c->pool_valid = false; c->ln_pool_valid = false; }
     c->burn = burn_rounds;
     c->pool_size = burn_rounds > 0 ? pool_size : 0;
+    if (burn_rounds == 0) c->top_K = 0;          // no burn-in trades: the dense-row table of the pool is not in use
+    return SDX_OK;
+}
+
+extern "C" int sdx_set_pair_group(sdx_ctx *c, int pair_group) {
+    if (!c) return SDX_ERR_INVALID;
+    SDX_REQUIRE(c, pair_group == 1 || pair_group == 32, SDX_ERR_INVALID, "pair_group must be 1 or 32");
+    c->pair_group = pair_group;
     return SDX_OK;
 }
 

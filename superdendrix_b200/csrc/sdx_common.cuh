@@ -43,9 +43,20 @@ struct sdx_ctx {
     int rows_are_samples = 0;
     uint32_t *d_trade_obs = nullptr;      // R x RS, observed matrix in trade orientation
     int *d_rowsize = nullptr;             // R: popcount of each trade row (invariant under Curveball)
-    // sparse layout of the trade rows (sdx_sparse.cuh): 0 = not built yet, 1 = in use, -1 = not applicable
-    int sp_state = 0, sp_n_dense = 0, sp_fp_words = 0;
-    uint32_t *d_sp_desc = nullptr, *d_sp_obs = nullptr;
+    // lane layout of the trade rows (sdx_lanes.cu): 0 = not built yet, 1 = built, -1 = not applicable to this matrix
+    int ln_state = 0;
+    int ln_ts = 0;                        // rows of at most ln_ts elements are index lists, the others stay bit-packed
+    int ln_slot_bytes = 0;                // one staging buffer of the lane kernel (largest row of a 32-null group)
+    int ln_has_bits = 0;
+    uint32_t ln_gsb = 0;                  // bytes of the state of one group of 32 nulls (compact state of one null: ln_gsb / 32)
+    uint2 *d_ln_desc = nullptr;           // R row descriptors: (byte offset in the group state, size | kind << 31)
+    uint8_t *d_ln_obs = nullptr;          // the observed matrix as one compact state
+    uint8_t *d_ln_pool = nullptr;         // the burn-in pool as pool_size compact states (valid with pool_valid)
+    size_t cap_ln_pool = 0;
+    bool ln_pool_valid = false;
+    // how the PAIR stream is shared (sdx_set_pair_group): 1 = every null draws its own row pairs; 32 = the 32 chains
+    // c, c+1, .. of an aligned block draw them from the stream of the block's first chain
+    int pair_group = 1;
     // burn-in pool (sdx_set_burn_in): pool_size well-mixed start states, each the observed matrix after `burn` rounds
     int64_t burn = 0;
     int pool_size = 0;
@@ -68,6 +79,13 @@ struct sdx_ctx {
     DevBuf scratch[20];
     // capacities (bytes) of the grow-only matrix / weight / pool buffers: re-uploads of the same shape never touch the allocator
     size_t cap_feat = 0, cap_samp = 0, cap_obs = 0, cap_rowsize = 0, cap_pool = 0, cap_w = 0, cap_mask = 0, cap_nsamp = 0;
+    // tuning knobs (benchmarks and tests only), read from the environment ONCE in sdx_create — never on the call path
+    struct Knobs {
+        int trade_g = 0, trade_warps = 0, trade_lb = -1, plan_cap = 0, grid_cap = 0;
+        long nulls_per_launch = 0, pad_smem = 0;
+        int lanes = 1;                    // 0: never use the lane kernel (pair_group 32 then runs on k_trade)
+        int lane_ts = 0, lane_wpc = 0, lane_min_chains = 0;
+    } knobs;
 };
 
 inline int sdx_fail(sdx_ctx *c, int code, const std::string &msg) {
@@ -158,7 +176,7 @@ inline PhiloxKeys make_keys(uint64_t seed) {
     return k;
 }
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &k) {
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &k) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c.x;
@@ -173,14 +191,14 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &k) {
     return c;
 }
 
-__device__ __forceinline__ uint4 stream_block(const PhiloxKeys &k, uint32_t kind, uint64_t id, uint32_t t, uint32_t block) {
+__host__ __device__ __forceinline__ uint4 stream_block(const PhiloxKeys &k, uint32_t kind, uint64_t id, uint32_t t, uint32_t block) {
     uint4 c;
     c.x = block; c.y = t; c.z = (uint32_t)id;
     c.w = ((uint32_t)(id >> 32) & 0x3fffffffu) | (kind << 30);
     return philox4x32_10(c, k);
 }
 
-__device__ __forceinline__ uint32_t pick4(const uint4 &v, uint32_t i) {
+__host__ __device__ __forceinline__ uint32_t pick4(const uint4 &v, uint32_t i) {
     uint32_t lo = (i & 1) ? v.y : v.x;
     uint32_t hi = (i & 1) ? v.w : v.z;
     return (i & 2) ? hi : lo;
@@ -192,14 +210,14 @@ struct ThreadStream {
     const PhiloxKeys &k;
     uint32_t kind; uint64_t id; uint32_t t;
     uint32_t block; uint32_t pos; uint4 buf;
-    __device__ __forceinline__ ThreadStream(const PhiloxKeys &keys, uint32_t kind_, uint64_t id_, uint32_t t_)
+    __host__ __device__ __forceinline__ ThreadStream(const PhiloxKeys &keys, uint32_t kind_, uint64_t id_, uint32_t t_)
         : k(keys), kind(kind_), id(id_), t(t_), block(0), pos(4) {}
-    __device__ __forceinline__ uint32_t next() {
+    __host__ __device__ __forceinline__ uint32_t next() {
         if (pos == 4) { buf = stream_block(k, kind, id, t, block++); pos = 0; }
         return pick4(buf, pos++);
     }
     // exactly uniform in [0, m)  (Lemire, with rejection)
-    __device__ __forceinline__ uint32_t below(uint32_t m) {
+    __host__ __device__ __forceinline__ uint32_t below(uint32_t m) {
         uint64_t prod = (uint64_t)next() * m;
         uint32_t lo = (uint32_t)prod;
         if (lo < m) {
@@ -210,7 +228,7 @@ struct ThreadStream {
     }
 };
 
-__device__ __forceinline__ void trade_pair(const PhiloxKeys &k, uint64_t null_id, uint32_t t, uint32_t R, uint32_t &a, uint32_t &b) {
+__host__ __device__ __forceinline__ void trade_pair(const PhiloxKeys &k, uint64_t null_id, uint32_t t, uint32_t R, uint32_t &a, uint32_t &b) {
     ThreadStream s(k, SDX_STREAM_PAIR, null_id, t);
     a = s.below(R);
     b = s.below(R - 1);

@@ -10,8 +10,16 @@ struct NullIndexing {          // local null index (within a launch) -> global n
     int64_t seg_off;           // chain-relative offset of the segment
     int seg_len;               // nulls per chain in this launch
     uint64_t null_lo, null_hi; // requested range [null_lo, null_hi)
+    int pair_group;            // sdx_set_pair_group: 1, or 32 = aligned blocks of 32 chains share the PAIR stream of their first chain
     __host__ __device__ uint64_t id(int64_t local) const {
         return (chain0 + (uint64_t)(local / seg_len)) * (uint64_t)chain_len + (uint64_t)seg_off + (uint64_t)(local % seg_len);
+    }
+    // stream id the row pairs of null `id` are drawn from: round j of chain c uses the pairs of round j of
+    // chain c - c % pair_group, so a block of pair_group chains walks the same schedule of row pairs
+    __host__ __device__ uint64_t pair_id(uint64_t id) const {
+        if (pair_group <= 1) return id;
+        const uint64_t c = id / (uint64_t)chain_len, j = id - c * (uint64_t)chain_len;
+        return (c - c % (uint64_t)pair_group) * (uint64_t)chain_len + j;
     }
 };
 
@@ -53,12 +61,13 @@ __global__ void __launch_bounds__(PL_NT) k_plan_levels(const __grid_constant__ P
     // shared-memory chain of the level walk and fills its latency.  Pairs and levels leave through the tiles, coalesced.
     const uint64_t null_id = ix.id(n < n_local ? n : 0);
     const bool burn = top_K >= 2 && null_id >= SDX_BURN_ID_MIN;     // burn-in rounds of the pool (the whole launch or none of it)
+    const uint64_t pair_id = ix.pair_id(null_id);
     for (int t0 = 0; t0 < T; t0 += PL_TT) {
         const int cnt = T - t0 < PL_TT ? T - t0 : PL_TT;
         for (int c = 0; c < cnt; ++c) {
             uint32_t a, b;
             if (burn) trade_pair_burn(keys, null_id, (uint32_t)(t0 + c), (uint32_t)R, top, (uint32_t)top_K, a, b);
-            else trade_pair(keys, null_id, (uint32_t)(t0 + c), (uint32_t)R, a, b);
+            else trade_pair(keys, pair_id, (uint32_t)(t0 + c), (uint32_t)R, a, b);
             tile_p[tid * (PL_TT + 1) + c] = a | (b << 16);
             const int la = last[(size_t)a * PL_NT], lb = last[(size_t)b * PL_NT];
             int l = (la > lb ? la : lb) + 1;
@@ -96,26 +105,19 @@ __global__ void __launch_bounds__(PL_NT) k_plan_levels(const __grid_constant__ P
 // trade and |a| + |b| bounds its symmetric difference.  Inside a level the plan lists the large
 // trades first and groups similar sizes, so the groups of one warp run loops of similar length and
 // the register fast path of trade_rows (n <= 64) is taken by whole warps.
-// With the sparse layout (ts >= 0: rows of at most ts carriers are index lists, sdx_sparse.cuh) classes 0 and 1 are
-// the trades that involve a bit-packed row and classes 2 and 3 the list x list trades (one per thread), split by the
-// total list length so that the threads of a warp walk lists of similar length.
-__device__ __forceinline__ int trade_class(int sa, int sb, int ts) {
+__device__ __forceinline__ int trade_class(int sa, int sb) {
     const int kb = sa < sb ? sa : sb;
-    if (ts >= 0) {
-        if (sa > ts || sb > ts) return sa + sb > 64 ? 0 : 1;
-        return sa + sb > 12 ? 2 : 3;
-    }
     if (sa + sb > 64) return 0;
     return kb > 8 ? 1 : (kb > 3 ? 2 : 3);
 }
 
 // Round table (k_trade): one u32 per round = the `ng` trades a CTA of the trade kernel runs at a time:
 //   bits 0-15 first plan entry, bits 16-30 number of trades, bit 31 last round of its level (barrier after it).
-// The kernel then needs no level bookkeeping at all.  rt == nullptr: not written (sparse / work-queue kernels use offs).
+// The kernel then needs no level bookkeeping at all.
 __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const uint32_t *__restrict__ pairs,
                             const uint16_t *__restrict__ lvl, const int *__restrict__ depth, const int *__restrict__ rowsize,
-                            const uint32_t *__restrict__ desc, int ts, void *__restrict__ plan, uint16_t *__restrict__ offs,
-                            int offs_stride, uint32_t *__restrict__ rt, int rt_stride, int *__restrict__ nrounds, int ng, int cache_bins) {
+                            uint2 *__restrict__ plan, uint32_t *__restrict__ rt, int rt_stride, int *__restrict__ nrounds, int ng,
+                            int cache_bins) {
     extern __shared__ uint32_t hist_smem[];        // per warp: dcap * SDX_NCLS + 2 bins + T u16 trade bins
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n = blockIdx.x * (blockDim.x >> 5) + wid;
@@ -127,13 +129,9 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
     uint32_t *hist = hist_smem + (size_t)wid * per_warp;
     uint16_t *bin = reinterpret_cast<uint16_t *>(hist + (dcap * SDX_NCLS + 2));
     const uint16_t *lv = lvl + (size_t)n * T;
-    // plan entry: (a | b << 16, t) for k_trade; (a | b << 16, t, descriptor of a, descriptor of b) for k_trade_sparse
-    uint2 *out2 = reinterpret_cast<uint2 *>(plan) + (size_t)n * T;
-    uint4 *out4 = reinterpret_cast<uint4 *>(plan) + (size_t)n * T;
-    auto emit = [&](uint32_t pos, uint32_t e, uint32_t t) {
-        if (desc) out4[pos] = make_uint4(e, t, desc[e & 0xffffu], desc[e >> 16]);
-        else out2[pos] = make_uint2(e, t);
-    };
+    // plan entry: (a | b << 16, t)
+    uint2 *out2 = plan + (size_t)n * T;
+    auto emit = [&](uint32_t pos, uint32_t e, uint32_t t) { out2[pos] = make_uint2(e, t); };
     const uint32_t *pr = pairs + (size_t)n * Tp;
     uint32_t *rtn = rt ? rt + (size_t)n * rt_stride : nullptr;
     if (D >= dcap) {            // very deep schedule: fall back to the sequential order (always valid)
@@ -149,7 +147,7 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
     __syncwarp();
     for (int t = lane; t < T; t += 32) {
         const uint32_t e = pr[t];
-        const int b = (lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16], ts);
+        const int b = (lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16]);
         if (cache_bins) bin[t] = (uint16_t)b;
         atomicAdd(&hist[b], 1u);
     }
@@ -169,10 +167,6 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
         carry += __shfl_sync(0xffffffffu, inc, 31);
     }
     __syncwarp();
-    // of[2l] = first entry of level l+1, of[2l+1] = its first class-2 entry (list x list trades start there), of[2D] = T
-    uint16_t *of = offs + (size_t)n * offs_stride;
-    for (int l = lane; l < D; l += 32) { of[2 * l] = (uint16_t)hist[l * SDX_NCLS]; of[2 * l + 1] = (uint16_t)hist[l * SDX_NCLS + 2]; }
-    if (lane == 0) of[2 * D] = (uint16_t)T;
     if (rtn) {
         // rounds of level l: ceil(n_l / ng); their positions in the table = prefix sum over the levels
         uint32_t rcarry = 0;
@@ -202,7 +196,7 @@ __global__ void k_plan_sort(int n_local, int R, int T, int Tp, int dcap, const u
     __syncwarp();
     for (int t = lane; t < T; t += 32) {
         const uint32_t e = pr[t];
-        const int b = cache_bins ? (int)bin[t] : (lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16], ts);
+        const int b = cache_bins ? (int)bin[t] : (lv[t] - 1) * SDX_NCLS + trade_class(rowsize[e & 0xffffu], rowsize[e >> 16]);
         const uint32_t pos = atomicAdd(&hist[b], 1u);
         emit(pos, e, (uint32_t)t);
     }

@@ -1,43 +1,24 @@
 // sdx_trade_kernel.cuh — k_trade: one CTA per chain, matrix in shared memory (or L2), trades level by level, fused scoring.
 // Included by sdx_curveball.cu only.
 #pragma once
+#include "sdx_nulls.cuh"
 #include "sdx_plan.cuh"
 
 // ---------------------------------------------------------------------------
 // trade kernel
 // ---------------------------------------------------------------------------
-struct ScoreArgs {
-    int n_profiles, k;
-    const int32_t *modules;           // P x k
-    const double *w;                  // P x S
-    const uint32_t *mask;             // P x wprS
-    const double *z_obs;              // P
-    unsigned long long *n_ge;         // P
-    double *null_scores;              // P x n_total, or null
-    int64_t n_total;                  // row length of null_scores
-    int S, wprS;
-    int rows_are_samples;
-    // column cache (k_trade, global-memory variant, rows are samples): the distinct features of all modules, and the
-    // modules as indices into that list.  n_ufeat = 0: not used.
-    const int32_t *ufeat;             // n_ufeat
-    const int32_t *umod;              // P x k
-    int n_ufeat;
-};
-
 struct TradeArgs {
     PhiloxKeys keys;
     NullIndexing ix;
     const uint32_t *observed;         // R x RS
     uint32_t *work;                   // gridDim.x x R x RS (global-resident variant only)
     uint32_t *carry;                  // n_units x R x RS: chain state between launches (or null)
-    const void *plan;                 // n_local x T: uint2 (a | b << 16, t), or uint4 with the two row descriptors (sparse layout)
-    const uint16_t *offs;             // n_local x offs_stride level offsets (sparse / work-queue kernels)
+    const uint2 *plan;                // n_local x T: (a | b << 16, t)
     const uint32_t *rt;               // n_local x rt_stride round table (k_trade), see k_plan_sort
     const int *nrounds;               // n_local
     int rt_stride;
     int dcap;                         // schedules at least this deep run in sequential order
     const int *depth;                 // n_local
-    int offs_stride;
     int n_units;                      // chain segments in this launch
     int R, RS, T, wprL;
     int save_carry;
@@ -46,10 +27,6 @@ struct TradeArgs {
     ScoreArgs sc;
     const uint32_t *pool;             // burn-in pool: pool_size start states in the kernel's state layout, or null
     int pool_size;
-    // sparse layout (k_trade_sparse only)
-    const uint32_t *desc;             // R row descriptors
-    const uint32_t *obs_state;        // fp_words: observed matrix in the sparse layout
-    int n_dense, fp_words;
 };
 
 // out-of-line copy of the scorer for the trade kernel: keeps its registers out of the trade loop's budget
@@ -95,7 +72,7 @@ __global__ void __launch_bounds__(lb_threads(LB), lb_blocks(LB)) k_trade(const _
             if (T > 0) {
                 // One table entry per round (k_plan_sort): first plan entry, number of trades, "last round of its level".
                 // The next round's trade and the descriptor after that are in flight while the current trades run.
-                const uint2 *pl = reinterpret_cast<const uint2 *>(p.plan) + (size_t)local * T;
+                const uint2 *pl = p.plan + (size_t)local * T;
                 const uint32_t *rt = p.rt + (size_t)local * p.rt_stride;
                 const int NR = p.nrounds[local];
                 const uint2 none = make_uint2(0u, 0u);

@@ -61,6 +61,11 @@ class Engine:
         (0 = start from the observed matrix, as a single reference chain does at null 0)."""
         self._check(self._lib.sdx_set_burn_in(self._ctx, int(burn_rounds), int(pool_size)))
 
+    def set_pair_group(self, pair_group: int):
+        """1: every null draws its own row pairs.  32: aligned blocks of 32 chains share the schedule of row pairs
+        (every null keeps its own deal stream) — the layout the one-thread-per-null kernel needs (include/sdx.h)."""
+        self._check(self._lib.sdx_set_pair_group(self._ctx, int(pair_group)))
+
     def timing(self) -> dict:
         t = _capi.Timing()
         self._check(self._lib.sdx_get_timing(self._ctx, C.byref(t)))
