@@ -48,10 +48,13 @@ struct sdx_ctx {
     int ln_ts = 0;                        // rows of at most ln_ts elements are index lists, the others stay bit-packed
     int ln_slot_bytes = 0;                // one staging buffer of the lane kernel (largest row of a 32-null group)
     int ln_has_bits = 0;
-    uint32_t ln_gsb = 0;                  // bytes of the state of one group of 32 nulls (compact state of one null: ln_gsb / 32)
+    uint32_t ln_gsb = 0;                  // bytes of the state of one group of 32 nulls: rows, then scratch (rank mask, scorer partials)
+    uint32_t ln_rows_bytes = 0, ln_c_off = 0, ln_pp_off = 0;      // LnLayout: the rows of a group state, offsets of its scratch
+    int ln_x_bytes = 0, ln_pf_bytes = 0;  // shared-memory buffers of one warp for a bit-packed row: the row, its prefix popcounts
     uint2 *d_ln_desc = nullptr;           // R row descriptors: (byte offset in the group state, size | kind << 31)
-    uint8_t *d_ln_obs = nullptr;          // the observed matrix as one compact state
-    uint8_t *d_ln_pool = nullptr;         // the burn-in pool as pool_size compact states (valid with pool_valid)
+    uint8_t *d_ln_obs = nullptr;          // the observed matrix as the rows of one group (32 copies, lanes interleaved)
+    uint8_t *d_ln_pool = nullptr;         // the burn-in pool: pool_size / 32 groups (ln_pool_groups), else pool_size compact states
+    bool ln_pool_groups = false;
     size_t cap_ln_pool = 0;
     bool ln_pool_valid = false;
     // how the PAIR stream is shared (sdx_set_pair_group): 1 = every null draws its own row pairs; 32 = the 32 chains

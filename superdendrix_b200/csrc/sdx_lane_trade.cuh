@@ -11,6 +11,14 @@
 // invariants of Curveball, so every row has a fixed slot and — because the 32 lanes trade the same two rows — every
 // loop bound below is warp-uniform: no lock-step inflation, no shuffles, no level plan.
 //
+// Three kinds of trade:
+//   list x list        both rows staged in shared memory (TMA), two merge walks, picked ranks in a register mask
+//   bit-packed x list  both staged (the bit-packed row in the warp's one large buffer X); nothing is converted: the
+//                      list's entries are tested against the bits, a picked rank is mapped to its element by a select on
+//                      the bits, and only the <= 2k elements that change rows are toggled
+//   bit-packed x bit-packed  both rows read and updated IN PLACE in the group state (every lane touches only its own
+//                      column), rank mask in the group's scratch words (rare: the few dense rows)
+//
 // Everything here is __host__ __device__ and touches memory only through the lane's own column pointers, so that
 // tests/tools/lane_host.cu can run the very same code lane by lane on the CPU against the oracle (no GPU needed).
 #pragma once
@@ -18,7 +26,7 @@
 
 #define LN_W 32                  // lanes (nulls) per group
 #define LN_SENT 0xFFFFu          // list sentinel: larger than every element (the lane kernel needs L <= 65535)
-#define LN_TS_MAX 64             // longest list the kernel accepts (symmetric difference <= 128 ranks)
+#define LN_TS_MAX 32             // longest list the kernel accepts (symmetric difference of two lists <= 64 ranks: a register pair)
 
 #ifdef __CUDA_ARCH__
 #define LN_WARP_MAX(x) __reduce_max_sync(0xffffffffu, (x))
@@ -41,6 +49,7 @@
 LN_HD uint32_t ln_size(uint2 d) { return d.y & 0xffffu; }
 LN_HD bool ln_is_bits(uint2 d) { return (d.y >> 31) != 0; }
 LN_HD uint32_t ln_row_bytes(uint2 d, int nw) { return ln_is_bits(d) ? (uint32_t)nw * 128u : ln_size(d) * 64u; }
+LN_HD uint32_t ln_stage_bytes(uint2 d) { return ln_is_bits(d) ? 0u : ln_size(d) * 64u; }      // the list buffers take only lists
 
 struct LnRng {                   // the DEAL stream of one trade of one null
     const PhiloxKeys *keys;
@@ -71,11 +80,35 @@ LN_HD uint32_t ln_pick(const LnRng &g, uint32_t i, uint32_t m, uint32_t x) {    
     return r;
 }
 
+// chosen ranks of a list x list trade: one register when 2 TS <= 32, a pair otherwise
+template <bool M64> struct LnMask;
+template <> struct LnMask<false> {
+    uint32_t v;
+    LN_HD LnMask() : v(0) {}
+    LN_HD explicit LnMask(uint32_t x) : v(x) {}
+    LN_HD bool test(uint32_t r) const { return (v >> r) & 1u; }
+    LN_HD void set(uint32_t r) { v |= 1u << r; }
+    LN_HD bool low() const { return v & 1u; }
+    LN_HD void shr() { v >>= 1; }
+    LN_HD LnMask inv() const { return LnMask(~v); }
+    static LN_HD LnMask fill(bool ones) { return LnMask(ones ? 0xffffffffu : 0u); }
+};
+template <> struct LnMask<true> {
+    uint64_t v;
+    LN_HD LnMask() : v(0) {}
+    LN_HD explicit LnMask(uint64_t x) : v(x) {}
+    LN_HD bool test(uint32_t r) const { return (v >> r) & 1ull; }
+    LN_HD void set(uint32_t r) { v |= 1ull << r; }
+    LN_HD bool low() const { return v & 1ull; }
+    LN_HD void shr() { v >>= 1; }
+    LN_HD LnMask inv() const { return LnMask(~v); }
+    static LN_HD LnMask fill(bool ones) { return LnMask(ones ? ~0ull : 0ull); }
+};
+
 struct LnDeal {                  // what phase 1 of a trade hands to phase 2
-    uint32_t cm;                 // chosen ranks (register form: n <= 32)
-    uint32_t lb;                 // |b \ a|
+    uint32_t k;                  // picks of this lane (0: the lane keeps its rows)
+    uint32_t cmn;                // bit-packed x list: which list entries are common
     bool go;                     // the trade is applied (src/curveball.py:29: skipped when one row contains the other)
-    bool small_is_a;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -83,96 +116,48 @@ struct LnDeal {                  // what phase 1 of a trade hands to phase 2
 // elements (one merge walk) and draws the picks; phase 2 is the second merge walk that deals the elements into the
 // output lists OA (sa entries) and OB (sb entries), both with room for one entry more.  The walks run sa + sb steps in
 // every lane (the c steps that a lane with c common elements has left over find both lists at their sentinels).
-// MREG: the chosen ranks fit one register (sa + sb <= 32); otherwise they live in C (u32 words at stride 32).
+// toA: bit r = the symmetric-difference element of rank r goes to row a.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool MREG>
-LN_HD LnDeal ln_ll_phase1(const uint16_t *A, int sa, const uint16_t *B, int sb, uint32_t *C, const LnRng &g, uint32_t &kmax_out) {
+// common elements of two sorted lists (one merge walk)
+LN_HD uint32_t ln_ll_common(const uint16_t *A, int sa, const uint16_t *B, int sb) {
     const int steps = sa + sb;
     const uint16_t *pa = A, *pb = B;
     uint32_t c = 0;
+#pragma unroll 2
     for (int s = 0; s < steps; ++s) {
         const uint32_t x = *pa, y = *pb;
-        const bool valid = (x & y) != LN_SENT;
-        const bool le = x <= y, ge = y <= x;
-        c += (le && ge && valid) ? 1u : 0u;
-        pa += (le && valid) ? LN_W : 0;
-        pb += (ge && valid) ? LN_W : 0;
+        const bool adva = x <= y && x != LN_SENT, advb = y <= x && y != LN_SENT;
+        if (adva && advb) ++c;
+        if (adva) pa += LN_W;
+        if (advb) pb += LN_W;
     }
-    const uint32_t La = (uint32_t)sa - c, Lb = (uint32_t)sb - c, n = La + Lb;
-    LnDeal d;
-    d.go = La != 0 && Lb != 0;
-    d.small_is_a = La <= Lb;
-    d.lb = Lb;
-    d.cm = 0;
-    const uint32_t k = d.go ? (d.small_is_a ? La : Lb) : 0u;
-    const uint32_t kmax = LN_WARP_MAX(k);
-    kmax_out = kmax;
-    if (kmax == 0) return d;                            // warp-uniform: nobody trades
-    if (!MREG) {
-        const int nwc = (steps >> 5) + 2;
-        for (int w = 0; w < nwc; ++w) C[w * LN_W] = 0u;
-    }
-    uint32_t cm = 0;
-    for (uint32_t blk = 0; blk * 4 < kmax; ++blk) {
-        const uint4 xb = stream_block(*g.keys, SDX_STREAM_DEAL, g.null_id, g.t, blk);
-        const uint32_t x[4] = {xb.x, xb.y, xb.z, xb.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t i = blk * 4 + q;
-            if (i < k) {
-                const uint32_t m = n - k + i + 1;       // Floyd: j = m - 1, r uniform in [0, j]
-                uint32_t r = ln_pick(g, i, m, x[q]);
-                if (MREG) {
-                    if ((cm >> r) & 1u) r = m - 1;
-                    cm |= 1u << r;
-                } else {
-                    uint32_t w = C[(r >> 5) * LN_W];
-                    if ((w >> (r & 31)) & 1u) { r = m - 1; w = C[(r >> 5) * LN_W]; }
-                    C[(r >> 5) * LN_W] = w | (1u << (r & 31));
-                }
-            }
-        }
-    }
-    d.cm = cm;
-    return d;
+    return c;
 }
 
-template <bool MREG>
-LN_HD void ln_ll_phase2(const uint16_t *A, int sa, const uint16_t *B, int sb, uint16_t *OA, uint16_t *OB, const uint32_t *C, const LnDeal &d) {
+template <bool M64>
+LN_HD void ln_ll_phase2(const uint16_t *A, int sa, const uint16_t *B, int sb, uint16_t *OA, uint16_t *OB, LnMask<M64> toA) {
     const int steps = sa + sb;
     const uint16_t *pa = A, *pb = B;
     uint16_t *oa = OA, *ob = OB;
-    // a lane that does not trade keeps its rows: every symmetric-difference element then comes from one row only, so
-    // "picked for the smaller side a" = all (b \ a is empty) or none (a \ b is empty) reproduces the input
-    const bool sia = d.go ? d.small_is_a : true;
-    const uint32_t keep = d.lb == 0 ? 0xffffffffu : 0u;
-    uint32_t cur = MREG ? (d.go ? d.cm : keep) : 0u, rank = 0;
+#pragma unroll 2
     for (int s = 0; s < steps; ++s) {
         const uint32_t x = *pa, y = *pb;
-        const bool valid = (x & y) != LN_SENT;
-        const bool le = x <= y, ge = y <= x;
-        const bool common = le && ge;
-        const bool symel = valid && !common;
-        if (!MREG) {
-            if (symel && (rank & 31u) == 0) cur = d.go ? C[(rank >> 5) * LN_W] : keep;
-        }
-        const bool picked = (cur & 1u) != 0;
-        if (symel) { cur >>= 1; ++rank; }
-        const bool to_a = common || picked == sia;
-        const bool to_b = common || picked != sia;
-        const uint16_t e = (uint16_t)(le ? x : y);
+        const bool adva = x <= y && x != LN_SENT, advb = y <= x && y != LN_SENT;      // neither: both lists are at their sentinels
+        const bool bit = toA.low();
+        const uint16_t e = (uint16_t)(x <= y ? x : y);
         *oa = e; *ob = e;                               // stored to both lists; only the list that takes it advances
-        oa += (valid && to_a) ? LN_W : 0;
-        ob += (valid && to_b) ? LN_W : 0;
-        pa += (le && valid) ? LN_W : 0;
-        pb += (ge && valid) ? LN_W : 0;
+        if (adva != advb) toA.shr();                    // a symmetric-difference element: dealt by its rank
+        if (adva ? (advb || bit) : (advb && bit)) oa += LN_W;          // common, or dealt to a
+        if (advb ? (adva || !bit) : (adva && !bit)) ob += LN_W;
+        if (adva) pa += LN_W;
+        if (advb) pb += LN_W;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// bit-packed x bit-packed (nw words each, stride 32).  Phase 1: |a\b|, |b\a| and the picks as a rank mask in C
-// (nw + 2 words).  Phase 2: every word takes its popc(a ^ b) bits of the rank mask and deposits them onto the set
-// bits of a ^ b (software pdep); DA / DB may alias A / B (each word is read before it is written, by its own lane).
+// bit-packed x bit-packed (nw words each, stride 32, IN PLACE).  Phase 1: |a\b|, |b\a| and the picks as a rank mask in
+// C (nw + 2 words).  Phase 2: every word takes its popc(a ^ b) bits of the rank mask and deposits them onto the set
+// bits of a ^ b (software pdep).
 // ---------------------------------------------------------------------------------------------------------------
 LN_HD uint32_t ln_funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
 #ifdef __CUDA_ARCH__
@@ -183,49 +168,24 @@ LN_HD uint32_t ln_funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
 #endif
 }
 
-LN_HD LnDeal ln_bb_phase1(const uint32_t *A, const uint32_t *B, int nw, uint32_t *C, const LnRng &g, uint32_t &kmax_out) {
-    uint32_t La = 0, Lb = 0;
+LN_HD void ln_bb_count(const uint32_t *A, const uint32_t *B, int nw, uint32_t &La, uint32_t &Lb) {
+    La = 0; Lb = 0;
+#pragma unroll 1
     for (int w = 0; w < nw; ++w) {
         const uint32_t a = A[w * LN_W], b = B[w * LN_W];
         La += LN_POPC(a & ~b);
         Lb += LN_POPC(b & ~a);
     }
-    const uint32_t n = La + Lb;
-    LnDeal d;
-    d.go = La != 0 && Lb != 0;
-    d.small_is_a = La <= Lb;
-    d.lb = Lb;
-    d.cm = 0;
-    const uint32_t k = d.go ? (d.small_is_a ? La : Lb) : 0u;
-    const uint32_t kmax = LN_WARP_MAX(k);
-    kmax_out = kmax;
-    if (kmax == 0) return d;
-    for (int w = 0; w < nw + 2; ++w) C[w * LN_W] = 0u;
-    for (uint32_t blk = 0; blk * 4 < kmax; ++blk) {
-        const uint4 xb = stream_block(*g.keys, SDX_STREAM_DEAL, g.null_id, g.t, blk);
-        const uint32_t x[4] = {xb.x, xb.y, xb.z, xb.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t i = blk * 4 + q;
-            if (i < k) {
-                const uint32_t m = n - k + i + 1;
-                uint32_t r = ln_pick(g, i, m, x[q]);
-                uint32_t w = C[(r >> 5) * LN_W];
-                if ((w >> (r & 31)) & 1u) { r = m - 1; w = C[(r >> 5) * LN_W]; }
-                C[(r >> 5) * LN_W] = w | (1u << (r & 31));
-            }
-        }
-    }
-    return d;
 }
 
-LN_HD void ln_bb_phase2(const uint32_t *A, const uint32_t *B, uint32_t *DA, uint32_t *DB, int nw, const uint32_t *C, const LnDeal &d) {
+LN_HD void ln_bb_phase2(uint32_t *A, uint32_t *B, int nw, const uint32_t *C, const LnDeal &d, bool small_is_a) {
+    if (!d.go) return;                                  // in place: a lane that does not trade has nothing to write
     uint32_t rank = 0;
+#pragma unroll 1
     for (int w = 0; w < nw; ++w) {
         const uint32_t a = A[w * LN_W], b = B[w * LN_W];
-        uint32_t na = a, nb = b;
         const uint32_t sym = a ^ b, cnt = LN_POPC(sym);
-        if (d.go && cnt) {
+        if (cnt) {
             const uint32_t w0 = rank >> 5;
             uint32_t ch = ln_funnel_r(C[w0 * LN_W], C[(w0 + 1) * LN_W], rank & 31u);
             if (cnt < 32) ch &= (1u << cnt) - 1u;
@@ -237,83 +197,255 @@ LN_HD void ln_bb_phase2(const uint32_t *A, const uint32_t *B, uint32_t *DA, uint
                 ch >>= 1;
             }
             const uint32_t ab = a & b, rest = sym ^ pk;
-            na = ab | (d.small_is_a ? pk : rest);
-            nb = ab | (d.small_is_a ? rest : pk);
+            A[w * LN_W] = ab | (small_is_a ? pk : rest);
+            B[w * LN_W] = ab | (small_is_a ? rest : pk);
         }
-        DA[w * LN_W] = na; DB[w * LN_W] = nb;
         rank += cnt;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// list <-> bit-packed scratch row (trades between a list row and a bit-packed row run as bit-packed trades)
+// bit-packed row (D: nw words STAGED in shared memory, sd elements) x list row (Lst: sl <= TS sorted entries, staged).
+// Row kinds follow the row size (list iff size <= TS), so the list is the smaller side:
+// |l\d| <= sl <= TS < sd - |d∩l| = |d\l|.  The list keeps its common elements and receives k = |l\d| of the n
+// symmetric-difference elements, chosen by rank (Floyd, as everywhere).  Nothing is converted: the list's entries are
+// tested against the bits, a picked rank is mapped to its element by a select on the bits, and only the <= 2k elements
+// that change rows are toggled in D.
+//   phase 1 (reads only): PF4[q] = elements of d below word 4q ((nw + 3) / 4 + 1 u16), per list entry RK[i] = its rank
+//                         in the symmetric difference (own entries) or the number of d\l elements below it (common
+//                         entries), the picked ranks PK[0 .. k)
+//   phase 2: resolves every pick against the ORIGINAL row d (a pick that is one of the list's own entries keeps it
+//            there; any other is the q-th element of d\l, found by a search in PF4 and a select in the word), then
+//            toggles the <= 2k bits of D and writes the new sorted list OL by counting, for every element, the
+//            elements below it.
+// All loop bounds (nw, sl, kmax) are warp-uniform.
 // ---------------------------------------------------------------------------------------------------------------
-LN_HD void ln_list_to_bits(const uint16_t *Lst, int size, uint32_t *X, int nw) {
-    for (int w = 0; w < nw; ++w) X[w * LN_W] = 0u;
-    for (int i = 0; i < size; ++i) {
-        const uint32_t e = Lst[i * LN_W];
-        X[(e >> 5) * LN_W] |= 1u << (e & 31);
+LN_HD uint32_t ln_bl_prepare(const uint32_t *D, int nw, const uint16_t *Lst, int sl, uint16_t *PF4, uint16_t *RK, uint32_t &cmn_out) {
+    const int nq = (nw + 3) >> 2;
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int q = 0; q < nq; ++q) {
+        PF4[q * LN_W] = (uint16_t)acc;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int w = 4 * q + v;
+            if (w < nw) acc += LN_POPC(D[w * LN_W]);
+        }
     }
+    PF4[nq * LN_W] = (uint16_t)acc;
+    uint32_t c = 0, cmn = 0;
+#pragma unroll 1
+    for (int i = 0; i < sl; ++i) {
+        const uint32_t e = Lst[i * LN_W], w = e >> 5, sh = e & 31u;
+        const uint32_t dw = D[w * LN_W];
+        const uint32_t bit = (dw >> sh) & 1u;
+        uint32_t below = (uint32_t)PF4[(w >> 2) * LN_W] + LN_POPC(dw & ((1u << sh) - 1u));     // elements of d below e
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            const uint32_t ww = (w & ~3u) + (uint32_t)v;
+            if (ww < w) below += LN_POPC(D[ww * LN_W]);
+        }
+        // the c common entries so far are all below e: below - c elements of d\l, i - c elements of l\d lie below it
+        RK[i * LN_W] = (uint16_t)(below - c + (bit ? 0u : (uint32_t)i - c));
+        cmn |= bit << i;
+        c += bit;
+    }
+    cmn_out = cmn;
+    return c;
 }
 
-LN_HD void ln_bits_to_list(const uint32_t *X, int nw, uint16_t *Out) {
-    uint16_t *o = Out;
-    for (int w = 0; w < nw; ++w) {
-        uint32_t x = X[w * LN_W];
-        while (x) {
-            *o = (uint16_t)(w * 32 + LN_FFS(x) - 1);
-            o += LN_W;
-            x &= x - 1;
+// position (0..31) of the j-th (0-based) set bit of x; j < popc(x)
+LN_HD uint32_t ln_select32(uint32_t x, uint32_t j) {
+    uint32_t pos = 0;
+#pragma unroll
+    for (int sh = 16; sh >= 1; sh >>= 1) {
+        const uint32_t lowc = LN_POPC(x & ((1u << sh) - 1u));
+        const bool up = j >= lowc;
+        j -= up ? lowc : 0u;
+        x = up ? (x >> sh) : x;
+        pos += up ? (uint32_t)sh : 0u;
+    }
+    return pos;
+}
+
+LN_HD void ln_bl_phase2(uint32_t *D, int nw, const uint16_t *Lst, int sl, uint16_t *OL, const uint16_t *PF4, const uint16_t *RK, uint16_t *PK,
+                        const LnDeal &d, uint32_t kmax) {
+    const uint32_t k = d.k, cmn = d.cmn;
+    const int nq = (nw + 3) >> 2;
+    uint32_t keep = 0;
+    int top = 1;
+    while (top < nq) top <<= 1;
+    // resolve the picks (the row d is still the original one)
+#pragma unroll 1
+    for (uint32_t j = 0; j < kmax; ++j) {
+        uint32_t el = LN_SENT;
+        if (j < k) {
+            const uint32_t r = PK[j * LN_W];
+            uint32_t cntb = 0, own = 0;
+#pragma unroll 1
+            for (int i = 0; i < sl; ++i) {
+                const uint32_t v = RK[i * LN_W];
+                const bool mine = !((cmn >> i) & 1u);
+                if (mine && v < r) ++cntb;
+                if (mine && v == r) own |= 1u << i;
+            }
+            keep |= own;
+            if (!own) {
+                const uint32_t q = r - cntb;            // the q-th element of d \ l ...
+                uint32_t y = q;                         // ... is the y-th element of d: the common entries with <= q elements of d\l below them precede it
+#pragma unroll 1
+                for (int i = 0; i < sl; ++i) {
+                    const uint32_t v = RK[i * LN_W];
+                    if (((cmn >> i) & 1u) && v <= q) ++y;
+                }
+                int lo = 0;                             // largest block of 4 words with PF4[lo] <= y
+#pragma unroll 1
+                for (int step = top >> 1; step >= 1; step >>= 1) {
+                    const int cand = lo + step;
+                    if (cand < nq && (uint32_t)PF4[cand * LN_W] <= y) lo = cand;
+                }
+                uint32_t base = PF4[lo * LN_W], w = 4u * (uint32_t)lo;
+                bool found = false;
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {           // the word inside the block (the last one needs no test)
+                    const uint32_t cnt = LN_POPC(D[w * LN_W]);
+                    if (!found && y >= base + cnt) { base += cnt; ++w; } else found = true;
+                }
+                el = w * 32u + ln_select32(D[w * LN_W], y - base);
+            }
+        }
+        PK[j * LN_W] = (uint16_t)el;                     // the element that moves from d to the list, or LN_SENT
+    }
+    // the list's own entries that were not picked move to d; the picked elements of d\l leave it
+    const uint32_t stay = cmn | keep;
+#pragma unroll 1
+    for (int i = 0; i < sl; ++i)
+        if (!((stay >> i) & 1u)) {
+            const uint32_t e = Lst[i * LN_W];
+            D[(e >> 5) * LN_W] |= 1u << (e & 31u);
+        }
+#pragma unroll 1
+    for (uint32_t j = 0; j < kmax; ++j) {
+        const uint32_t el = PK[j * LN_W];
+        if (el != LN_SENT) D[(el >> 5) * LN_W] &= ~(1u << (el & 31u));
+    }
+    // the new list, sorted: position of an element = number of elements below it
+    uint32_t nst = 0;
+#pragma unroll 1
+    for (int i = 0; i < sl; ++i)
+        if ((stay >> i) & 1u) {
+            const uint32_t e = Lst[i * LN_W];
+            uint32_t pos = nst++;
+#pragma unroll 1
+            for (uint32_t j = 0; j < kmax; ++j) pos += (uint32_t)PK[j * LN_W] < e ? 1u : 0u;
+            OL[pos * LN_W] = (uint16_t)e;
+        }
+#pragma unroll 1
+    for (uint32_t j = 0; j < kmax; ++j) {
+        const uint32_t x = PK[j * LN_W];
+        if (x != LN_SENT) {
+            uint32_t pos = 0;
+#pragma unroll 1
+            for (int i = 0; i < sl; ++i) pos += (((stay >> i) & 1u) && (uint32_t)Lst[i * LN_W] < x) ? 1u : 0u;
+#pragma unroll 1
+            for (uint32_t j2 = 0; j2 < kmax; ++j2) pos += (uint32_t)PK[j2 * LN_W] < x ? 1u : 0u;
+            OL[pos * LN_W] = (uint16_t)x;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One trade of one lane on staged rows.  inA / inB: the two rows as they sit in the group state (lists or words, lanes
-// interleaved); outA / outB: the new rows in the same form; X: scratch row (nw words), C: chosen ranks — both at stride
-// 32 and already offset to the lane.  Phase 1 only reads the rows (and writes the list sentinels), phase 2 writes the
-// outputs; the kernel waits for the previous bulk store between the two.  A trade between a list row and a bit-packed
-// row runs as a bit-packed trade on the scratch form of the list.
+// One trade of one lane.  Staged lists: inA / inB as they arrive from the group state, outA / outB the new lists.  The
+// bit-packed row of a bit-packed x list trade is staged in X and updated there; the two rows of a bit-packed x
+// bit-packed trade are read and written in place through gA / gB (the lane's column of the row in the group state).
+// Scratch, all at stride 32 and already offset to the lane: PF4 ((nw + 3) / 4 + 1 u16), RK / PK (TS u16 each; the kernel
+// puts them into the list buffers the bit-packed row does not use), C (nw + 2 u32 words of the group state).
+// Phase 1 only reads the rows (and writes the list sentinels), phase 2 writes; the kernel waits for the previous bulk
+// store between the two.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool MREG>
-LN_HD LnDeal ln_trade_phase1(uint2 dA, uint2 dB, uint8_t *inA, uint8_t *inB, uint32_t *X, uint32_t *C, int nw, int lane, const LnRng &g,
-                             uint32_t &kmax) {
+template <bool M64>
+struct LnTrade {
+    LnDeal deal;
+    LnMask<M64> toA;
+    bool small_is_a;
+};
+
+template <bool M64>
+LN_HD void ln_trade_phase1(LnTrade<M64> &tr, uint2 dA, uint2 dB, uint16_t *inA, uint16_t *inB, uint32_t *gA, uint32_t *gB, const uint32_t *X,
+                           uint16_t *PF, uint16_t *RK, uint16_t *PK, uint32_t *C, int nw, const LnRng &g, uint32_t &kmax) {
     const int sa = (int)ln_size(dA), sb = (int)ln_size(dB);
     const bool ba = ln_is_bits(dA), bb = ln_is_bits(dB);
+    const int kind = ba == bb ? (ba ? 2 : 0) : 1;        // 0: list x list, 1: bit-packed x list, 2: bit-packed x bit-packed
     kmax = 0;
-    LnDeal deal;
-    deal.cm = 0; deal.lb = 0; deal.go = false; deal.small_is_a = true;
-    if (sa == 0 || sb == 0) return deal;                  // an empty row never trades (warp-uniform)
-    if (!ba && !bb) {
-        uint16_t *A = reinterpret_cast<uint16_t *>(inA) + lane, *B = reinterpret_cast<uint16_t *>(inB) + lane;
-        A[sa * LN_W] = (uint16_t)LN_SENT;
-        B[sb * LN_W] = (uint16_t)LN_SENT;
-        return ln_ll_phase1<MREG>(A, sa, B, sb, C, g, kmax);
+    tr.deal.k = 0; tr.deal.cmn = 0; tr.deal.go = false; tr.small_is_a = true;
+    if (sa == 0 || sb == 0) return;                     // an empty row never trades (warp-uniform)
+    // |a \ b|, |b \ a| by the kind of the rows
+    uint32_t La, Lb;
+    if (kind == 0) {
+        inA[sa * LN_W] = (uint16_t)LN_SENT;
+        inB[sb * LN_W] = (uint16_t)LN_SENT;
+        const uint32_t c = ln_ll_common(inA, sa, inB, sb);
+        La = (uint32_t)sa - c; Lb = (uint32_t)sb - c;
+    } else if (kind == 2) {
+        ln_bb_count(gA, gB, nw, La, Lb);
+    } else {
+        const uint32_t c = ln_bl_prepare(X, nw, ba ? inB : inA, ba ? sb : sa, PF, RK, tr.deal.cmn);
+        La = (uint32_t)sa - c; Lb = (uint32_t)sb - c;
     }
-    if (!ba) ln_list_to_bits(reinterpret_cast<const uint16_t *>(inA) + lane, sa, X, nw);
-    if (!bb) ln_list_to_bits(reinterpret_cast<const uint16_t *>(inB) + lane, sb, X, nw);
-    const uint32_t *srcA = ba ? reinterpret_cast<const uint32_t *>(inA) + lane : X;
-    const uint32_t *srcB = bb ? reinterpret_cast<const uint32_t *>(inB) + lane : X;
-    return ln_bb_phase1(srcA, srcB, nw, C, g, kmax);
+    const uint32_t n = La + Lb;
+    tr.deal.go = La != 0 && Lb != 0;
+    tr.small_is_a = La <= Lb;
+    const uint32_t k = tr.deal.go ? (tr.small_is_a ? La : Lb) : 0u;
+    tr.deal.k = k;
+    // a lane that does not trade keeps its rows: every symmetric-difference element then comes from one row only
+    tr.toA = LnMask<M64>::fill(Lb == 0);
+    kmax = LN_WARP_MAX(k);
+    if (kmax == 0) return;                              // warp-uniform: nobody trades
+    if (kind == 2) {
+#pragma unroll 1
+        for (int w = 0; w < nw + 2; ++w) C[w * LN_W] = 0u;
+    }
+    // Floyd's picks: k ranks out of n (the one place the DEAL stream is drawn)
+    LnMask<M64> cm;
+#pragma unroll 1
+    for (uint32_t blk = 0; blk * 4 < kmax; ++blk) {
+        const uint4 xb = stream_block(*g.keys, SDX_STREAM_DEAL, g.null_id, g.t, blk);
+        const uint32_t x[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t i = blk * 4 + q;
+            if (i < k) {
+                const uint32_t m = n - k + i + 1;       // j = m - 1, r uniform in [0, j]; every rank chosen so far is < j
+                uint32_t r = ln_pick(g, i, m, x[q]);
+                if (kind == 0) {
+                    if (cm.test(r)) r = m - 1;
+                    cm.set(r);
+                } else if (kind == 1) {
+                    bool dup = false;
+#pragma unroll 1
+                    for (uint32_t j = 0; j < i; ++j) dup = dup || PK[j * LN_W] == r;
+                    if (dup) r = m - 1;
+                    PK[i * LN_W] = (uint16_t)r;
+                } else {
+                    uint32_t w = C[(r >> 5) * LN_W];
+                    if ((w >> (r & 31)) & 1u) { r = m - 1; w = C[(r >> 5) * LN_W]; }
+                    C[(r >> 5) * LN_W] = w | (1u << (r & 31));
+                }
+            }
+        }
+    }
+    if (kind == 0 && tr.deal.go) tr.toA = tr.small_is_a ? cm : cm.inv();
 }
 
-template <bool MREG>
-LN_HD void ln_trade_phase2(uint2 dA, uint2 dB, const uint8_t *inA, const uint8_t *inB, uint8_t *outA, uint8_t *outB, uint32_t *X,
-                           const uint32_t *C, int nw, int lane, const LnDeal &deal) {
+template <bool M64>
+LN_HD void ln_trade_phase2(const LnTrade<M64> &tr, uint2 dA, uint2 dB, const uint16_t *inA, const uint16_t *inB, uint16_t *outA, uint16_t *outB,
+                           uint32_t *gA, uint32_t *gB, uint32_t *X, const uint16_t *PF, const uint16_t *RK, uint16_t *PK, const uint32_t *C,
+                           int nw, uint32_t kmax) {
     const int sa = (int)ln_size(dA), sb = (int)ln_size(dB);
     const bool ba = ln_is_bits(dA), bb = ln_is_bits(dB);
-    if (!ba && !bb) {
-        ln_ll_phase2<MREG>(reinterpret_cast<const uint16_t *>(inA) + lane, sa, reinterpret_cast<const uint16_t *>(inB) + lane, sb,
-                           reinterpret_cast<uint16_t *>(outA) + lane, reinterpret_cast<uint16_t *>(outB) + lane, C, deal);
-        return;
-    }
-    const uint32_t *srcA = ba ? reinterpret_cast<const uint32_t *>(inA) + lane : X;
-    const uint32_t *srcB = bb ? reinterpret_cast<const uint32_t *>(inB) + lane : X;
-    uint32_t *dstA = ba ? reinterpret_cast<uint32_t *>(outA) + lane : X;
-    uint32_t *dstB = bb ? reinterpret_cast<uint32_t *>(outB) + lane : X;
-    ln_bb_phase2(srcA, srcB, dstA, dstB, nw, C, deal);
-    if (!ba) ln_bits_to_list(X, nw, reinterpret_cast<uint16_t *>(outA) + lane);
-    if (!bb) ln_bits_to_list(X, nw, reinterpret_cast<uint16_t *>(outB) + lane);
+    if (!ba && !bb) ln_ll_phase2<M64>(inA, sa, inB, sb, outA, outB, tr.toA);
+    else if (ba && bb) ln_bb_phase2(gA, gB, nw, C, tr.deal, tr.small_is_a);
+    else ln_bl_phase2(X, nw, ba ? inB : inA, ba ? sb : sa, ba ? outB : outA, PF, RK, PK, tr.deal, kmax);
 }
 
 // entry of the trade schedule: rows a, b (14 bits each) and, in bits 28..30, whether the trade shares a row with the
@@ -331,7 +463,7 @@ LN_HD uint32_t ln_entry_rows_share(uint32_t e, uint32_t q) {
 // both kernels and a null equal to the observed matrix scores exactly z_obs (ties count, src/superdendrix.py:192).
 // PP / PN: 32 fp64 partials each at stride 32 (scratch of this lane).
 // ---------------------------------------------------------------------------------------------------------------
-LN_HD double ln_score(const uint8_t *state, int lane, const uint2 *desc, int nwL, const int32_t *mod, int k,
+LN_HD double ln_score(const uint8_t *state, int lane, const uint2 *desc, const int32_t *mod, int k,
                       const double *w, const uint32_t *mask, int S, double *PP, double *PN) {
     const int nw = (S + 31) >> 5;
     for (int i = 0; i < 32; ++i) { PP[i * LN_W] = 0.0; PN[i * LN_W] = 0.0; }
@@ -354,7 +486,6 @@ LN_HD double ln_score(const uint8_t *state, int lane, const uint2 *desc, int nwL
             }
         }
     }
-    (void)nwL;
     for (int wi = 0; wi < nw; ++wi) {
         const uint32_t m = mask[wi];
         uint32_t r[SDX_MAX_K];
@@ -362,7 +493,7 @@ LN_HD double ln_score(const uint8_t *state, int lane, const uint2 *desc, int nwL
 #pragma unroll
         for (int j = 0; j < SDX_MAX_K; ++j) {
             uint32_t x = 0;
-            if (bp[j]) x = LN_LDCG32(bp[j] + (size_t)wi * LN_W);
+            if (bp[j]) x = bp[j][(size_t)wi * LN_W];
             else {
                 while (left[j] > 0 && (head[j] >> 5) == (uint32_t)wi) {
                     x |= 1u << (head[j] & 31);
@@ -402,7 +533,7 @@ LN_HD void ln_emit_rows(const uint8_t *state, int lane, const uint2 *desc, int R
         uint32_t *o = dst + (size_t)r * wprL;
         if (ln_is_bits(d)) {
             const uint32_t *q = reinterpret_cast<const uint32_t *>(state + d.x) + lane;
-            for (int w = 0; w < wprL; ++w) o[w] = LN_LDCG32(q + (size_t)w * LN_W);
+            for (int w = 0; w < wprL; ++w) o[w] = q[(size_t)w * LN_W];
         } else {
             const uint16_t *p = reinterpret_cast<const uint16_t *>(state + d.x) + lane;
             const int n = (int)ln_size(d);
@@ -417,7 +548,7 @@ LN_HD void ln_emit_rows(const uint8_t *state, int lane, const uint2 *desc, int R
     }
 }
 
-// start state of the lane's chain: a compact state (the group layout with one lane: list entries / words contiguous)
+// start state of the lane's chain from a compact state (the group layout with one lane: list entries / words contiguous)
 LN_HD void ln_load_state(uint8_t *state, int lane, const uint2 *desc, int R, int wprL, const uint8_t *compact) {
     for (int r = 0; r < R; ++r) {
         const uint2 d = desc[r];
@@ -439,11 +570,17 @@ LN_HD void ln_load_state(uint8_t *state, int lane, const uint2 *desc, int R, int
 // ---------------------------------------------------------------------------------------------------------------
 struct LnLayout {
     int ts = 0, slot_bytes = 0, n_bits = 0, max_list = 0;
-    uint32_t gsb = 0;
+    uint32_t rows_bytes = 0;     // the rows of the 32 nulls (what a start state holds)
+    uint32_t c_off = 0;          // rank mask of bit-packed x bit-packed trades: (nw + 2) x 32 u32
+    uint32_t pp_off = 0;         // scorer partials: 2 x 32 x 32 fp64
+    uint32_t gsb = 0;            // bytes of one group state: rows, then the scratch above
+    int x_bytes = 0;             // shared-memory buffers of one warp for a bit-packed row: the row itself (X) ...
+    int pf_bytes = 0;            // ... and its prefix popcounts, one per 4 words (PF4)
 };
 
 inline int ln_default_ts(int nw) {
-    // a list trade costs ~28 instructions per element of the two rows, a bit-packed trade ~60 per word: short rows are lists
+    // a list trade costs ~30 instructions per element of the two rows, a trade with a bit-packed row ~5 per word + ~100 per
+    // list entry: short rows are lists
     int ts = nw / 2 + 4;
     if (ts < 16) ts = 16;
     if (ts > LN_TS_MAX) ts = LN_TS_MAX;
@@ -452,15 +589,21 @@ inline int ln_default_ts(int nw) {
 
 inline LnLayout ln_build_layout(const int *size, int R, int nw, int ts, uint2 *desc) {
     LnLayout lay;
+    if (ts > LN_TS_MAX) ts = LN_TS_MAX;
     lay.ts = ts;
     uint32_t off = 0;
     for (int r = 0; r < R; ++r)
         if (size[r] > ts) { desc[r] = make_uint2(off, (uint32_t)(size[r] > 0xffff ? 0xffff : size[r]) | 0x80000000u); off += (uint32_t)nw * 128u; ++lay.n_bits; }
     for (int r = 0; r < R; ++r)
         if (size[r] <= ts) { desc[r] = make_uint2(off, (uint32_t)size[r]); off += (uint32_t)size[r] * 64u; if (size[r] > lay.max_list) lay.max_list = size[r]; }
-    lay.gsb = ((off + 127u) / 128u) * 128u + 128u;
-    int slot = (lay.max_list + 1) * 64;
-    if (lay.n_bits && nw * 128 > slot) slot = nw * 128;
-    lay.slot_bytes = ((slot + 127) / 128) * 128;
+    lay.rows_bytes = ((off + 127u) / 128u) * 128u;
+    lay.c_off = lay.rows_bytes;
+    lay.pp_off = lay.c_off + (lay.n_bits ? (uint32_t)(nw + 2) * 128u : 0u);
+    lay.gsb = lay.pp_off + 2u * 32u * 32u * 8u;
+    // one staging buffer: the longest list + its sentinel; in a trade with a bit-packed row the unused buffers hold RK / PK (ts u16 each)
+    lay.slot_bytes = (lay.max_list + 1) * 64;
+    if (lay.n_bits && lay.slot_bytes < ts * 64) lay.slot_bytes = ts * 64;
+    lay.x_bytes = lay.n_bits ? nw * 128 : 0;
+    lay.pf_bytes = lay.n_bits ? (((nw + 3) / 4 + 1) * 64 + 127) / 128 * 128 : 0;
     return lay;
 }

@@ -13,14 +13,19 @@
 // no level plan, no plan memory and no barrier.
 //
 // Data movement: the state of a group of 32 nulls (C1: ~200 KB, lists of u16 indices for rows of <= TS elements,
-// bit-packed words for the others, lanes interleaved) lives in global memory / L2.  One elected lane moves the two
+// bit-packed words for the others, lanes interleaved) lives in global memory / L2.  One elected lane moves the LIST
 // rows of a trade into shared memory with TMA bulk copies (cp.async.bulk + mbarrier, two trades ahead: the schedule is
-// known, so a row pair is in flight while the previous two trades run) and the new rows back with bulk stores.  A trade
-// that shares a row with one of the three trades before it cannot be prefetched blindly: it waits for the bulk stores
-// in flight (cp.async.bulk.wait_group) or is loaded when its turn comes (~3 % of the trades).
+// known, so a row pair is in flight while the previous two trades run) and the new lists back with bulk stores.  A trade
+// that shares a list with one of the three trades before it cannot be prefetched blindly: it waits for the bulk stores
+// in flight (cp.async.bulk.wait_group) or is loaded when its turn comes (~3 % of the trades).  The group states of a
+// launch (C1: 3 125 x 220 KB) do not fit L2, so every row comes from HBM: the prefetch is what hides that latency.
+// A bit-packed row (the few dense ones) of a bit-packed x list trade has ONE large buffer X per warp, filled one trade
+// ahead; a trade between two bit-packed rows (1 %) works in place in the group state.  A warp needs 6 list buffers + X +
+// the prefix popcounts (C1: 10 KB), so 22 warps share an SM.
 //
 // The burn-in pool (sdx_set_burn_in) is still built by k_trade — 1 480 states are too few lanes for this kernel and
-// its dense x dense trades want the cooperative kernel — and converted once to compact states (k_ln_compact).
+// its dense x dense trades want the cooperative kernel — and converted once to the lane layout (k_ln_compact): whole
+// groups when the pool size is a multiple of 32 (a chain's start state is then one block copy), compact states otherwise.
 #include <algorithm>
 
 #include "sdx_lane_trade.cuh"
@@ -69,8 +74,8 @@ struct LaneArgs {
     int R, T, wprL;
     int slot_bytes;                   // one staging buffer
     int desc_bytes, warp_bytes;       // shared-memory layout: descriptor table, then warp_bytes per warp
-    int scratch_x_words;              // words of the scratch row X (0 when the matrix has no bit-packed row)
-    uint32_t gsb;                     // bytes of one group state
+    int x_bytes;                      // the buffer of a bit-packed row inside warp_bytes
+    uint32_t gsb, rows_bytes, c_off, pp_off;      // group state: rows, rank-mask scratch, scorer partials
     uint8_t *states;                  // n_groups x gsb
     uint64_t chain0;                  // first chain of group 0 of this launch (a multiple of 32)
     int64_t chain_len;
@@ -78,25 +83,30 @@ struct LaneArgs {
     int seg_len;
     uint64_t null_lo, null_hi;        // requested nulls
     int n_groups;
-    const uint8_t *src_states;        // n_src compact start states (the burn-in pool, or the observed matrix)
+    const uint8_t *src_states;        // start states: n_src groups of rows_bytes (src_groups), else n_src compact states of rows_bytes / 32
     int n_src;
+    int src_groups;
     uint32_t *out_rows;               // (null_id - null_lo) x R x wprL, zero-filled, or null
     unsigned long long *applied;      // (null_id - null_lo), or null
     ScoreArgs sc;
 };
 
-// bit-packed states (n x R x RS words, the layout of k_trade) -> compact states (one warp per row)
-__global__ void k_ln_compact(const uint32_t *__restrict__ rows, int n_states, int R, int RS, int wprL, const uint2 *__restrict__ desc,
-                             uint32_t csb, uint8_t *__restrict__ out) {
+// bit-packed states (n x R x RS words, the layout of k_trade; src_stride = 0: the same state n times) -> lane layout, one
+// warp per (state, row).  interleave = 0: compact states of csb bytes each (entries contiguous); 1: groups of 32 states,
+// csb bytes per group, state st in lane st % 32 of group st / 32.
+__global__ void k_ln_compact(const uint32_t *__restrict__ rows, size_t src_stride, int n_states, int R, int RS, int wprL,
+                             const uint2 *__restrict__ desc, uint32_t csb, int interleave, uint8_t *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t job = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (job >= (int64_t)n_states * R) return;
     const int st = (int)(job / R), r = (int)(job - (int64_t)st * R);
-    const uint32_t *src = rows + ((size_t)st * R + r) * RS;
+    const uint32_t *src = rows + (size_t)st * src_stride + (size_t)r * RS;
     const uint2 d = desc[r];
-    uint8_t *dst = out + (size_t)st * csb + d.x / LN_W;
+    const int stride = interleave ? LN_W : 1;
+    uint8_t *dst = interleave ? out + (size_t)(st >> 5) * csb + d.x : out + (size_t)st * csb + d.x / LN_W;
+    const int col = interleave ? (st & 31) : 0;
     if (ln_is_bits(d)) {
-        for (int w = lane; w < wprL; w += 32) reinterpret_cast<uint32_t *>(dst)[w] = src[w];
+        for (int w = lane; w < wprL; w += 32) reinterpret_cast<uint32_t *>(dst)[(size_t)w * stride + col] = src[w];
         return;
     }
     uint16_t *list = reinterpret_cast<uint16_t *>(dst);
@@ -112,7 +122,7 @@ __global__ void k_ln_compact(const uint32_t *__restrict__ rows, int n_states, in
             if (lane >= o) inc += v;
         }
         int pos = base + inc - cnt;
-        for (uint32_t y = x; y; y &= y - 1) list[pos++] = (uint16_t)(w * 32 + __ffs(y) - 1);
+        for (uint32_t y = x; y; y &= y - 1) { list[(size_t)pos * stride + col] = (uint16_t)(w * 32 + __ffs(y) - 1); ++pos; }
         base += __shfl_sync(0xffffffffu, inc, 31);
     }
 }
@@ -120,36 +130,65 @@ __global__ void k_ln_compact(const uint32_t *__restrict__ rows, int n_states, in
 // ---------------------------------------------------------------------------
 // the trade kernel: one warp per group of 32 chains
 // ---------------------------------------------------------------------------
+// entries of 32 trades, one per lane: a | b << 14 | flags << 28 (one copy of the PAIR draw in the kernel: code size)
+static __device__ __noinline__ uint32_t ln_make_entries(const PhiloxKeys *keys, uint64_t pid, uint32_t t0, uint32_t prev, uint32_t T, uint32_t R) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t u = t0 + (uint32_t)lane;
+    uint32_t a = 0, b = 1;
+    if (u < T) trade_pair(*keys, pid, u, R, a, b);
+    uint32_t e = a | (b << 14), fl = 0;
+#pragma unroll
+    for (int d = 1; d <= 3; ++d) {
+        const uint32_t q0 = __shfl_sync(0xffffffffu, e, (lane - d) & 31), q1 = __shfl_sync(0xffffffffu, prev, (lane - d) & 31);
+        const uint32_t q = lane >= d ? q0 : q1;
+        fl |= (u >= (uint32_t)d && ln_entry_rows_share(e, q)) ? (1u << (d - 1)) : 0u;
+    }
+    return e | (fl << 28);
+}
+
 #define LN_FLAG_PREV 1u               // shares a row with the trade before it: loaded when its turn comes
 #define LN_FLAG_NEAR 6u               // shares a row with the second / third trade before it: wait for the stores in flight
-template <bool MREG>
-__global__ void __launch_bounds__(256) k_trade_lanes(const __grid_constant__ LaneArgs p) {
+#define LN_MAX_THREADS 768
+template <bool M64>
+__global__ void __launch_bounds__(LN_MAX_THREADS, 1) k_trade_lanes(const __grid_constant__ LaneArgs p) {
     extern __shared__ __align__(128) uint8_t ln_smem[];
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, WPC = blockDim.x >> 5;
     const int R = p.R, T = p.T, nw = p.wprL, SLOT = p.slot_bytes;
     uint2 *s_desc = reinterpret_cast<uint2 *>(ln_smem);
     for (int i = threadIdx.x; i < R; i += blockDim.x) s_desc[i] = p.desc[i];
+    // per warp: stage 0 (lists a, b) | out (a, b) | stage 1 (a, b) | X | PF4 | three mbarriers
     uint8_t *wbase = ln_smem + p.desc_bytes + (size_t)wid * p.warp_bytes;
-    uint8_t *inb = wbase;                                   // stage s: row a at inb + 2 s SLOT, row b at inb + (2 s + 1) SLOT
-    uint8_t *outA = wbase + 4 * (size_t)SLOT, *outB = outA + SLOT;
-    uint32_t *X = reinterpret_cast<uint32_t *>(wbase + 6 * (size_t)SLOT) + lane;          // scratch row (bit-packed form of a list row)
-    uint32_t *C = X + (size_t)p.scratch_x_words * LN_W;                                   // chosen ranks
-    uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + p.warp_bytes - 16);
-    double *PP = reinterpret_cast<double *>(wbase) + lane, *PN = PP + 32 * LN_W;          // scorer partials (alias the idle staging buffers)
-    if (lane == 0) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); }
+    uint8_t *outA8 = wbase + 2 * (size_t)SLOT, *outB8 = outA8 + SLOT;
+    uint16_t *outA = reinterpret_cast<uint16_t *>(outA8) + lane, *outB = reinterpret_cast<uint16_t *>(outB8) + lane;
+    uint8_t *X8 = wbase + 6 * (size_t)SLOT;
+    uint32_t *X = reinterpret_cast<uint32_t *>(X8) + lane;
+    uint16_t *PF = reinterpret_cast<uint16_t *>(X8 + p.x_bytes) + lane;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + p.warp_bytes - 32);
+    if (lane == 0) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); mbar_init(smem_u32(&bars[2]), 1); }
     fence_mbar_init();
     fence_proxy_async();
     __syncthreads();
 
     uint32_t it = 0;                                        // trades issued so far by this warp: stage = it & 1, parity = (it >> 1) & 1
+    uint32_t xit = 0;                                       // loads of X so far: parity = xit & 1
     for (int g = blockIdx.x * WPC + wid; g < p.n_groups; g += gridDim.x * WPC) {
         const uint64_t c_base = p.chain0 + (uint64_t)g * LN_W;
         const uint64_t my_chain = c_base + (uint64_t)lane;
         uint8_t *state = p.states + (size_t)g * p.gsb;
+        uint32_t *C = reinterpret_cast<uint32_t *>(state + p.c_off) + lane;
+        double *PP = reinterpret_cast<double *>(state + p.pp_off) + lane, *PN = PP + 32 * LN_W;
         if (p.seg_off == 0) {
-            const uint8_t *src = p.src_states + (size_t)(p.n_src > 1 ? my_chain % (uint64_t)p.n_src : 0) * (p.gsb / LN_W);
-            ln_load_state(state, lane, s_desc, R, nw, src);
+            if (p.src_groups) {                             // the 32 start states are one block of the pool: copy it
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.src_states + (size_t)((c_base / LN_W) % (uint64_t)p.n_src) * p.rows_bytes);
+                uint4 *dst = reinterpret_cast<uint4 *>(state);
+                const int n16 = (int)(p.rows_bytes >> 4);
+#pragma unroll 8
+                for (int i = lane; i < n16; i += 32) dst[i] = __ldg(src + i);
+            } else {
+                const uint8_t *src = p.src_states + (size_t)(my_chain % (uint64_t)p.n_src) * (p.rows_bytes / LN_W);
+                ln_load_state(state, lane, s_desc, R, nw, src);
+            }
         }
         fence_proxy_async();                                // the bulk copies below read what the lanes just wrote
         __syncwarp();
@@ -161,36 +200,32 @@ __global__ void __launch_bounds__(256) k_trade_lanes(const __grid_constant__ Lan
             const uint64_t null_id = my_chain * (uint64_t)p.chain_len + round;
             unsigned int applied = 0;
 
-            auto issue = [&](uint32_t st, uint2 dA, uint2 dB) {                     // lane 0: rows of one trade -> stage st
-                const uint32_t bytesA = ln_row_bytes(dA, nw), bytesB = ln_row_bytes(dB, nw);
+            auto issue = [&](uint32_t st, uint2 dA, uint2 dB) {                     // lane 0: the lists of one trade -> stage st
+                const uint32_t bytesA = ln_stage_bytes(dA), bytesB = ln_stage_bytes(dB);
                 const uint32_t bar = smem_u32(&bars[st]);
+                uint8_t *sA = wbase + (size_t)(st ? 4 : 0) * SLOT;
                 mbar_expect_tx(bar, bytesA + bytesB);
-                if (bytesA) bulk_g2s(smem_u32(inb + (size_t)(2 * st) * SLOT), state + dA.x, bytesA, bar);
-                if (bytesB) bulk_g2s(smem_u32(inb + (size_t)(2 * st + 1) * SLOT), state + dB.x, bytesB, bar);
+                if (bytesA) bulk_g2s(smem_u32(sA), state + dA.x, bytesA, bar);
+                if (bytesB) bulk_g2s(smem_u32(sA + SLOT), state + dB.x, bytesB, bar);
             };
-            // entries of 32 trades, one per lane: a | b << 14 | flags << 28
-            auto make_entries = [&](uint32_t t0, uint32_t prev) -> uint32_t {
-                const uint32_t u = t0 + (uint32_t)lane;
-                uint32_t a = 0, b = 1;
-                if (u < (uint32_t)T) trade_pair(p.keys, pid, u, (uint32_t)R, a, b);
-                uint32_t e = a | (b << 14), fl = 0;
-#pragma unroll
-                for (int d = 1; d <= 3; ++d) {
-                    const uint32_t q0 = __shfl_sync(FULL, e, (lane - d) & 31), q1 = __shfl_sync(FULL, prev, (lane - d) & 31);
-                    const uint32_t q = lane >= d ? q0 : q1;
-                    fl |= (u >= (uint32_t)d && ln_entry_rows_share(e, q)) ? (1u << (d - 1)) : 0u;
-                }
-                return e | (fl << 28);
+            auto issue_x = [&](uint2 dA, uint2 dB) {                                // lane 0: the bit-packed row of a bit-packed x list trade -> X
+                const uint32_t bar = smem_u32(&bars[2]);
+                mbar_expect_tx(bar, (uint32_t)nw * 128u);
+                bulk_g2s(smem_u32(X8), state + (ln_is_bits(dA) ? dA.x : dB.x), (uint32_t)nw * 128u, bar);
             };
+            auto make_entries = [&](uint32_t t0, uint32_t prev) -> uint32_t { return ln_make_entries(&p.keys, pid, t0, prev, (uint32_t)T, (uint32_t)R); };
 
             uint32_t pr_cur = 0, pr_next = 0;
+            bool x_busy = false;                                                    // the latest bulk store reads X
             if (T > 0) {
                 pr_cur = make_entries(0, 0);
                 pr_next = make_entries(32, pr_cur);
                 // prologue: trades 0 and 1 (nothing is in flight: the pipeline is drained between rounds)
                 const uint32_t e0 = __shfl_sync(FULL, pr_cur, 0), e1 = __shfl_sync(FULL, pr_cur, 1);
                 if (lane == 0) {
-                    issue(it & 1u, s_desc[e0 & 0x3fffu], s_desc[(e0 >> 14) & 0x3fffu]);
+                    const uint2 d0a = s_desc[e0 & 0x3fffu], d0b = s_desc[(e0 >> 14) & 0x3fffu];
+                    issue(it & 1u, d0a, d0b);
+                    if (ln_is_bits(d0a) != ln_is_bits(d0b)) issue_x(d0a, d0b);
                     if (T > 1 && !((e1 >> 28) & LN_FLAG_PREV)) issue((it + 1) & 1u, s_desc[e1 & 0x3fffu], s_desc[(e1 >> 14) & 0x3fffu]);
                 }
             }
@@ -199,40 +234,64 @@ __global__ void __launch_bounds__(256) k_trade_lanes(const __grid_constant__ Lan
                 const uint32_t ent = __shfl_sync(FULL, pr_cur, t & 31);
                 const uint32_t a = ent & 0x3fffu, b = (ent >> 14) & 0x3fffu, fl = ent >> 28;
                 const uint2 dA = s_desc[a], dB = s_desc[b];
+                const bool ba = ln_is_bits(dA), bb = ln_is_bits(dB);
+                const bool use_x = ba != bb;
                 const uint32_t st = it & 1u, par = (it >> 1) & 1u;
-                if (t > 0 && (fl & LN_FLAG_PREV)) {                                 // could not be prefetched: the trade before wrote one of its rows
+                if (t > 0 && (fl & LN_FLAG_PREV)) {                                 // could not be prefetched: the trade before wrote one of its lists
                     if (lane == 0) { bulk_wait<0>(); issue(st, dA, dB); }
                 }
                 mbar_wait(smem_u32(&bars[st]), par);
+                if (use_x) { mbar_wait(smem_u32(&bars[2]), xit & 1u); ++xit; }
 
-                uint8_t *inA = inb + (size_t)(2 * st) * SLOT, *inB = inA + SLOT;
+                uint8_t *sA8 = wbase + (size_t)(st ? 4 : 0) * SLOT;
+                uint16_t *inA = reinterpret_cast<uint16_t *>(sA8) + lane, *inB = reinterpret_cast<uint16_t *>(sA8 + SLOT) + lane;
+                uint32_t *gA = reinterpret_cast<uint32_t *>(state + dA.x) + lane, *gB = reinterpret_cast<uint32_t *>(state + dB.x) + lane;
+                // a bit-packed x list trade keeps RK in the list buffer the bit-packed row does not use and PK in its output
+                // buffer: that one must not be under a bulk store any more
+                uint16_t *RK = ba ? inA : inB, *PK = ba ? outA : outB;
+                if (use_x) {
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                }
                 const LnRng rng{&p.keys, null_id, (uint32_t)t};
                 uint32_t kmax = 0;
-                const LnDeal deal = ln_trade_phase1<MREG>(dA, dB, inA, inB, X, C, nw, lane, rng, kmax);
+                LnTrade<M64> tr;
+                ln_trade_phase1<M64>(tr, dA, dB, inA, inB, gA, gB, X, PF, RK, PK, C, nw, rng, kmax);
                 // the output buffers are free once the previous bulk store has read them; every store but the latest is complete
                 if (lane == 0) { bulk_wait<1>(); bulk_wait_read<0>(); }
                 __syncwarp();
                 if (kmax != 0) {
-                    ln_trade_phase2<MREG>(dA, dB, inA, inB, outA, outB, X, C, nw, lane, deal);
-                    applied += deal.go ? 1u : 0u;
+                    ln_trade_phase2<M64>(tr, dA, dB, inA, inB, outA, outB, gA, gB, X, PF, RK, PK, C, nw, kmax);
+                    applied += tr.deal.go ? 1u : 0u;
                 }
                 fence_proxy_async_smem();                   // bulk stores read, and the next bulk load overwrites, what the lanes just wrote
                 __syncwarp();
+                // the rows of trade t + 1 / t + 2 that are fetched now
+                const uint32_t u1 = (uint32_t)t + 1, u2 = (uint32_t)t + 2;
+                const uint32_t e1 = __shfl_sync(FULL, (u1 >> 5) == ((uint32_t)t >> 5) ? pr_cur : pr_next, u1 & 31);
+                const uint32_t e2 = __shfl_sync(FULL, (u2 >> 5) == ((uint32_t)t >> 5) ? pr_cur : pr_next, u2 & 31);
                 if (lane == 0) {
                     if (kmax != 0) {
-                        bulk_s2g(state + dA.x, smem_u32(outA), ln_row_bytes(dA, nw));
-                        bulk_s2g(state + dB.x, smem_u32(outB), ln_row_bytes(dB, nw));
+                        if (!ba) bulk_s2g(state + dA.x, smem_u32(outA8), ln_stage_bytes(dA));
+                        else if (use_x) bulk_s2g(state + dA.x, smem_u32(X8), (uint32_t)nw * 128u);
+                        if (!bb) bulk_s2g(state + dB.x, smem_u32(outB8), ln_stage_bytes(dB));
+                        else if (use_x) bulk_s2g(state + dB.x, smem_u32(X8), (uint32_t)nw * 128u);
                     }
                     bulk_commit();                          // one group per trade (possibly empty): group index == trade index
-                }
-                // prefetch the rows of trade t + 2 into the stage that just became free
-                if (t + 2 < T) {
-                    const uint32_t u = (uint32_t)t + 2;
-                    const uint32_t eu = __shfl_sync(FULL, (u >> 5) == ((uint32_t)t >> 5) ? pr_cur : pr_next, u & 31);
-                    const uint32_t flu = eu >> 28;
-                    if (lane == 0 && !(flu & LN_FLAG_PREV)) {
-                        if (flu & LN_FLAG_NEAR) bulk_wait<0>();
-                        issue(st, s_desc[eu & 0x3fffu], s_desc[(eu >> 14) & 0x3fffu]);
+                    x_busy = use_x && kmax != 0;
+                    // the bit-packed row of trade t + 1 -> X (one trade ahead: X is a single buffer)
+                    if (u1 < (uint32_t)T) {
+                        const uint2 d1a = s_desc[e1 & 0x3fffu], d1b = s_desc[(e1 >> 14) & 0x3fffu];
+                        if (ln_is_bits(d1a) != ln_is_bits(d1b)) {
+                            if ((e1 >> 28) & 3u) bulk_wait<0>();            // shares a row with trade t or t - 1: their stores must have landed
+                            else if (x_busy) bulk_wait_read<0>();           // the store of this trade still reads X
+                            issue_x(d1a, d1b);
+                        }
+                    }
+                    // the lists of trade t + 2 -> the stage that just became free
+                    if (u2 < (uint32_t)T && !((e2 >> 28) & LN_FLAG_PREV)) {
+                        if ((e2 >> 28) & LN_FLAG_NEAR) bulk_wait<0>();
+                        issue(st, s_desc[e2 & 0x3fffu], s_desc[(e2 >> 14) & 0x3fffu]);
                     }
                 }
             }
@@ -249,14 +308,12 @@ __global__ void __launch_bounds__(256) k_trade_lanes(const __grid_constant__ Lan
                 for (int pr = 0; pr < p.sc.n_profiles; ++pr) {
                     double W = 0.0;
                     if (emit)
-                        W = ln_score(state, lane, s_desc, nw, p.sc.modules + (size_t)pr * p.sc.k, p.sc.k, p.sc.w + (size_t)pr * p.sc.S,
+                        W = ln_score(state, lane, s_desc, p.sc.modules + (size_t)pr * p.sc.k, p.sc.k, p.sc.w + (size_t)pr * p.sc.S,
                                      p.sc.mask + (size_t)pr * p.sc.wprS, p.sc.S, PP, PN);
                     const unsigned ge = __ballot_sync(FULL, emit && W >= p.sc.z_obs[pr]);
                     if (lane == 0 && ge) atomicAdd(&p.sc.n_ge[pr], (unsigned long long)__popc(ge));
                     if (emit && p.sc.null_scores) p.sc.null_scores[(size_t)pr * p.sc.n_total + (null_id - p.null_lo)] = W;
                 }
-                fence_proxy_async_smem();                   // the partials lived in the staging buffers the next bulk loads overwrite
-                __syncwarp();
             }
         }
     }
@@ -270,10 +327,13 @@ void sdx_lanes_invalidate(sdx_ctx *c, bool matrix_changed) {
     c->ln_pool_valid = false;
 }
 
-static int ln_run_compact(sdx_ctx *c, const uint32_t *d_states, int n, uint8_t *d_out) {
+// d_states: n bit-packed states (stride 0: one state, n copies) -> groups of 32 (interleave) or compact states
+static int ln_run_compact(sdx_ctx *c, const uint32_t *d_states, size_t src_stride, int n, bool interleave, uint8_t *d_out) {
     const int64_t jobs = (int64_t)n * c->R;
-    SDX_CUDA(c, cudaMemsetAsync(d_out, 0, (size_t)n * (c->ln_gsb / LN_W), c->stream));
-    k_ln_compact<<<(unsigned)((jobs + 7) / 8), 256, 0, c->stream>>>(d_states, n, c->R, c->RS, c->wprL, c->d_ln_desc, c->ln_gsb / LN_W, d_out);
+    const size_t bytes = interleave ? (size_t)((n + 31) / 32) * c->ln_rows_bytes : (size_t)n * (c->ln_rows_bytes / LN_W);
+    SDX_CUDA(c, cudaMemsetAsync(d_out, 0, bytes, c->stream));
+    k_ln_compact<<<(unsigned)((jobs + 7) / 8), 256, 0, c->stream>>>(d_states, src_stride, n, c->R, c->RS, c->wprL, c->d_ln_desc,
+                                                                    interleave ? c->ln_rows_bytes : c->ln_rows_bytes / LN_W, interleave ? 1 : 0, d_out);
     c->timing.launches++; c->total_launches++;
     SDX_CUDA(c, cudaGetLastError());
     return SDX_OK;
@@ -292,46 +352,58 @@ static int ln_layout(sdx_ctx *c) {
     if (c->knobs.lane_ts > 0) ts = std::min(c->knobs.lane_ts, LN_TS_MAX);
     std::vector<uint2> desc((size_t)R);
     const LnLayout lay = ln_build_layout(size.data(), R, nw, ts, desc.data());
-    const int slot = lay.slot_bytes, n_bits = lay.n_bits;
-    const uint32_t gsb = lay.gsb;
-    if (slot > 16 * 1024) return SDX_OK;                 // rows too long to stage six of them per warp: k_trade runs this matrix
-    c->ln_ts = ts; c->ln_slot_bytes = slot; c->ln_has_bits = n_bits > 0; c->ln_gsb = gsb;
+    if (lay.x_bytes > 16 * 1024) return SDX_OK;          // rows too long for the per-warp buffer of a bit-packed row: k_trade runs this matrix
+    c->ln_ts = lay.ts; c->ln_slot_bytes = lay.slot_bytes; c->ln_has_bits = lay.n_bits > 0; c->ln_gsb = lay.gsb;
+    c->ln_rows_bytes = lay.rows_bytes; c->ln_c_off = lay.c_off; c->ln_pp_off = lay.pp_off; c->ln_pf_bytes = lay.pf_bytes; c->ln_x_bytes = lay.x_bytes;
     if (c->d_ln_desc) cudaFree(c->d_ln_desc);
     if (c->d_ln_obs) cudaFree(c->d_ln_obs);
     c->d_ln_desc = nullptr; c->d_ln_obs = nullptr;
     SDX_CUDA(c, cudaMalloc(&c->d_ln_desc, sizeof(uint2) * R));
-    SDX_CUDA(c, cudaMalloc(&c->d_ln_obs, gsb / LN_W));
+    SDX_CUDA(c, cudaMalloc(&c->d_ln_obs, lay.rows_bytes));
     SDX_CUDA(c, cudaMemcpyAsync(c->d_ln_desc, desc.data(), sizeof(uint2) * R, cudaMemcpyHostToDevice, c->stream));
     SDX_CUDA(c, cudaStreamSynchronize(c->stream));       // desc goes out of scope
-    SDX_TRY(ln_run_compact(c, c->d_trade_obs, 1, c->d_ln_obs));
+    SDX_TRY(ln_run_compact(c, c->d_trade_obs, 0, LN_W, true, c->d_ln_obs));
     c->ln_state = 1;
     return SDX_OK;
 }
 
-struct LnGeom { int wpc, desc_bytes, warp_bytes, x_words; size_t smem; bool mreg; };
+struct LnGeom { int wpc, grid, desc_bytes, warp_bytes; size_t smem; bool m64; };
 
-static bool ln_geometry(sdx_ctx *c, bool scoring, LnGeom *g) {
-    const int nw = c->wprL, slot = c->ln_slot_bytes;
-    g->mreg = 2 * c->ln_ts <= 32;                        // the chosen ranks of a list x list trade fit one register
-    g->x_words = c->ln_has_bits ? nw : 0;
-    const int c_words = std::max(c->ln_has_bits ? nw + 2 : 0, g->mreg ? 0 : ((2 * c->ln_ts) >> 5) + 2);
-    int wb = 6 * slot + (g->x_words + c_words) * 128 + 16;
-    if (scoring && wb < 2 * 32 * 32 * 8 + 16) wb = 2 * 32 * 32 * 8 + 16;      // the scorer's 64 partials per lane alias the staging buffers
+// Warps per CTA and grid for n_groups groups: as many resident warps per SM as shared memory and registers allow, but
+// never fewer CTAs than SMs when the groups are few (one warp runs one group at a time).
+static bool ln_geometry(sdx_ctx *c, int64_t n_groups, LnGeom *g) {
+    g->m64 = 2 * c->ln_ts > 32;                          // the chosen ranks of a list x list trade need a register pair
+    int wb = 6 * c->ln_slot_bytes + c->ln_x_bytes + c->ln_pf_bytes + 32;
     wb = ((wb + 127) / 128) * 128;
     g->warp_bytes = wb;
     g->desc_bytes = ((c->R * 8 + 127) / 128) * 128;
     const size_t budget = c->smem_optin > 2048 ? c->smem_optin - 1024 : 0;
-    // warps per CTA: the choice that keeps most warps resident per SM
-    int best = 0, best_w = 0;
-    for (int wpc = 1; wpc <= 8; wpc *= 2) {
+    const void *kern = g->m64 ? (const void *)k_trade_lanes<true> : (const void *)k_trade_lanes<false>;
+    static const int cand[] = {1, 2, 3, 4, 6, 8, 11, 12, 16, 20, 22, 24};
+    int best = 0, best_grid = 0;
+    double best_cost = 1e300;
+    int best_cap = 0;
+    for (int wpc : cand) {
+        if (c->knobs.lane_wpc > 0 && wpc != c->knobs.lane_wpc) continue;
         const size_t need = (size_t)g->desc_bytes + (size_t)wpc * wb;
-        if (need > budget) break;
-        const int per_sm = (int)std::min<size_t>((228 * 1024) / (need + 1024), 32) * wpc;
-        if (per_sm > best_w) { best_w = per_sm; best = wpc; }
+        if (need > budget || wpc * 32 > LN_MAX_THREADS) continue;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) { cudaGetLastError(); continue; }
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, wpc * 32, need) != cudaSuccess || nb < 1) { cudaGetLastError(); continue; }
+        const int cap = nb * wpc;                        // resident warps per SM
+        const int64_t ctas = (n_groups + wpc - 1) / wpc;
+        const int64_t slots = (int64_t)nb * c->sm_count;
+        // rounds a warp slot of the busiest SM runs one after the other
+        double cost;
+        if (ctas <= slots) cost = (double)((ctas + c->sm_count - 1) / c->sm_count) * wpc / (double)std::min<int64_t>(cap, 16);      // one wave: warps of the busiest SM, ~16 warps saturate the issue slots
+        else cost = (double)n_groups / ((double)cap * c->sm_count) + 1.0;
+        if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && cap > best_cap)) {
+            best_cost = cost; best = wpc; best_cap = cap;
+            best_grid = (int)std::min<int64_t>(ctas, slots);
+        }
     }
-    if (c->knobs.lane_wpc > 0 && (size_t)g->desc_bytes + (size_t)c->knobs.lane_wpc * wb <= budget && c->knobs.lane_wpc <= 8) best = c->knobs.lane_wpc;
     if (best == 0) return false;
-    g->wpc = best;
+    g->wpc = best; g->grid = best_grid;
     g->smem = (size_t)g->desc_bytes + (size_t)best * wb;
     return true;
 }
@@ -344,7 +416,7 @@ bool sdx_lanes_applicable(sdx_ctx *c, int64_t n_chains, int64_t T, bool fused_sc
     const int64_t min_chains = c->knobs.lane_min_chains > 0 ? c->knobs.lane_min_chains : 64;
     if (n_chains < min_chains) return false;                     // a handful of chains is latency bound: k_trade runs them level-parallel
     LnGeom g;
-    return ln_geometry(c, fused_scoring, &g);
+    return ln_geometry(c, (n_chains + LN_W - 1) / LN_W, &g);
 }
 
 // sdx_curveball.cu
@@ -357,23 +429,24 @@ int sdx_run_nulls_lanes(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nul
     int rc;
     // start states: the burn-in pool (built by k_trade, converted once) or the observed matrix
     const uint8_t *src = c->d_ln_obs;
-    int n_src = 1;
+    int n_src = 1, src_groups = 1;
     if (c->burn > 0) {
         const bool was_valid = c->pool_valid && c->pool_seed == seed && c->pool_T == T;
         if ((rc = sdx_ensure_pool(c, seed, T))) return rc;
+        const bool groups = c->pool_size % LN_W == 0;
         if (!was_valid || !c->ln_pool_valid) {
-            const size_t bytes = (size_t)c->pool_size * (c->ln_gsb / LN_W);
+            const size_t bytes = groups ? (size_t)(c->pool_size / LN_W) * c->ln_rows_bytes : (size_t)c->pool_size * (c->ln_rows_bytes / LN_W);
             SDX_TRY(sdx_reserve(c, c->d_ln_pool, c->cap_ln_pool, bytes));
-            SDX_TRY(ln_run_compact(c, c->d_pool, c->pool_size, c->d_ln_pool));
-            c->ln_pool_valid = true;
+            SDX_TRY(ln_run_compact(c, c->d_pool, (size_t)c->R * c->RS, c->pool_size, groups, c->d_ln_pool));
+            c->ln_pool_valid = true; c->ln_pool_groups = groups;
         }
-        src = c->d_ln_pool; n_src = c->pool_size;
+        src = c->d_ln_pool;
+        src_groups = c->ln_pool_groups ? 1 : 0;
+        n_src = src_groups ? c->pool_size / LN_W : c->pool_size;
     }
     LaunchTimer timer(c);
     ScoreArgs sc{};
     if (hs && (rc = sdx_score_setup(c, hs, n_nulls, false, &sc, &timer))) return rc;
-    LnGeom geo;
-    if (!ln_geometry(c, hs != nullptr, &geo)) return sdx_fail(c, SDX_ERR_UNSUPPORTED, "lane kernel: shared memory layout does not fit");
 
     float trade_ms = 0;
     int n_launch = 0;
@@ -404,10 +477,12 @@ int sdx_run_nulls_lanes(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nul
         SDX_TRY(sdx_scratch(c, SL_LN_STATE, (size_t)groups_per_launch * c->ln_gsb, &p_states));
         const int seg_cap = (int)std::min<int64_t>(chain_len, 64);
         const int64_t n_segs = (chain_len + seg_cap - 1) / seg_cap;
-        auto kern = geo.mreg ? k_trade_lanes<true> : k_trade_lanes<false>;
-        SDX_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
         for (int64_t gb = 0; gb < n_groups; gb += groups_per_launch) {
             const int64_t ng = std::min(groups_per_launch, n_groups - gb);
+            LnGeom geo;
+            if (!ln_geometry(c, ng, &geo)) return sdx_fail(c, SDX_ERR_UNSUPPORTED, "lane kernel: shared memory layout does not fit");
+            auto kern = geo.m64 ? k_trade_lanes<true> : k_trade_lanes<false>;
+            SDX_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
             // nulls of this batch of groups: chains are contiguous in the null index
             const uint64_t b_lo = std::max<uint64_t>(null0, (g_first + (uint64_t)gb) * LN_W * (uint64_t)chain_len);
             const uint64_t b_hi = std::min<uint64_t>(null_hi, (g_first + (uint64_t)(gb + ng)) * LN_W * (uint64_t)chain_len);
@@ -421,17 +496,18 @@ int sdx_run_nulls_lanes(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nul
                 LaneArgs a{};
                 a.keys = make_keys(seed);
                 a.desc = c->d_ln_desc; a.R = R; a.T = (int)T; a.wprL = nw;
-                a.slot_bytes = c->ln_slot_bytes; a.desc_bytes = geo.desc_bytes; a.warp_bytes = geo.warp_bytes; a.scratch_x_words = geo.x_words;
-                a.gsb = c->ln_gsb; a.states = (uint8_t *)p_states;
+                a.slot_bytes = c->ln_slot_bytes; a.desc_bytes = geo.desc_bytes; a.warp_bytes = geo.warp_bytes; a.x_bytes = c->ln_x_bytes;
+                a.gsb = c->ln_gsb; a.rows_bytes = c->ln_rows_bytes; a.c_off = c->ln_c_off; a.pp_off = c->ln_pp_off;
+                a.states = (uint8_t *)p_states;
                 a.chain0 = (g_first + (uint64_t)gb) * LN_W; a.chain_len = chain_len;
                 a.seg_off = sg * seg_cap;
                 a.seg_len = (int)std::min<int64_t>(seg_cap, chain_len - sg * seg_cap);
                 a.null_lo = null0; a.null_hi = null_hi; a.n_groups = (int)ng;
-                a.src_states = src; a.n_src = n_src;
+                a.src_states = src; a.n_src = n_src; a.src_groups = src_groups;
                 a.out_rows = d_out ? d_out - (size_t)(b_lo - null0) * out_per : nullptr;      // the kernel indexes by null_id - null_lo
                 a.applied = (unsigned long long *)p_app; a.sc = sc;
                 cudaEventRecord(c->ev[3], c->stream);
-                kern<<<(unsigned)((ng + geo.wpc - 1) / geo.wpc), geo.wpc * 32, geo.smem, c->stream>>>(a);
+                kern<<<(unsigned)geo.grid, geo.wpc * 32, geo.smem, c->stream>>>(a);
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return sdx_fail(c, SDX_ERR_CUDA, std::string("lane kernel launch failed: ") + cudaGetErrorString(e));
                 cudaEventRecord(c->ev[4], c->stream);

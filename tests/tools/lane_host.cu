@@ -40,19 +40,21 @@ extern "C" int lane_host_run(const uint32_t *start, int n_start, int R, int nw, 
     std::vector<uint2> desc((size_t)R);
     if (ts <= 0) ts = ln_default_ts(nw);
     const LnLayout lay = ln_build_layout(size.data(), R, nw, ts, desc.data());
-    const bool mreg = 2 * ts <= 32;
+    const bool m64 = 2 * lay.ts > 32;
     const PhiloxKeys keys = make_keys(seed);
-    std::vector<uint8_t> state(lay.gsb, 0), compact(lay.gsb / LN_W, 0);
+    std::vector<uint8_t> state(lay.gsb, 0), compact(lay.rows_bytes / LN_W, 0);
     for (int lane = 0; lane < LN_W; ++lane) {
         const uint64_t ch = chain0 + (uint64_t)lane;
         std::fill(compact.begin(), compact.end(), 0);
         compact_state(start + (size_t)(ch % (uint64_t)n_start) * R * nw, R, nw, desc.data(), compact.data());
         ln_load_state(state.data(), lane, desc.data(), R, nw, compact.data());
     }
-    const size_t SLOT = (size_t)lay.slot_bytes;
-    std::vector<uint8_t> inA(SLOT + 64, 0xAB), inB(SLOT + 64, 0xAB), outA(SLOT + 64, 0xCD), outB(SLOT + 64, 0xCD);
-    std::vector<uint32_t> X((size_t)(nw + 1) * LN_W), C((size_t)(nw + 8) * LN_W);
-    std::vector<double> PP(32 * LN_W), PN(32 * LN_W);
+    // staging buffers exactly as the kernel sizes them, followed by canaries: an overrun fails the run instead of passing silently
+    const size_t SLOT = (size_t)lay.slot_bytes, PFB = (size_t)lay.pf_bytes, XB = (size_t)lay.x_bytes;
+    std::vector<uint8_t> inA(SLOT + 64), inB(SLOT + 64), outA(SLOT + 64), outB(SLOT + 64), pf(PFB + 64), xb(XB + 64);
+    auto guard_ok = [&](const std::vector<uint8_t> &v, size_t n, uint8_t fill) { for (size_t q = n; q < v.size(); ++q) if (v[q] != fill) return false; return true; };
+    uint32_t *C = reinterpret_cast<uint32_t *>(state.data() + lay.c_off);
+    double *PP = reinterpret_cast<double *>(state.data() + lay.pp_off), *PN = PP + 32 * LN_W;
     std::vector<uint32_t> ent((size_t)T + 1);
     for (int j = 0; j < rounds; ++j) {
         const uint64_t round = (uint64_t)round0 + (uint64_t)j;
@@ -70,32 +72,49 @@ extern "C" int lane_host_run(const uint32_t *start, int n_start, int R, int nw, 
         for (int64_t t = 0; t < T; ++t) {
             const uint32_t a = ent[t] & 0x3fffu, b = (ent[t] >> 14) & 0x3fffu;
             const uint2 dA = desc[a], dB = desc[b];
-            // "bulk loads": the two rows, exactly their bytes
-            memset(inA.data(), 0xAB, inA.size()); memset(inB.data(), 0xAB, inB.size());
-            memcpy(inA.data(), state.data() + dA.x, ln_row_bytes(dA, nw));
-            memcpy(inB.data(), state.data() + dB.x, ln_row_bytes(dB, nw));
-            std::vector<LnDeal> deals(LN_W);
+            const bool ba = ln_is_bits(dA), bb = ln_is_bits(dB);
+            // "bulk loads": the lists, exactly their bytes; the bit-packed row of a bit-packed x list trade -> X
+            memset(inA.data(), 0xAB, inA.size()); memset(inB.data(), 0xAB, inB.size()); memset(pf.data(), 0xEF, pf.size()); memset(xb.data(), 0x77, xb.size());
+            if (ba != bb) memcpy(xb.data(), state.data() + (ba ? dA.x : dB.x), (size_t)nw * 128);
+            memcpy(inA.data(), state.data() + dA.x, ln_stage_bytes(dA));
+            memcpy(inB.data(), state.data() + dB.x, ln_stage_bytes(dB));
+            memset(outA.data(), 0xCD, outA.size()); memset(outB.data(), 0xCD, outB.size());
+            std::vector<LnTrade<false>> tr32(LN_W);
+            std::vector<LnTrade<true>> tr64(LN_W);
             uint32_t kmax = 0;
-            // phase 1 of all lanes; a list row goes through the lane's scratch, so X / C must be per lane: they are (stride 32)
-            // but phase 2 of a bit-packed trade needs the scratch of phase 1 -> run both phases lane by lane after the vote
-            std::vector<uint32_t> kk(LN_W);
+            auto ptrs = [&](int lane, uint16_t *&pinA, uint16_t *&pinB, uint16_t *&poA, uint16_t *&poB, uint32_t *&gA, uint32_t *&gB, uint16_t *&PF,
+                            uint16_t *&RK, uint16_t *&PK, uint32_t *&X) {
+                X = reinterpret_cast<uint32_t *>(xb.data()) + lane;
+                pinA = reinterpret_cast<uint16_t *>(inA.data()) + lane; pinB = reinterpret_cast<uint16_t *>(inB.data()) + lane;
+                poA = reinterpret_cast<uint16_t *>(outA.data()) + lane; poB = reinterpret_cast<uint16_t *>(outB.data()) + lane;
+                gA = reinterpret_cast<uint32_t *>(state.data() + dA.x) + lane; gB = reinterpret_cast<uint32_t *>(state.data() + dB.x) + lane;
+                PF = reinterpret_cast<uint16_t *>(pf.data()) + lane;
+                RK = ba ? pinA : pinB; PK = ba ? poA : poB;
+            };
+            // phase 1 of all lanes (reads only; scratch is per lane: stride 32), the vote, then phase 2 of all lanes
             for (int lane = 0; lane < LN_W; ++lane) {
                 const LnRng g{&keys, (chain0 + (uint64_t)lane) * (uint64_t)chain_len + round, (uint32_t)t};
+                uint16_t *pinA, *pinB, *poA, *poB, *PF, *RK, *PK; uint32_t *gA, *gB, *X;
+                ptrs(lane, pinA, pinB, poA, poB, gA, gB, PF, RK, PK, X);
                 uint32_t km = 0;
-                deals[lane] = mreg ? ln_trade_phase1<true>(dA, dB, inA.data(), inB.data(), X.data() + lane, C.data() + lane, nw, lane, g, km)
-                                   : ln_trade_phase1<false>(dA, dB, inA.data(), inB.data(), X.data() + lane, C.data() + lane, nw, lane, g, km);
+                if (m64) ln_trade_phase1<true>(tr64[lane], dA, dB, pinA, pinB, gA, gB, X, PF, RK, PK, C + lane, nw, g, km);
+                else ln_trade_phase1<false>(tr32[lane], dA, dB, pinA, pinB, gA, gB, X, PF, RK, PK, C + lane, nw, g, km);
                 if (km > kmax) kmax = km;
             }
             if (kmax != 0) {
-                memset(outA.data(), 0xCD, outA.size()); memset(outB.data(), 0xCD, outB.size());
                 for (int lane = 0; lane < LN_W; ++lane) {
-                    if (mreg) ln_trade_phase2<true>(dA, dB, inA.data(), inB.data(), outA.data(), outB.data(), X.data() + lane, C.data() + lane, nw, lane, deals[lane]);
-                    else ln_trade_phase2<false>(dA, dB, inA.data(), inB.data(), outA.data(), outB.data(), X.data() + lane, C.data() + lane, nw, lane, deals[lane]);
-                    ap[lane] += deals[lane].go ? 1 : 0;
+                    uint16_t *pinA, *pinB, *poA, *poB, *PF, *RK, *PK; uint32_t *gA, *gB, *X;
+                    ptrs(lane, pinA, pinB, poA, poB, gA, gB, PF, RK, PK, X);
+                    if (m64) ln_trade_phase2<true>(tr64[lane], dA, dB, pinA, pinB, poA, poB, gA, gB, X, PF, RK, PK, C + lane, nw, kmax);
+                    else ln_trade_phase2<false>(tr32[lane], dA, dB, pinA, pinB, poA, poB, gA, gB, X, PF, RK, PK, C + lane, nw, kmax);
+                    ap[lane] += (m64 ? tr64[lane].deal.go : tr32[lane].deal.go) ? 1 : 0;
                 }
-                // "bulk stores"
-                memcpy(state.data() + dA.x, outA.data(), ln_row_bytes(dA, nw));
-                memcpy(state.data() + dB.x, outB.data(), ln_row_bytes(dB, nw));
+                if (!guard_ok(inA, SLOT, 0xAB) || !guard_ok(inB, SLOT, 0xAB) || !guard_ok(outA, SLOT, 0xCD) || !guard_ok(outB, SLOT, 0xCD) ||
+                    !guard_ok(pf, PFB, 0xEF) || !guard_ok(xb, XB, 0x77)) return -3;   // staging / scratch overrun
+                // "bulk stores": the new lists, the updated bit-packed row
+                if (ba != bb) memcpy(state.data() + (ba ? dA.x : dB.x), xb.data(), (size_t)nw * 128);
+                if (!ba) memcpy(state.data() + dA.x, outA.data(), ln_stage_bytes(dA));
+                if (!bb) memcpy(state.data() + dB.x, outB.data(), ln_stage_bytes(dB));
             }
         }
         for (int lane = 0; lane < LN_W; ++lane) {
@@ -103,7 +122,7 @@ extern "C" int lane_host_run(const uint32_t *start, int n_start, int R, int nw, 
             memset(dst, 0, sizeof(uint32_t) * (size_t)R * nw);
             ln_emit_rows(state.data(), lane, desc.data(), R, nw, dst);
             if (applied) applied[(size_t)j * LN_W + lane] = ap[lane];
-            if (W) W[(size_t)j * LN_W + lane] = ln_score(state.data(), lane, desc.data(), nw, mod, k, w, mask, S, PP.data() + lane, PN.data() + lane);
+            if (W) W[(size_t)j * LN_W + lane] = ln_score(state.data(), lane, desc.data(), mod, k, w, mask, S, PP + lane, PN + lane);
         }
     }
     return 0;
@@ -115,5 +134,5 @@ extern "C" int lane_host_layout(const int *size, int R, int nw, int ts, uint32_t
     const LnLayout lay = ln_build_layout(size, R, nw, ts, desc.data());
     for (int r = 0; r < R; ++r) { desc_xy[2 * r] = desc[r].x; desc_xy[2 * r + 1] = desc[r].y; }
     *slot_bytes = lay.slot_bytes; *gsb = lay.gsb; *n_bits = lay.n_bits;
-    return ts;
+    return lay.ts;
 }
