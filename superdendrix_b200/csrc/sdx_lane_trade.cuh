@@ -121,9 +121,31 @@ struct LnDeal {                  // what phase 1 of a trade hands to phase 2
 // common elements of two sorted lists (one merge walk)
 LN_HD uint32_t ln_ll_common(const uint16_t *A, int sa, const uint16_t *B, int sb) {
     const int steps = sa + sb;
-    const uint16_t *pa = A, *pb = B;
     uint32_t c = 0;
+#ifdef __CUDA_ARCH__
+    // the compiler turns the predicates of the C loop below into register arithmetic (~18 instructions per step); spelled
+    // out it is 10: two loads, four compares, one predicate AND, three predicated adds
+    uint32_t pa = (uint32_t)__cvta_generic_to_shared(A), pb = (uint32_t)__cvta_generic_to_shared(B);
 #pragma unroll 2
+    for (int s = 0; s < steps; ++s) {
+        asm volatile("{\n\t"
+                     ".reg .pred px, py, pA, pB, pC;\n\t"
+                     ".reg .b32 x, y;\n\t"
+                     "ld.shared.u16 x, [%1];\n\t"
+                     "ld.shared.u16 y, [%2];\n\t"
+                     "setp.ne.u32 px, x, 0xFFFF;\n\t"
+                     "setp.ne.u32 py, y, 0xFFFF;\n\t"
+                     "setp.le.and.u32 pA, x, y, px;\n\t"
+                     "setp.le.and.u32 pB, y, x, py;\n\t"
+                     "and.pred pC, pA, pB;\n\t"
+                     "@pC add.u32 %0, %0, 1;\n\t"
+                     "@pA add.u32 %1, %1, 64;\n\t"
+                     "@pB add.u32 %2, %2, 64;\n\t"
+                     "}"
+                     : "+r"(c), "+r"(pa), "+r"(pb) :: "memory");
+    }
+#else
+    const uint16_t *pa = A, *pb = B;
     for (int s = 0; s < steps; ++s) {
         const uint32_t x = *pa, y = *pb;
         const bool adva = x <= y && x != LN_SENT, advb = y <= x && y != LN_SENT;
@@ -131,6 +153,7 @@ LN_HD uint32_t ln_ll_common(const uint16_t *A, int sa, const uint16_t *B, int sb
         if (adva) pa += LN_W;
         if (advb) pb += LN_W;
     }
+#endif
     return c;
 }
 
@@ -139,7 +162,6 @@ LN_HD void ln_ll_phase2(const uint16_t *A, int sa, const uint16_t *B, int sb, ui
     const int steps = sa + sb;
     const uint16_t *pa = A, *pb = B;
     uint16_t *oa = OA, *ob = OB;
-#pragma unroll 2
     for (int s = 0; s < steps; ++s) {
         const uint32_t x = *pa, y = *pb;
         const bool adva = x <= y && x != LN_SENT, advb = y <= x && y != LN_SENT;      // neither: both lists are at their sentinels
@@ -153,6 +175,48 @@ LN_HD void ln_ll_phase2(const uint16_t *A, int sa, const uint16_t *B, int sb, ui
         if (advb) pb += LN_W;
     }
 }
+
+#ifdef __CUDA_ARCH__
+// the same walk with the predicates spelled out (the compiler's version of the loop above runs ~38 instructions per step)
+template <>
+__device__ __forceinline__ void ln_ll_phase2<false>(const uint16_t *A, int sa, const uint16_t *B, int sb, uint16_t *OA, uint16_t *OB,
+                                                    LnMask<false> toA) {
+    const int steps = sa + sb;
+    uint32_t pa = (uint32_t)__cvta_generic_to_shared(A), pb = (uint32_t)__cvta_generic_to_shared(B);
+    uint32_t oa = (uint32_t)__cvta_generic_to_shared(OA), ob = (uint32_t)__cvta_generic_to_shared(OB);
+    uint32_t m = toA.v;
+#pragma unroll 2
+    for (int s = 0; s < steps; ++s) {
+        asm volatile("{\n\t"
+                     ".reg .pred px, py, pA, pB, pS, pC, pbit, pTA, pTB, t1, t2;\n\t"
+                     ".reg .b32 x, y, e, bit;\n\t"
+                     "ld.shared.u16 x, [%0];\n\t"
+                     "ld.shared.u16 y, [%1];\n\t"
+                     "setp.ne.u32 px, x, 0xFFFF;\n\t"
+                     "setp.ne.u32 py, y, 0xFFFF;\n\t"
+                     "setp.le.and.u32 pA, x, y, px;\n\t"
+                     "setp.le.and.u32 pB, y, x, py;\n\t"
+                     "min.u32 e, x, y;\n\t"
+                     "st.shared.u16 [%2], e;\n\t"
+                     "st.shared.u16 [%3], e;\n\t"
+                     "and.b32 bit, %4, 1;\n\t"
+                     "setp.ne.u32 pbit, bit, 0;\n\t"
+                     "xor.pred pS, pA, pB;\n\t"
+                     "and.pred pC, pA, pB;\n\t"
+                     "and.pred t1, pS, pbit;\n\t"
+                     "and.pred t2, pS, !pbit;\n\t"
+                     "or.pred pTA, pC, t1;\n\t"
+                     "or.pred pTB, pC, t2;\n\t"
+                     "@pS shr.u32 %4, %4, 1;\n\t"
+                     "@pTA add.u32 %2, %2, 64;\n\t"
+                     "@pTB add.u32 %3, %3, 64;\n\t"
+                     "@pA add.u32 %0, %0, 64;\n\t"
+                     "@pB add.u32 %1, %1, 64;\n\t"
+                     "}"
+                     : "+r"(pa), "+r"(pb), "+r"(oa), "+r"(ob), "+r"(m) :: "memory");
+    }
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------
 // bit-packed x bit-packed (nw words each, stride 32, IN PLACE).  Phase 1: |a\b|, |b\a| and the picks as a rank mask in
@@ -211,13 +275,12 @@ LN_HD void ln_bb_phase2(uint32_t *A, uint32_t *B, int nw, const uint32_t *C, con
 // symmetric-difference elements, chosen by rank (Floyd, as everywhere).  Nothing is converted: the list's entries are
 // tested against the bits, a picked rank is mapped to its element by a select on the bits, and only the <= 2k elements
 // that change rows are toggled in D.
-//   phase 1 (reads only): PF4[q] = elements of d below word 4q ((nw + 3) / 4 + 1 u16), per list entry RK[i] = its rank
-//                         in the symmetric difference (own entries) or the number of d\l elements below it (common
-//                         entries), the picked ranks PK[0 .. k)
+//   phase 1 (reads only): PF4[q] = elements of d below word 4q ((nw + 3) / 4 + 1 u16), per list entry RK[i] = its key
+//                         (see ln_bl_prepare), the picked ranks PK[0 .. k) in ASCENDING order (insertion as they are drawn)
 //   phase 2: resolves every pick against the ORIGINAL row d (a pick that is one of the list's own entries keeps it
-//            there; any other is the q-th element of d\l, found by a search in PF4 and a select in the word), then
-//            toggles the <= 2k bits of D and writes the new sorted list OL by counting, for every element, the
-//            elements below it.
+//            there; any other is the y-th element of d, found by a search in PF4 and a select in the word), then
+//            toggles the <= 2k bits of D and merges the entries that stay with the elements that arrive (both ascending)
+//            into the new sorted list OL.
 // All loop bounds (nw, sl, kmax) are warp-uniform.
 // ---------------------------------------------------------------------------------------------------------------
 LN_HD uint32_t ln_bl_prepare(const uint32_t *D, int nw, const uint16_t *Lst, int sl, uint16_t *PF4, uint16_t *RK, uint32_t &cmn_out) {
@@ -245,8 +308,10 @@ LN_HD uint32_t ln_bl_prepare(const uint32_t *D, int nw, const uint16_t *Lst, int
             const uint32_t ww = (w & ~3u) + (uint32_t)v;
             if (ww < w) below += LN_POPC(D[ww * LN_W]);
         }
-        // the c common entries so far are all below e: below - c elements of d\l, i - c elements of l\d lie below it
-        RK[i * LN_W] = (uint16_t)(below - c + (bit ? 0u : (uint32_t)i - c));
+        // key = elements of d\l below e + the list's own (not common) entries below e; the c common entries so far are all
+        // below e.  For an own entry the key is its rank in the symmetric difference; a d\l element of rank r lies above a
+        // common entry iff key <= r, above an own entry iff key < r.  Keys never decrease along the list.
+        RK[i * LN_W] = (uint16_t)(below + (uint32_t)i - 2u * c);
         cmn |= bit << i;
         c += bit;
     }
@@ -281,23 +346,19 @@ LN_HD void ln_bl_phase2(uint32_t *D, int nw, const uint16_t *Lst, int sl, uint16
         uint32_t el = LN_SENT;
         if (j < k) {
             const uint32_t r = PK[j * LN_W];
-            uint32_t cntb = 0, own = 0;
-#pragma unroll 1
+            uint32_t nlt = 0, nle = 0;                  // entries with key < r, key <= r: prefixes of the list
+#pragma unroll 2
             for (int i = 0; i < sl; ++i) {
                 const uint32_t v = RK[i * LN_W];
-                const bool mine = !((cmn >> i) & 1u);
-                if (mine && v < r) ++cntb;
-                if (mine && v == r) own |= 1u << i;
+                if (v < r) ++nlt;
+                if (v <= r) ++nle;
             }
+            const uint32_t mlt = nlt >= 32 ? 0xffffffffu : (1u << nlt) - 1u, mle = nle >= 32 ? 0xffffffffu : (1u << nle) - 1u;
+            const uint32_t own = ~cmn & (mle ^ mlt);    // the own entry of rank r, if there is one
             keep |= own;
             if (!own) {
-                const uint32_t q = r - cntb;            // the q-th element of d \ l ...
-                uint32_t y = q;                         // ... is the y-th element of d: the common entries with <= q elements of d\l below them precede it
-#pragma unroll 1
-                for (int i = 0; i < sl; ++i) {
-                    const uint32_t v = RK[i * LN_W];
-                    if (((cmn >> i) & 1u) && v <= q) ++y;
-                }
+                // the y-th element of d: rank r minus the own entries below it plus the common entries below it
+                const uint32_t y = r - (uint32_t)LN_POPC(~cmn & mlt) + (uint32_t)LN_POPC(cmn & mle);
                 int lo = 0;                             // largest block of 4 words with PF4[lo] <= y
 #pragma unroll 1
                 for (int step = top >> 1; step >= 1; step >>= 1) {
@@ -314,7 +375,7 @@ LN_HD void ln_bl_phase2(uint32_t *D, int nw, const uint16_t *Lst, int sl, uint16
                 el = w * 32u + ln_select32(D[w * LN_W], y - base);
             }
         }
-        PK[j * LN_W] = (uint16_t)el;                     // the element that moves from d to the list, or LN_SENT
+        PK[j * LN_W] = (uint16_t)el;                     // the element that moves from d to the list (ascending in j), or LN_SENT
     }
     // the list's own entries that were not picked move to d; the picked elements of d\l leave it
     const uint32_t stay = cmn | keep;
@@ -329,28 +390,22 @@ LN_HD void ln_bl_phase2(uint32_t *D, int nw, const uint16_t *Lst, int sl, uint16
         const uint32_t el = PK[j * LN_W];
         if (el != LN_SENT) D[(el >> 5) * LN_W] &= ~(1u << (el & 31u));
     }
-    // the new list, sorted: position of an element = number of elements below it
-    uint32_t nst = 0;
+    // the new list: the entries that stay and the elements that arrive, both ascending, merged.  Every step consumes
+    // one list entry or one pick (sl + kmax steps); an entry that left and a pick that was an own entry emit nothing.
+    // (x == e never happens for two elements: an arriving element was not in the list.)
+    const uint16_t *pl = Lst, *pp = PK;
+    uint16_t *ol = OL;
+    uint32_t st = stay, il = 0, ip = 0;
+    const uint32_t steps = (uint32_t)sl + kmax;
 #pragma unroll 1
-    for (int i = 0; i < sl; ++i)
-        if ((stay >> i) & 1u) {
-            const uint32_t e = Lst[i * LN_W];
-            uint32_t pos = nst++;
-#pragma unroll 1
-            for (uint32_t j = 0; j < kmax; ++j) pos += (uint32_t)PK[j * LN_W] < e ? 1u : 0u;
-            OL[pos * LN_W] = (uint16_t)e;
-        }
-#pragma unroll 1
-    for (uint32_t j = 0; j < kmax; ++j) {
-        const uint32_t x = PK[j * LN_W];
-        if (x != LN_SENT) {
-            uint32_t pos = 0;
-#pragma unroll 1
-            for (int i = 0; i < sl; ++i) pos += (((stay >> i) & 1u) && (uint32_t)Lst[i * LN_W] < x) ? 1u : 0u;
-#pragma unroll 1
-            for (uint32_t j2 = 0; j2 < kmax; ++j2) pos += (uint32_t)PK[j2 * LN_W] < x ? 1u : 0u;
-            OL[pos * LN_W] = (uint16_t)x;
-        }
+    for (uint32_t s = 0; s < steps; ++s) {
+        const uint32_t e = il < (uint32_t)sl ? (uint32_t)*pl : 0x10000u;         // past the end: larger than every element
+        const uint32_t x = ip < kmax ? (uint32_t)*pp : 0x10000u;
+        const bool take_l = e < x && x != LN_SENT;                               // a pick that was an own entry (LN_SENT) is skipped at once
+        const bool emit = take_l ? (st & 1u) != 0 : (x < LN_SENT);
+        *ol = (uint16_t)(take_l ? e : x);
+        if (emit) ol += LN_W;
+        if (take_l) { pl += LN_W; ++il; st >>= 1; } else { pp += LN_W; ++ip; }
     }
 }
 
@@ -421,11 +476,19 @@ LN_HD void ln_trade_phase1(LnTrade<M64> &tr, uint2 dA, uint2 dB, uint16_t *inA, 
                     if (cm.test(r)) r = m - 1;
                     cm.set(r);
                 } else if (kind == 1) {
+                    // PK[0 .. i) ascending: position of r, or the end for the replacement m - 1 of a rank drawn before
+                    uint32_t pos = 0;
                     bool dup = false;
 #pragma unroll 1
-                    for (uint32_t j = 0; j < i; ++j) dup = dup || PK[j * LN_W] == r;
-                    if (dup) r = m - 1;
-                    PK[i * LN_W] = (uint16_t)r;
+                    for (uint32_t j = 0; j < i; ++j) {
+                        const uint32_t v = PK[j * LN_W];
+                        if (v < r) ++pos;
+                        dup = dup || v == r;
+                    }
+                    if (dup) { r = m - 1; pos = i; }
+#pragma unroll 1
+                    for (uint32_t j = i; j > pos; --j) PK[j * LN_W] = PK[(j - 1) * LN_W];
+                    PK[pos * LN_W] = (uint16_t)r;
                 } else {
                     uint32_t w = C[(r >> 5) * LN_W];
                     if ((w >> (r & 31)) & 1u) { r = m - 1; w = C[(r >> 5) * LN_W]; }

@@ -110,7 +110,8 @@ extern "C" int lane_host_run(const uint32_t *start, int n_start, int R, int nw, 
                     ap[lane] += (m64 ? tr64[lane].deal.go : tr32[lane].deal.go) ? 1 : 0;
                 }
                 if (!guard_ok(inA, SLOT, 0xAB) || !guard_ok(inB, SLOT, 0xAB) || !guard_ok(outA, SLOT, 0xCD) || !guard_ok(outB, SLOT, 0xCD) ||
-                    !guard_ok(pf, PFB, 0xEF) || !guard_ok(xb, XB, 0x77)) return -3;   // staging / scratch overrun
+                    !guard_ok(pf, PFB, 0xEF) || !guard_ok(xb, XB, 0x77))
+                    return -3 - (!guard_ok(inA, SLOT, 0xAB) ? 10 : 0) - (!guard_ok(inB, SLOT, 0xAB) ? 20 : 0) - (!guard_ok(outA, SLOT, 0xCD) ? 40 : 0) - (!guard_ok(outB, SLOT, 0xCD) ? 80 : 0) - (!guard_ok(pf, PFB, 0xEF) ? 160 : 0) - (!guard_ok(xb, XB, 0x77) ? 320 : 0);   // staging / scratch overrun
                 // "bulk stores": the new lists, the updated bit-packed row
                 if (ba != bb) memcpy(state.data() + (ba ? dA.x : dB.x), xb.data(), (size_t)nw * 128);
                 if (!ba) memcpy(state.data() + dA.x, outA.data(), ln_stage_bytes(dA));
