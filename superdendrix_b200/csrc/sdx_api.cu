@@ -66,6 +66,7 @@ extern "C" int sdx_create(int device, sdx_ctx **out) {
         c->knobs.lane_ts = (int)geti("SDX_LANE_TS", 0);
         c->knobs.lane_wpc = (int)geti("SDX_LANE_WPC", 0);
         c->knobs.lane_min_chains = (int)geti("SDX_LANE_MIN_CHAINS", 0);
+        c->knobs.lane_debug = (int)geti("SDX_LANE_DEBUG", 0);
     }
     *out = c;
     return SDX_OK;
@@ -82,7 +83,7 @@ static void free_matrix(sdx_ctx *c) {
     c->d_feat = c->d_samp = c->d_trade_obs = nullptr;
     c->d_rowsize = nullptr;
     c->d_ln_desc = nullptr; c->d_ln_obs = nullptr; c->d_ln_pool = nullptr; c->cap_ln_pool = 0;
-    c->ln_state = 0; c->ln_pool_valid = false;
+    c->ln_state = 0; c->ln_geo_valid = false; c->ln_pool_valid = false;
     if (c->d_pool) cudaFree(c->d_pool);
     c->d_pool = nullptr;
     c->pool_valid = false;
@@ -93,7 +94,7 @@ static void free_matrix(sdx_ctx *c) {
 
 // a new matrix invalidates everything derived from the old one; the buffers themselves are kept and reused
 static void invalidate_matrix(sdx_ctx *c) {
-    c->ln_state = 0;                  // the lane layout (row kinds and offsets) is rebuilt on first use
+    c->ln_state = 0; c->ln_geo_valid = false;                  // the lane layout (row kinds and offsets) is rebuilt on first use
     c->ln_pool_valid = false;
     c->pool_valid = false;
     c->top_K = 0;

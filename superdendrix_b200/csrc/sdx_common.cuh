@@ -55,6 +55,9 @@ struct sdx_ctx {
     uint8_t *d_ln_obs = nullptr;          // the observed matrix as the rows of one group (32 copies, lanes interleaved)
     uint8_t *d_ln_pool = nullptr;         // the burn-in pool: pool_size / 32 groups (ln_pool_groups), else pool_size compact states
     bool ln_pool_groups = false;
+    alignas(8) unsigned char ln_geo[64] = {};   // cached launch geometry of the lane kernel (LnGeom) for ln_geo_groups groups
+    int64_t ln_geo_groups = -1;
+    bool ln_geo_valid = false;
     size_t cap_ln_pool = 0;
     bool ln_pool_valid = false;
     // how the PAIR stream is shared (sdx_set_pair_group): 1 = every null draws its own row pairs; 32 = the 32 chains
@@ -87,7 +90,7 @@ struct sdx_ctx {
         int trade_g = 0, trade_warps = 0, trade_lb = -1, plan_cap = 0, grid_cap = 0;
         long nulls_per_launch = 0, pad_smem = 0;
         int lanes = 1;                    // 0: never use the lane kernel (pair_group 32 then runs on k_trade)
-        int lane_ts = 0, lane_wpc = 0, lane_min_chains = 0;
+        int lane_ts = 0, lane_wpc = 0, lane_min_chains = 0, lane_debug = 0;
     } knobs;
 };
 

@@ -148,9 +148,12 @@ static __device__ __noinline__ uint32_t ln_make_entries(const PhiloxKeys *keys, 
 
 #define LN_FLAG_PREV 1u               // shares a row with the trade before it: loaded when its turn comes
 #define LN_FLAG_NEAR 6u               // shares a row with the second / third trade before it: wait for the stores in flight
-#define LN_MAX_THREADS 768
-template <bool M64>
-__global__ void __launch_bounds__(LN_MAX_THREADS, 1) k_trade_lanes(const __grid_constant__ LaneArgs p) {
+#define LN_MAX_THREADS 704
+// REGS: registers per thread.  80 keeps 22 warps (the groups of 100 000 nulls in ONE wave) resident per SM; 128 has no
+// spills and is what a launch with fewer groups than that runs (registers are allocated in units of 512 per warp, so 88
+// would already drop to 20 warps).
+template <bool M64, int REGS>
+__global__ void __maxnreg__(REGS) k_trade_lanes(const __grid_constant__ LaneArgs p) {
     extern __shared__ __align__(128) uint8_t ln_smem[];
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, WPC = blockDim.x >> 5;
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(LN_MAX_THREADS, 1) k_trade_lanes(const __grid_
 // host side
 // ---------------------------------------------------------------------------
 void sdx_lanes_invalidate(sdx_ctx *c, bool matrix_changed) {
-    if (matrix_changed) c->ln_state = 0;
+    if (matrix_changed) { c->ln_state = 0; c->ln_geo_valid = false; }
     c->ln_pool_valid = false;
 }
 
@@ -367,44 +370,57 @@ static int ln_layout(sdx_ctx *c) {
     return SDX_OK;
 }
 
-struct LnGeom { int wpc, grid, desc_bytes, warp_bytes; size_t smem; bool m64; };
+struct LnGeom { int wpc, grid, desc_bytes, warp_bytes; size_t smem; bool m64; const void *kern; };
+
+static const void *ln_kernel(bool m64, bool wide) {
+    if (m64) return wide ? (const void *)k_trade_lanes<true, 128> : (const void *)k_trade_lanes<true, 80>;
+    return wide ? (const void *)k_trade_lanes<false, 128> : (const void *)k_trade_lanes<false, 80>;
+}
 
 // Warps per CTA and grid for n_groups groups: as many resident warps per SM as shared memory and registers allow, but
 // never fewer CTAs than SMs when the groups are few (one warp runs one group at a time).
 static bool ln_geometry(sdx_ctx *c, int64_t n_groups, LnGeom *g) {
+    if (c->ln_geo_groups == n_groups && c->ln_geo_valid) { *g = *reinterpret_cast<const LnGeom *>(c->ln_geo); return true; }
     g->m64 = 2 * c->ln_ts > 32;                          // the chosen ranks of a list x list trade need a register pair
     int wb = 6 * c->ln_slot_bytes + c->ln_x_bytes + c->ln_pf_bytes + 32;
     wb = ((wb + 127) / 128) * 128;
     g->warp_bytes = wb;
     g->desc_bytes = ((c->R * 8 + 127) / 128) * 128;
     const size_t budget = c->smem_optin > 2048 ? c->smem_optin - 1024 : 0;
-    const void *kern = g->m64 ? (const void *)k_trade_lanes<true> : (const void *)k_trade_lanes<false>;
-    static const int cand[] = {1, 2, 3, 4, 6, 8, 11, 12, 16, 20, 22, 24};
-    int best = 0, best_grid = 0;
+    static const int cand[] = {1, 2, 3, 4, 6, 8, 11, 12, 16, 20, 22};
+    int best = 0, best_grid = 0, best_cap = 0;
     double best_cost = 1e300;
-    int best_cap = 0;
-    for (int wpc : cand) {
-        if (c->knobs.lane_wpc > 0 && wpc != c->knobs.lane_wpc) continue;
-        const size_t need = (size_t)g->desc_bytes + (size_t)wpc * wb;
-        if (need > budget || wpc * 32 > LN_MAX_THREADS) continue;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) { cudaGetLastError(); continue; }
-        int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, wpc * 32, need) != cudaSuccess || nb < 1) { cudaGetLastError(); continue; }
-        const int cap = nb * wpc;                        // resident warps per SM
-        const int64_t ctas = (n_groups + wpc - 1) / wpc;
-        const int64_t slots = (int64_t)nb * c->sm_count;
-        // rounds a warp slot of the busiest SM runs one after the other
-        double cost;
-        if (ctas <= slots) cost = (double)((ctas + c->sm_count - 1) / c->sm_count) * wpc / (double)std::min<int64_t>(cap, 16);      // one wave: warps of the busiest SM, ~16 warps saturate the issue slots
-        else cost = (double)n_groups / ((double)cap * c->sm_count) + 1.0;
-        if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && cap > best_cap)) {
-            best_cost = cost; best = wpc; best_cap = cap;
-            best_grid = (int)std::min<int64_t>(ctas, slots);
+    const void *best_kern = nullptr;
+    for (int wide = 1; wide >= 0; --wide) {              // the 128-register variant first: it wins ties
+        const void *kern = ln_kernel(g->m64, wide != 0);
+        for (int wpc : cand) {
+            if (c->knobs.lane_wpc > 0 && wpc != c->knobs.lane_wpc) continue;
+            const size_t need = (size_t)g->desc_bytes + (size_t)wpc * wb;
+            if (need > budget || wpc * 32 > LN_MAX_THREADS) continue;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) { cudaGetLastError(); continue; }
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, wpc * 32, need) != cudaSuccess || nb < 1) { cudaGetLastError(); continue; }
+            const int cap = nb * wpc;                    // resident warps per SM
+            if (c->knobs.lane_debug) fprintf(stderr, "[lanes] %d regs, wpc %d: %zu B, %d CTAs / SM -> %d warps / SM\n", wide ? 128 : 80, wpc, need, nb, cap);
+            const int64_t ctas = (n_groups + wpc - 1) / wpc;
+            const int64_t slots = (int64_t)nb * c->sm_count;
+            // time ~ waves x round time of a warp that shares its SM with `busiest - 1` others.  Measured at C1 (ms per
+            // round of 1 920 trades): 6.8 alone, 7.7 / 7.9 / 8.8 / 13.7 with 5 / 7 / 11 / 22 warps per SM ~ 6.5 + 0.33 w.
+            const int64_t busiest = ctas <= slots ? (ctas + c->sm_count - 1) / c->sm_count * wpc : cap;
+            const double cost = (double)((ctas + slots - 1) / slots) * (6.5 + 0.33 * (double)busiest) + 1e-5 * wpc;
+            if (cost < best_cost - 1e-9) {
+                best_cost = cost; best = wpc; best_cap = cap; best_kern = kern;
+                best_grid = (int)std::min<int64_t>(ctas, slots);
+            }
         }
     }
     if (best == 0) return false;
-    g->wpc = best; g->grid = best_grid;
+    g->wpc = best; g->grid = best_grid; g->kern = best_kern;
+    if (c->knobs.lane_debug) fprintf(stderr, "[lanes] %lld groups -> %d warps per CTA, grid %d\n", (long long)n_groups, best, best_grid);
     g->smem = (size_t)g->desc_bytes + (size_t)best * wb;
+    static_assert(sizeof(LnGeom) <= sizeof(c->ln_geo), "LnGeom cache");
+    memcpy(c->ln_geo, g, sizeof(LnGeom));                 // the occupancy queries above are per (matrix, number of groups)
+    c->ln_geo_groups = n_groups; c->ln_geo_valid = true;
     return true;
 }
 
@@ -481,8 +497,7 @@ int sdx_run_nulls_lanes(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nul
             const int64_t ng = std::min(groups_per_launch, n_groups - gb);
             LnGeom geo;
             if (!ln_geometry(c, ng, &geo)) return sdx_fail(c, SDX_ERR_UNSUPPORTED, "lane kernel: shared memory layout does not fit");
-            auto kern = geo.m64 ? k_trade_lanes<true> : k_trade_lanes<false>;
-            SDX_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
+            SDX_CUDA(c, cudaFuncSetAttribute(geo.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
             // nulls of this batch of groups: chains are contiguous in the null index
             const uint64_t b_lo = std::max<uint64_t>(null0, (g_first + (uint64_t)gb) * LN_W * (uint64_t)chain_len);
             const uint64_t b_hi = std::min<uint64_t>(null_hi, (g_first + (uint64_t)(gb + ng)) * LN_W * (uint64_t)chain_len);
@@ -507,8 +522,9 @@ int sdx_run_nulls_lanes(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nul
                 a.out_rows = d_out ? d_out - (size_t)(b_lo - null0) * out_per : nullptr;      // the kernel indexes by null_id - null_lo
                 a.applied = (unsigned long long *)p_app; a.sc = sc;
                 cudaEventRecord(c->ev[3], c->stream);
-                kern<<<(unsigned)geo.grid, geo.wpc * 32, geo.smem, c->stream>>>(a);
-                cudaError_t e = cudaGetLastError();
+                void *kargs[] = {&a};
+                cudaError_t e = cudaLaunchKernel(geo.kern, dim3((unsigned)geo.grid), dim3((unsigned)geo.wpc * 32), kargs, geo.smem, c->stream);
+                if (e == cudaSuccess) e = cudaGetLastError();
                 if (e != cudaSuccess) return sdx_fail(c, SDX_ERR_CUDA, std::string("lane kernel launch failed: ") + cudaGetErrorString(e));
                 cudaEventRecord(c->ev[4], c->stream);
                 timer.count();
