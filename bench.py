@@ -32,13 +32,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+from superdendrix_b200 import defaults      # noqa: E402
+
 NULLS_PER_STEP = 100_000
-CHAIN_LEN, BURN_ROUNDS, POOL_SIZE = 16, 6, 1480       # short chains from a burnt-in pool: stationary nulls
-if os.environ.get("SDX_BENCH_CHAINS"):                # experiments only: "chain_len,burn,pool"
-    CHAIN_LEN, BURN_ROUNDS, POOL_SIZE = (int(x) for x in os.environ["SDX_BENCH_CHAINS"].split(","))
+# every null is one ordinary round away from a burnt-in pool state; blocks of 32 chains share their row pairs
+CHAIN_LEN, BURN_ROUNDS, POOL_SIZE, PAIR_GROUP = defaults.CHAIN_LEN, defaults.BURN_ROUNDS, defaults.POOL_SIZE, defaults.PAIR_GROUP
+if os.environ.get("SDX_BENCH_CHAINS"):                # experiments only: "chain_len,burn,pool,pair_group"
+    CHAIN_LEN, BURN_ROUNDS, POOL_SIZE, PAIR_GROUP = (int(x) for x in os.environ["SDX_BENCH_CHAINS"].split(","))
 SEED = 1764          # the reference's default -rs (src/generate_null_matrices.py:32)
 POPC_PEAK_NOMINAL = 148 * 16 * 1.965e9     # 32-bit popc/s
-NCU_DRAM_BYTES_PER_NULL = (439615744.0 + 6422784.0) / 23680     # profiles/r01_k_trade_k.ncu-rep: plan (8 B per trade) + one 43 KB pool state per chain of 16
+# profiles/r02_k_trade_lanes_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum of one 100 000-null launch of this configuration
+NCU_DRAM_BYTES_PER_NULL = (7.252417e9 + 8.019517e9) / 100000
 
 
 def workload():
@@ -206,6 +210,7 @@ def run_ours(args):
     eng.upload_matrix(rows_np, S)
     eng.upload_weights(w_np)
     eng.set_burn_in(BURN_ROUNDS, POOL_SIZE)
+    eng.set_pair_group(PAIR_GROUP)
     R, L, wpr, ras = eng.trade_shape()
     T = 5 * min(S, F)
     n = args.nulls
@@ -265,6 +270,8 @@ def run_ours(args):
     sampler.join()
     ms_e2e, _, _, _, ge2, _, _ = timed(step_e2e, args.steps, max(args.warmup, 1), 10_000)
 
+    strong = strong_scaling(args, eng, torch, dist, stream, flush, modules, rows_np, w_np, S, rank, world, barrier)
+
     t = torch.tensor([ms, ms_e2e, trade_ms, plan_ms], dtype=torch.float64, device="cuda")
     counts[0] = ge
     if world > 1:
@@ -292,7 +299,6 @@ def run_ours(args):
         trade_launches = max(int(trade_launches), 1)         # k_trade launches in the timed region (sdx_timing.trade_launches)
         per_launch_nulls = n * args.steps / trade_launches   # whole waves of chains per launch
         avg_launch_ms = trade_ms / trade_launches
-        achieved = (bytes_per_null * per_launch_nulls / 1e9) / (avg_launch_ms / 1e3)
         popc_per_null = T * 2 * wd
         int_peaks = eng.measure_int_peaks()          # POPC / LOP3 rates measured on this box, outside the timed region
         line = {
@@ -304,22 +310,32 @@ def run_ours(args):
                        "nulls_per_step_per_gpu": n, "trades_per_null": T, "chain_len": CHAIN_LEN, "stat": "fixed",
                        "burn_in": "chains start from a pool of %d states burnt in for %d rounds; the pool is cached per (matrix, seed): "
                                   "built once before the timed region of `value`, rebuilt every step of `e2e` (the matrix is re-uploaded)" % (POOL_SIZE, BURN_ROUNDS),
-                       "l2": "flushed between timed iterations (256 MiB memset); inputs are 51 KB and SMEM-resident by design",
+                       "pair_group": PAIR_GROUP,
+                       "l2": "flushed between timed iterations (256 MiB memset); the working states of a launch (%d MB) exceed L2" % (n // 32 * 220 // 1000),
                        "sharding": "null index ranges per rank, all_reduce(SUM) of exceedance counts"},
             "e2e": {"value": e2e_value, "unit": "nulls/s",
                     "h2d_bytes_per_step": int(rows_np.nbytes + w_np.nbytes + modules.nbytes),
                     "d2h_bytes_per_step": int(8 + 8), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_trade", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_NULL * per_launch_nulls,
-                         "traffic_source": "ncu --set full capture profiles/r01_k_trade_k.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum of one 23680-null launch of this configuration): per null x nulls per launch",
-                         "peak_source": peaks_src,
-                         "bytes_per_null": bytes_per_null, "avg_launch_ms": avg_launch_ms, "nulls_per_launch": per_launch_nulls, "trade_launches": trade_launches,
-                         "kernel_share_of_step": trade_ms / ms, "plan_share_of_step": plan_ms / ms,
-                         "popc_per_s": popc_per_null * value / world, "popc_frac_of_nominal": popc_per_null * value / world / POPC_PEAK_NOMINAL,
-                         "popc_peak_measured": int_peaks["popc_per_s"], "lop3_peak_measured": int_peaks["lop3_per_s"],
-                         "popc_frac_of_measured": popc_per_null * value / world / int_peaks["popc_per_s"],
-                         "note": "working set is shared-memory resident: algorithmic bytes are SMEM row transfers; the only compulsory HBM traffic of the kernel is the trade plan (traffic)"},
+            "roofline": {"bound": "issue (INT / popc pipe; not HBM, not tensor)", "kernel": "k_trade_lanes",
+                         "achieved": popc_per_null * per_launch_nulls / (avg_launch_ms / 1e3), "peak": int_peaks["popc_per_s"], "unit": "popc/s",
+                         "frac": popc_per_null * per_launch_nulls / (avg_launch_ms / 1e3) / int_peaks["popc_per_s"],
+                         "definition": "SURVEY 8d: algorithmic popc = 2 * T * Wd = %d per null x nulls per launch / launch time (CUDA events on the "
+                                       "launching stream), against the 32-bit POPC rate measured on this box by sdx_measure_int_peaks" % popc_per_null,
+                         "peak_source": "measured on this box (register-only micro-kernel); nominal %.3g" % POPC_PEAK_NOMINAL,
+                         "frac_of_nominal": popc_per_null * per_launch_nulls / (avg_launch_ms / 1e3) / POPC_PEAK_NOMINAL,
+                         "lop3_peak_measured": int_peaks["lop3_per_s"],
+                         "traffic": NCU_DRAM_BYTES_PER_NULL * per_launch_nulls,
+                         "traffic_source": "ncu --set full capture of one 100000-null launch of this configuration (profiles/r02_k_trade_lanes_ncu_summary.md): "
+                                           "dram__bytes_read.sum + dram__bytes_write.sum per null x nulls per launch",
+                         "hbm": {"achieved_gbs": NCU_DRAM_BYTES_PER_NULL * per_launch_nulls / 1e9 / (avg_launch_ms / 1e3), "peak_gbs": hbm_peak,
+                                 "frac": NCU_DRAM_BYTES_PER_NULL * per_launch_nulls / 1e9 / (avg_launch_ms / 1e3) / hbm_peak, "peak_source": peaks_src,
+                                 "note": "the states of the %d groups of 32 nulls of a launch (220 KB each) do not fit L2: every row of every trade "
+                                         "is staged from HBM by TMA and written back; far from the HBM roofline, which is why the bound is issue" % int(per_launch_nulls // 32)},
+                         "row_bytes_per_null_algorithmic": bytes_per_null,
+                         "avg_launch_ms": avg_launch_ms, "nulls_per_launch": per_launch_nulls, "trade_launches": trade_launches,
+                         "kernel_share_of_step": trade_ms / ms, "plan_share_of_step": plan_ms / ms},
+            "strong_scaling": strong,
             "clocks": sampler.summary(),
             "exceedances": int(counts.item()), "p_value": float(counts.item()) / total_nulls,
             "wall_s_timed_region": wall,
@@ -337,6 +353,48 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def strong_scaling(args, eng, torch, dist, stream, flush, modules, rows_np, w_np, S, rank, world, barrier):
+    """configs[1] as BASELINE.json states it: 100 000 nulls IN TOTAL, sharded over the ranks by null index the way the
+    reference shards one `-p` over processes by `-pre` (src/generate_null_matrices.py:29,82), through the product's own
+    superdendrix_b200.dist.null_pvalue — the all-reduce of the counts and the read of the result are inside the timed
+    region.  `resident`: matrix, weights and burn-in pool already on the device.  `e2e`: every step uploads matrix and
+    weights from pinned host memory, so the pool is rebuilt — each rank burns 1/world of it, one all-gather over NVLink."""
+    from superdendrix_b200 import dist as sdist
+    total = NULLS_PER_STEP
+    steps, warmup = max(args.steps, 3), max(args.warmup, 2)
+    z_obs = eng.null_pvalue(SEED, 0, 0, modules)["z_obs"]
+    out = {}
+
+    def run(e2e, step):
+        if e2e:
+            eng.upload_matrix(rows_np, S)
+            eng.upload_weights(w_np)
+        r = sdist.null_pvalue(eng, SEED, total, modules, null0=step * total, chain_len=CHAIN_LEN, burn=BURN_ROUNDS, pool_size=POOL_SIZE,
+                              pair_group=PAIR_GROUP, z_obs=None if e2e else z_obs)
+        return int(r["n_ge"][0])
+
+    for name, e2e in (("resident", False), ("e2e", True)):
+        for i in range(warmup):
+            run(e2e, 50_000 + i)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        ge = []
+        for i in range(steps):
+            flush.zero_()
+            barrier()
+            ev[i][0].record(stream)
+            ge.append(run(e2e, 60_000 + i))
+            ev[i][1].record(stream)
+        barrier()
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out[name] = {"ms_per_100k_nulls": float(ms.item()), "nulls_per_s": total / (float(ms.item()) / 1e3), "exceedances_first_step": ge[0]}
+    out["workload"] = "C1 as stated: %d nulls in total over %d GPU(s), dist.null_pvalue (all_reduce and result read inside the timed region)" % (total, world)
+    out["scaling"] = "strong"
+    return out
 
 
 def secondary(eng, torch):
@@ -435,7 +493,9 @@ def secondary(eng, torch):
             os.mkdir(os.path.join(d, "rand_mat"))
             n = 2000
             t0 = time.perf_counter()
-            gnm.main(["-m", mut, "-p", str(n), "-o", os.path.join(d, "rand_mat") + "/", "--mode", "restart", "-v", "40"])
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):      # the CLI prints like the reference's; stdout carries the JSON line only
+                gnm.main(["-m", mut, "-p", str(n), "-o", os.path.join(d, "rand_mat") + "/", "--mode", "restart", "-v", "40"])
             t_gen = time.perf_counter() - t0
             t0 = time.perf_counter()
             rows, _ = i_o.read_nulls_tsv(os.path.join(d, "rand_mat") + "/", 0, n, samples, features)

@@ -26,6 +26,7 @@
 #ifndef SDX_H
 #define SDX_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -135,6 +136,20 @@ int sdx_curveball(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, 
  * on the GPU count.  The pool is built on first use and cached until the matrix, the seed or n_trades change.
  * burn_rounds = 0 (default) starts every chain from the observed matrix. */
 int sdx_set_burn_in(sdx_ctx *ctx, int64_t burn_rounds, int pool_size);
+
+/* The burn-in pool built in parts — the multi-GPU form of the pool (the reference's counterpart is one burn-in per
+ * `-pre` process, src/generate_null_matrices.py:29,71-74): rank r burns a slice of the pool_size states, the slices are
+ * exchanged with an all-gather over NVLink directly on the pool's device memory, and every rank commits the same pool.
+ *   sdx_pool_begin   allocates the pool for (seed, n_trades; -1 = 5*min(S,F)); *d_pool = its DEVICE address (pool_size
+ *                    states of *state_bytes bytes, state j at offset j * state_bytes); the pool is invalid until commit
+ *   sdx_pool_build   burns states [first_state, first_state + n_states) into their slots (synchronous)
+ *   sdx_pool_commit  declares every slot written (by sdx_pool_build or by the caller's exchange)
+ *   sdx_pool_valid   1 when a committed pool for (matrix, seed, n_trades, burn-in) is cached, else 0 (never an error code)
+ * A pool built this way is bit-identical to the one sdx_curveball / sdx_null_pvalue build on first use. */
+int sdx_pool_begin(sdx_ctx *ctx, uint64_t seed, int64_t n_trades, void **d_pool, size_t *state_bytes);
+int sdx_pool_build(sdx_ctx *ctx, int first_state, int n_states);
+int sdx_pool_commit(sdx_ctx *ctx);
+int sdx_pool_valid(sdx_ctx *ctx, uint64_t seed, int64_t n_trades);
 
 /* How the PAIR stream (which two rows trade t exchanges) is shared between nulls.  pair_group = 1 (default): every
  * null draws its own pairs, stream id = its null index.  pair_group = 32: the chains of an aligned block of 32

@@ -62,6 +62,10 @@ PROTOTYPES = {
     "sdx_curveball": (C.c_int, [_ctx, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, _u32p, _i64p]),
     "sdx_set_burn_in": (C.c_int, [_ctx, C.c_int64, C.c_int]),
     "sdx_set_pair_group": (C.c_int, [_ctx, C.c_int]),
+    "sdx_pool_begin": (C.c_int, [_ctx, C.c_uint64, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "sdx_pool_build": (C.c_int, [_ctx, C.c_int, C.c_int]),
+    "sdx_pool_commit": (C.c_int, [_ctx]),
+    "sdx_pool_valid": (C.c_int, [_ctx, C.c_uint64, C.c_int64]),
     "sdx_curveball_replay": (C.c_int, [_ctx, _u32p, _i32p, _i32p, _u32p, C.c_int64, _u32p, _i64p]),
     "sdx_null_pvalue": (C.c_int, [_ctx, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _i32p,
                                   C.c_int, _f64p, _i64p, _f64p, _f64p]),

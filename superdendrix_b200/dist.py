@@ -115,23 +115,61 @@ def allgather_array(a, group=None):
 # ---------------------------------------------------------------------------
 # sharded operations.  `engine` is a superdendrix_b200.engine.Engine (or any object with the same methods).
 # ---------------------------------------------------------------------------
-def shard_chains(n, chain_len, rank, world):
-    """Null range of a rank as whole chains (so no rank has to replay the prefix of a chain another rank owns)."""
-    n_chains = -(-int(n) // int(chain_len))
-    c_lo, c_hi = shard_range(n_chains, rank, world)
-    return min(c_lo * chain_len, n), min(c_hi * chain_len, n)
+def shard_chains(n, chain_len, rank, world, pair_group=1):
+    """Null range of a rank as whole chains (so no rank has to replay the prefix of a chain another rank owns) — whole
+    blocks of pair_group chains when the chains of a block share their schedule of row pairs (one warp runs a block)."""
+    unit = int(chain_len) * max(int(pair_group), 1)
+    n_units = -(-int(n) // unit)
+    u_lo, u_hi = shard_range(n_units, rank, world)
+    return min(u_lo * unit, n), min(u_hi * unit, n)
 
 
-def null_pvalue(engine, seed, n_nulls, modules, null0=0, n_trades=-1, stat=0, z_obs=None, chain_len=16, burn=6,
-                pool_size=1480, group=None):
-    """Permutation p-values over n_nulls nulls sharded by null index.  Nulls come in short chains (chain_len) that
-    start from burnt-in pool states (Engine.set_burn_in), so every null is a draw from the stationary distribution —
-    what the reference gets from its single long chain — and there are enough chains to fill every GPU.  Streams and
-    pool are keyed on global indices: the counts do not depend on the number of ranks.
-    Returns dict(n_ge, p, z_obs, n_nulls)."""
+def build_pool(engine, seed, n_trades=-1, pool_size=None, group=None):
+    """The burn-in pool built once across the ranks: rank r burns its slice of the pool states, the slices are exchanged
+    with ONE all-gather over NVLink directly on the pool's device memory (include/sdx.h: sdx_pool_begin / build /
+    commit), every rank commits the same pool.  Falls back to a local build for a single rank, an engine without the
+    part-wise entry points (the oracle stand-in of the CPU tests) or a pool that does not split evenly."""
     rank, world = _world(group)
-    lo, hi = shard_chains(n_nulls, chain_len, rank, world)
+    if world == 1 or not hasattr(engine, "pool_begin") or pool_size is None or pool_size % world:
+        return False
+    torch, dist = _dist()
+    if dist.get_backend(group) != "nccl" or engine.pool_valid(seed, n_trades):        # the same on every rank: same sequence of calls
+        return False
+    ptr, state_bytes = engine.pool_begin(seed, n_trades)
+    per = pool_size // world
+    engine.pool_build(rank * per, per)
+
+    class _Pool:                      # the library's device buffer as a torch tensor (no copy)
+        __cuda_array_interface__ = {"shape": (pool_size * state_bytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    whole = torch.as_tensor(_Pool(), device=_device(group))
+    mine = whole[rank * per * state_bytes:(rank + 1) * per * state_bytes]
+    dist.all_gather_into_tensor(whole, mine, group=group)        # in place: every rank's slice lands at its offset
+    torch.cuda.current_stream().synchronize()
+    engine.pool_commit()
+    return True
+
+
+def null_pvalue(engine, seed, n_nulls, modules, null0=0, n_trades=-1, stat=0, z_obs=None, chain_len=None, burn=None,
+                pool_size=None, pair_group=None, group=None, shared_pool=True):
+    """Permutation p-values over n_nulls nulls sharded by null index (the reference shards one `-p` over processes
+    by `-pre`, src/generate_null_matrices.py:29,82).  Every null is chain_len ordinary rounds away from a burnt-in pool
+    state (Engine.set_burn_in), so it is a draw from the stationary distribution — what the reference gets from its
+    single long chain — and there are enough independent units to fill every GPU.  Streams and pool are keyed on global
+    indices and ranks take whole blocks of chains: the counts do not depend on the number of ranks.
+    Returns dict(n_ge, p, z_obs, n_nulls)."""
+    from . import defaults
+    chain_len = defaults.CHAIN_LEN if chain_len is None else chain_len
+    burn = defaults.BURN_ROUNDS if burn is None else burn
+    pool_size = defaults.POOL_SIZE if pool_size is None else pool_size
+    pair_group = defaults.PAIR_GROUP if pair_group is None else pair_group
+    rank, world = _world(group)
+    lo, hi = shard_chains(n_nulls, chain_len, rank, world, pair_group)
     engine.set_burn_in(burn, pool_size)
+    if hasattr(engine, "set_pair_group"):
+        engine.set_pair_group(pair_group)
+    if shared_pool and burn > 0 and stat == 0:
+        build_pool(engine, seed, n_trades, pool_size, group)
     if z_obs is None:
         z_obs = engine.null_pvalue(seed, 0, 0, modules, n_trades=n_trades, stat=stat)["z_obs"]     # same on every rank
     res = engine.null_pvalue(seed, null0 + lo, hi - lo, modules, n_trades=n_trades, chain_len=chain_len, stat=stat, z_obs=z_obs)

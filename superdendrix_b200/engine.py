@@ -56,7 +56,7 @@ class Engine:
         """Run on a caller-owned CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
         self._check(self._lib.sdx_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)))
 
-    def set_burn_in(self, burn_rounds: int, pool_size: int = 1480):
+    def set_burn_in(self, burn_rounds: int, pool_size: int = 1472):
         """Chains start from one of ``pool_size`` states that have already seen ``burn_rounds`` rounds of trades
         (0 = start from the observed matrix, as a single reference chain does at null 0)."""
         self._check(self._lib.sdx_set_burn_in(self._ctx, int(burn_rounds), int(pool_size)))
@@ -65,6 +65,21 @@ class Engine:
         """1: every null draws its own row pairs.  32: aligned blocks of 32 chains share the schedule of row pairs
         (every null keeps its own deal stream) — the layout the one-thread-per-null kernel needs (include/sdx.h)."""
         self._check(self._lib.sdx_set_pair_group(self._ctx, int(pair_group)))
+
+    def pool_begin(self, seed: int, n_trades: int = -1):
+        """Start building the burn-in pool in parts (multi-GPU): returns (device address, bytes per state)."""
+        ptr, nb = C.c_void_p(), C.c_size_t()
+        self._check(self._lib.sdx_pool_begin(self._ctx, C.c_uint64(seed), C.c_int64(n_trades), C.byref(ptr), C.byref(nb)))
+        return ptr.value, nb.value
+
+    def pool_build(self, first_state: int, n_states: int):
+        self._check(self._lib.sdx_pool_build(self._ctx, int(first_state), int(n_states)))
+
+    def pool_valid(self, seed: int, n_trades: int = -1) -> bool:
+        return bool(self._lib.sdx_pool_valid(self._ctx, C.c_uint64(seed), C.c_int64(n_trades)))
+
+    def pool_commit(self):
+        self._check(self._lib.sdx_pool_commit(self._ctx))
 
     def timing(self) -> dict:
         t = _capi.Timing()

@@ -27,7 +27,7 @@ import time
 
 import numpy as np
 
-from . import bitpack
+from . import bitpack, defaults
 from .engine import Engine
 from .i_o import dense_matrix, getLogger, load_mutation_data, write_nulls_tsv
 
@@ -63,8 +63,9 @@ def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, ba
     try:
         eng.upload_dense(dense)
         R, L, wpr, rows_are_samples = eng.trade_shape()
-        chain_len = {"chained": max(int(n_nulls), 1), "parallel": 16, "restart": 1}[mode]
-        eng.set_burn_in(burn_in if mode == "parallel" else 0, 1480)
+        chain_len = {"chained": max(int(n_nulls), 1), "parallel": defaults.CHAIN_LEN, "restart": 1}[mode]
+        eng.set_burn_in(burn_in if mode == "parallel" else 0, defaults.POOL_SIZE)
+        eng.set_pair_group(defaults.PAIR_GROUP if mode == "parallel" else 1)
         # a chain starts at a multiple of chain_len: with prefix a multiple of n_nulls every process owns one chain
         done = 0
         while done < n_nulls:

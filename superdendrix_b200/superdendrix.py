@@ -37,7 +37,7 @@ import time
 
 import numpy as np
 
-from . import bitpack
+from . import bitpack, defaults
 from .engine import SDX_STAT_FIXED, SDX_STAT_MAXK, Engine
 from .i_o import getLogger, load_events, load_mutation_data, pack_features, read_nulls_tsv
 
@@ -268,8 +268,9 @@ def null_loop(genes, samples, profile, events_to_samples, module, zP, args, logg
         eng.upload_matrix(pack_features(genes, samples, events_to_samples), len(samples))
         eng.upload_weights(w_vec)
         mod = np.array([[gidx[g] for g in module] + [-1] * (max(k, 1) - k)], dtype=np.int32)
-        chain, burn = {"parallel": (16, args.burn_in), "chained": (max(n, 1), 0), "restart": (1, 0)}[args.mode]
-        eng.set_burn_in(burn, 1480)
+        chain, burn = {"parallel": (defaults.CHAIN_LEN, args.burn_in), "chained": (max(n, 1), 0), "restart": (1, 0)}[args.mode]
+        eng.set_burn_in(burn, defaults.POOL_SIZE)
+        eng.set_pair_group(defaults.PAIR_GROUP if args.mode == "parallel" else 1)
         res = eng.null_pvalue(args.random_seed, 0, n, mod, chain_len=chain, stat=stat, z_obs=np.array([zP]), want_scores=True)
         return int(res["n_ge"][0]), n, res["null_scores"][0]
     # files: <-nm><i>.tsv, restricted to the profiled samples as src/superdendrix.py:186 does.  Read in batches by the

@@ -15,10 +15,13 @@ class OracleEngine:
         self.frows = bitpack.pack_rows(self.dense.T)
         self.ras = self.F >= self.S
         self.trows = bitpack.pack_rows(self.dense if self.ras else self.dense.T)
-        self.burn, self.pool = 0, 1
+        self.burn, self.pool, self.pair_group = 0, 1, 1
 
-    def set_burn_in(self, burn_rounds, pool_size=1480):
+    def set_burn_in(self, burn_rounds, pool_size=1472):
         self.burn, self.pool = int(burn_rounds), int(pool_size)
+
+    def set_pair_group(self, pair_group):
+        self.pair_group = int(pair_group)
 
     def null_pvalue(self, seed, null0, n_nulls, modules, n_trades=-1, chain_len=1, stat=0, z_obs=None, want_scores=False):
         modules = np.atleast_2d(modules)
@@ -28,7 +31,8 @@ class OracleEngine:
         zo = z if z_obs is None else np.asarray(z_obs)
         n_ge = np.zeros(self.P, dtype=np.int64)
         if n_nulls:
-            nulls, _ = oracle.curveball_nulls(self.trows, seed, null0, n_nulls, T, chain_len, burn=self.burn, pool_size=self.pool)
+            nulls, _ = oracle.curveball_nulls(self.trows, seed, null0, n_nulls, T, chain_len, burn=self.burn, pool_size=self.pool,
+                                              pair_group=self.pair_group)
             for m in nulls:
                 fr = bitpack.pack_rows(bitpack.unpack_rows(m, max(self.S, self.F)).T) if self.ras else m
                 for p, mod in enumerate(modules):

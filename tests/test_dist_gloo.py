@@ -30,13 +30,14 @@ def _worker(rank, world, port, out_dir):
     from superdendrix_b200 import dist
     dense, w, modules = _inputs()
     eng = OracleEngine(dense, w)
-    pv = dist.null_pvalue(eng, seed=7, n_nulls=37, modules=modules, chain_len=4, burn=3, pool_size=5)
+    pv = dist.null_pvalue(eng, seed=7, n_nulls=37, modules=modules, chain_len=4, burn=3, pool_size=5, pair_group=1)
+    pg = dist.null_pvalue(eng, seed=7, n_nulls=150, modules=modules, chain_len=1, burn=2, pool_size=64, pair_group=32)      # blocks of 32 chains per rank
     sc = dist.scan(eng, profile=0, k=3, topn=6)
     jobs = np.array([[0, 3, 5], [1, 2, -1], [4, -1, -1], [0, 1, 2], [6, 7, -1]], dtype=np.int32)
     pj = np.array([0, 1, 1, 0, 1], dtype=np.int32)
     cp = dist.condperm_batch(eng, jobs, 50, seed=3, perm_id0=8, profile_of_job=pj)
     rs = dist.ranksum(eng, jobs, pj)
-    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), n_ge=pv["n_ge"], p=pv["p"], sW=sc["W"], sF=sc["features"], sC=sc["coverage"],
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), n_ge=pv["n_ge"], p=pv["p"], g_ge=pg["n_ge"], sW=sc["W"], sF=sc["features"], sC=sc["coverage"],
              sN=sc["n_scored"], cp=cp[0], cpW=cp[1], z=rs["z"], s2=rs["twice_rank_sum"])
     tdist.destroy_process_group()
 
@@ -50,7 +51,9 @@ def test_two_ranks_reduce_to_the_single_process_result(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     dense, w, modules = _inputs()
     eng = OracleEngine(dense, w)
-    one = dist.null_pvalue(eng, seed=7, n_nulls=37, modules=modules, chain_len=4, burn=3, pool_size=5)      # world = 1 path
+    one = dist.null_pvalue(eng, seed=7, n_nulls=37, modules=modules, chain_len=4, burn=3, pool_size=5, pair_group=1)      # world = 1 path
+    one_g = dist.null_pvalue(eng, seed=7, n_nulls=150, modules=modules, chain_len=1, burn=2, pool_size=64, pair_group=32)
+    assert dist.shard_chains(150, 1, 0, 2, 32) == (0, 96) and dist.shard_chains(150, 1, 1, 2, 32) == (96, 150)
     sc1 = eng.scan(0, 3, 6)
     jobs = np.array([[0, 3, 5], [1, 2, -1], [4, -1, -1], [0, 1, 2], [6, 7, -1]], dtype=np.int32)
     pj = np.array([0, 1, 1, 0, 1], dtype=np.int32)
@@ -59,6 +62,7 @@ def test_two_ranks_reduce_to_the_single_process_result(tmp_path):
     for r in range(2):
         z = np.load(tmp_path / ("rank%d.npz" % r))
         assert np.array_equal(z["n_ge"], one["n_ge"]) and np.allclose(z["p"], one["p"])
+        assert np.array_equal(z["g_ge"], one_g["n_ge"])
         assert np.array_equal(z["sF"], sc1["features"]) and np.array_equal(z["sW"], sc1["W"]) and np.array_equal(z["sC"], sc1["coverage"])
         assert int(z["sN"]) == sc1["n_scored"] == 24 + 24 * 23 // 2 + 24 * 23 * 22 // 6
         assert np.array_equal(z["cp"], cp1[0]) and np.array_equal(z["cpW"], cp1[1])

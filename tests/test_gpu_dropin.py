@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 from oracle import refport
-from superdendrix_b200 import bitpack, curveball, dist, generate_null_matrices as gnm, i_o, synth
+from superdendrix_b200 import bitpack, curveball, dist, generate_null_matrices as gnm, i_o, synth, defaults
 from superdendrix_b200 import superdendrix as sd
 from superdendrix_b200.engine import Engine
 
@@ -161,7 +161,8 @@ def test_generate_null_matrices_cli_writes_reference_format(tmp_path):
     out4 = tmp_path / "par"
     out4.mkdir()
     gnm.main(["-m", os.path.join(gdir, "features.tsv"), "-p", "5", "-o", str(out4) + "/", "-rs", "5", "--mode", "parallel", "--burn-in", "4"])
-    want, _ = oracle.curveball_nulls(rows_of(dense), 5, 0, 5, 5 * R, 16, burn=4, pool_size=1480)
+    want, _ = oracle.curveball_nulls(rows_of(dense), 5, 0, 5, 5 * R, defaults.CHAIN_LEN, burn=4, pool_size=defaults.POOL_SIZE,
+                                     pair_group=defaults.PAIR_GROUP)
     nd = i_o.dense_matrix(genes, samples, i_o.load_mutation_data(str(out4 / "4.tsv"))[5])
     assert np.array_equal(bitpack.pack_rows(nd if ras else nd.T), want[4])
 
@@ -204,7 +205,8 @@ def test_driver_end_to_end_against_oracle(tmp_path, stat):
     assert abs(last["zP"] - zP) <= 1e-9 * np.abs(wv).sum()
     # null loop: same nulls through the oracle
     obs = rows_of(d)
-    nulls, _ = oracle.curveball_nulls(obs, 9, 0, 64, 5 * obs.shape[0], 16, burn=6, pool_size=1480)     # --mode parallel (default)
+    nulls, _ = oracle.curveball_nulls(obs, 9, 0, 64, 5 * obs.shape[0], defaults.CHAIN_LEN, burn=defaults.BURN_ROUNDS, pool_size=defaults.POOL_SIZE,
+                                      pair_group=defaults.PAIR_GROUP)     # --mode parallel (default)
     ras = d.shape[1] >= d.shape[0]
     sc = []
     for m in nulls:
@@ -265,8 +267,8 @@ def test_dist_functions_single_rank():
     with Engine(0) as eng:
         eng.upload_dense(dense)
         eng.upload_weights(w)
-        pv = dist.null_pvalue(eng, 3, 50, modules)                   # chains of 32 from the burnt-in pool
-        direct = eng.null_pvalue(3, 0, 50, modules, chain_len=16)
+        pv = dist.null_pvalue(eng, 3, 50, modules)                   # the defaults: one round from the burnt-in pool, blocks of 32 chains
+        direct = eng.null_pvalue(3, 0, 50, modules, chain_len=defaults.CHAIN_LEN)
         assert np.array_equal(pv["n_ge"], direct["n_ge"]) and np.allclose(pv["p"], direct["n_ge"] / 50)
         whole = eng.scan(0, 3, 8)
         # two "ranks" emulated in one process: ranges merge to the whole
@@ -298,7 +300,8 @@ def test_batched_screen_equals_per_profile_pipeline(tmp_path):
         res = scr.screen(eng, rows, S, w, mask, k=3, cond_it=cond_it, n_nulls=n_nulls, seed=seed, stat="fixed")
     obs = rows_of(dense)
     ras = F >= S
-    nulls, _ = oracle.curveball_nulls(obs, seed, 0, n_nulls, 5 * obs.shape[0], 16, burn=6, pool_size=1480)
+    nulls, _ = oracle.curveball_nulls(obs, seed, 0, n_nulls, 5 * obs.shape[0], defaults.CHAIN_LEN, burn=defaults.BURN_ROUNDS,
+                                      pool_size=defaults.POOL_SIZE, pair_group=defaults.PAIR_GROUP)
     for p in range(P):
         wm = np.where(mask[p], w[p], 0.0)
         mk = bitpack.pack_mask(np.nonzero(mask[p])[0], S)
