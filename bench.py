@@ -271,6 +271,10 @@ def run_ours(args):
     ms_e2e, _, _, _, ge2, _, _ = timed(step_e2e, args.steps, max(args.warmup, 1), 10_000)
 
     strong = strong_scaling(args, eng, torch, dist, stream, flush, modules, rows_np, w_np, S, rank, world, barrier)
+    full = None if args.no_extra else full_size_configs(eng, torch, dist, rank, world, barrier)
+    # back to the headline workload for the roofline peaks measured below
+    eng.upload_matrix(rows_np, S)
+    eng.upload_weights(w_np)
 
     t = torch.tensor([ms, ms_e2e, trade_ms, plan_ms], dtype=torch.float64, device="cuda")
     counts[0] = ge
@@ -336,6 +340,7 @@ def run_ours(args):
                          "avg_launch_ms": avg_launch_ms, "nulls_per_launch": per_launch_nulls, "trade_launches": trade_launches,
                          "kernel_share_of_step": trade_ms / ms, "plan_share_of_step": plan_ms / ms},
             "strong_scaling": strong,
+            "full_size_configs": full,
             "clocks": sampler.summary(),
             "exceedances": int(counts.item()), "p_value": float(counts.item()) / total_nulls,
             "wall_s_timed_region": wall,
@@ -394,6 +399,79 @@ def strong_scaling(args, eng, torch, dist, stream, flush, modules, rows_np, w_np
         out[name] = {"ms_per_100k_nulls": float(ms.item()), "nulls_per_s": total / (float(ms.item()) / 1e3), "exceedances_first_step": ge[0]}
     out["workload"] = "C1 as stated: %d nulls in total over %d GPU(s), dist.null_pvalue (all_reduce and result read inside the timed region)" % (total, world)
     out["scaling"] = "strong"
+    return out
+
+
+def full_size_configs(eng, torch, dist, rank, world, barrier):
+    """BASELINE configs[2..4] at FULL size through superdendrix_b200.dist on `world` GPUs (sharded by subset range / null
+    range / job; collectives and result reads inside the timed region; wall time between barriers, max over ranks):
+      C2  exhaustive k<=3 scan, 1 000 x ~2 000
+      C3  batched screen: 500 profiles x 10 000 shared nulls of the 1 000 x ~5 000 matrix (rows = samples: k_trade, global-memory variant)
+      C4  18 000 profiles: conditional permutations (3 features x 10 000 permutations each) + rank-sum"""
+    from superdendrix_b200 import bitpack, dist as sdist, synth
+    out = {"n_gpus": world}
+
+    def timed(fn, reps=2):
+        best, res = None, None
+        for _ in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            res = fn()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t.item()) if best is None else min(best, float(t.item()))
+        return best, res
+
+    try:
+        dense, _, _ = synth.feature_matrix(1000, 2000, seed=20)
+        eng.upload_matrix(bitpack.pack_rows(dense.T), 1000)
+        eng.upload_weights(synth.weights(1000, 1, seed=3))
+        dt, r = timed(lambda: sdist.scan(eng, 0, 3, 16), reps=3)
+        out["c2_scan"] = {"workload": "C2: exhaustive k<=3 scan, %d features x 1000 samples, sharded by smallest feature index" % dense.shape[1],
+                          "subsets": int(r["n_scored"]), "ms": dt * 1e3, "subsets_per_s": r["n_scored"] / dt, "best": [int(x) for x in r["features"][0]],
+                          "best_W": float(r["W"][0])}
+    except Exception as e:      # noqa: BLE001
+        out["c2_scan"] = {"error": str(e)}
+    try:
+        dense, _, _ = synth.feature_matrix(1000, 5000, seed=20)
+        S, F = dense.shape
+        n_prof, n_nulls = 500, 10000
+        w = synth.weights(S, n_prof, seed=5)
+        eng.upload_matrix(bitpack.pack_rows(dense.T), S)
+        eng.upload_weights(w)
+        rng = np.random.default_rng(2)
+        order = np.argsort(-dense.sum(0), kind="stable")[:60]
+        mods = np.sort(np.stack([rng.choice(order, 3, replace=False) for _ in range(n_prof)]), axis=1).astype(np.int32)
+        sdist.null_pvalue(eng, SEED, 256 * world, mods)                       # warm-up: pool (1472 x 640 KB) + scratch
+        dt, r = timed(lambda: sdist.null_pvalue(eng, SEED, n_nulls, mods), reps=2)
+        out["c3_screen"] = {"workload": "C3: %d profiles x %d shared nulls, %d x %d matrix (rows = samples, %d trades per null), pool resident" % (
+                                n_prof, n_nulls, S, F, 5 * S),
+                            "ms": dt * 1e3, "nulls_per_s": n_nulls / dt, "profile_null_scores_per_s": n_nulls * n_prof / dt,
+                            "p_mean": float(np.mean(r["p"]))}
+    except Exception as e:      # noqa: BLE001
+        out["c3_screen"] = {"error": str(e)}
+    try:
+        dense, _, _ = workload()
+        S, F = dense.shape
+        n_prof = 18000
+        w = synth.weights(S, n_prof, seed=11)
+        eng.upload_matrix(bitpack.pack_rows(dense.T), S)
+        eng.upload_weights(w)
+        rng = np.random.default_rng(1)
+        order = np.argsort(-dense.sum(0), kind="stable")[:40]
+        mods = np.sort(np.stack([rng.choice(order, 3, replace=False) for _ in range(n_prof)]), axis=1).astype(np.int32)
+        pj = np.arange(n_prof, dtype=np.int32)
+        sdist.condperm_batch(eng, mods[:64 * world], 1000, SEED, 0, pj[:64 * world])
+        dt, r = timed(lambda: sdist.condperm_batch(eng, mods, 10000, SEED, 0, pj), reps=2)
+        dt2, r2 = timed(lambda: sdist.ranksum(eng, mods, pj), reps=2)
+        out["c4_genome_wide"] = {"workload": "C4: %d profiles x k=3 module: 10000 conditional permutations per feature, then rank-sum per profile" % n_prof,
+                                 "condperm_ms": dt * 1e3, "permuted_scores_per_s": n_prof * 3 * 10000 / dt,
+                                 "ranksum_ms": dt2 * 1e3, "ranksum_profiles_per_s": n_prof / dt2, "ranksum_p_median": float(np.median(r2["p"]))}
+    except Exception as e:      # noqa: BLE001
+        out["c4_genome_wide"] = {"error": str(e)}
     return out
 
 

@@ -185,6 +185,15 @@ int sdx_null_pvalue(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls
                     int64_t chain_len, int stat, const int32_t *modules, int k, const double *z_obs,
                     int64_t *n_ge, double *null_scores, double *z_obs_out);
 
+/* The same loop over nulls the CALLER supplies — the reference's own form of the loop: it reads null i from
+ * <nm><i>.tsv restricted to the profiled samples (src/superdendrix.py:175-192, src/i_o.py:57).  feature_rows:
+ * n_nulls x F x words_per_row packed feature rows over the uploaded matrix's samples (host or device memory; e.g. the
+ * output of sdx_read_nulls_tsv).  Every null is scored for every uploaded profile in one call: stat = SDX_STAT_FIXED
+ * scores module p on the null, SDX_STAT_MAXK re-optimises over |M| <= k_p (k_p = size of module p, :173).
+ * z_obs == NULL: the statistic of the uploaded (observed) matrix.  null_scores: n_profiles x n_nulls, or NULL. */
+int sdx_null_pvalue_rows(sdx_ctx *ctx, const uint32_t *feature_rows, int64_t n_nulls, int stat, const int32_t *modules,
+                         int k, const double *z_obs, int64_t *n_ge, double *null_scores, double *z_obs_out);
+
 /* Exhaustive scan of every feature subset of size 1..k (k <= 3) under W for
  * one profile: the integral optimum of the ILP of src/superdendrix.py:294-313,
  * 393-401.  hits: the topn best subsets, W descending (ties: enumeration

@@ -175,6 +175,20 @@ def scan(rows, S, w, k, topn=8, mask=None):
     return oW, oF, oC, int(n)
 
 
+def scan_range(rows, S, w, k, topn, a_lo, a_hi, mask=None):
+    """The scan restricted to subsets whose smallest feature index is in [a_lo, a_hi)."""
+    rows = _u32(rows)
+    F, wpr = rows.shape
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    mk = _u32(mask) if mask is not None else None
+    oW = np.zeros(topn); oF = np.zeros((topn, 3), dtype=np.int32); oC = np.zeros(topn, dtype=np.int32)
+    lib().sdxo_scan_range.restype = C.c_int64
+    n = lib().sdxo_scan_range(_p(rows, C.c_uint32), C.c_int(F), C.c_int(wpr), C.c_int(S), _p(w, C.c_double),
+                              _p(mk, C.c_uint32), C.c_int(k), C.c_int(topn), C.c_int(a_lo), C.c_int(a_hi), _p(oW, C.c_double),
+                              _p(oF, C.c_int32), _p(oC, C.c_int32))
+    return oW, oF, oC, int(n)
+
+
 def condperm(rows, S, feats, w, sample_idx, seed, perm_id0, P):
     rows = _u32(rows)
     f = np.ascontiguousarray(feats, dtype=np.int32)

@@ -490,13 +490,16 @@ static void hit_insert(sdxo_hit *top, int *n, int cap, const sdxo_hit *h) {
     top[i] = *h;
 }
 
-SDXO_API int64_t sdxo_scan(const uint32_t *rows, int F, int wpr, int S, const double *w, const uint32_t *mask,
-                           int k, int topn, double *outW, int32_t *outF, int32_t *outCov) {
+/* Subsets whose smallest feature index lies in [a_lo, a_hi) (the unit the scan is sharded by); a_lo = 0, a_hi = F is
+ * the whole enumeration.  Returns the number of subsets scored.  Ties keep enumeration order (size-major, then
+ * lexicographic) within the range. */
+SDXO_API int64_t sdxo_scan_range(const uint32_t *rows, int F, int wpr, int S, const double *w, const uint32_t *mask,
+                                 int k, int topn, int a_lo, int a_hi, double *outW, int32_t *outF, int32_t *outCov) {
     sdxo_hit *top = (sdxo_hit *)calloc((size_t)topn, sizeof(sdxo_hit));
     int n = 0; int64_t rank = 0;
     int32_t f[3]; int32_t ov, ac; sdxo_hit h;
     for (int size = 1; size <= k && size <= 3; ++size) {
-        for (int a = 0; a < F; ++a) {
+        for (int a = a_lo; a < a_hi && a < F; ++a) {
             if (size == 1) {
                 f[0] = a; f[1] = f[2] = -1;
                 sdxo_score_set(rows, wpr, S, f, 1, w, mask, &h.W, &h.cov, &ov, &ac);
@@ -525,6 +528,11 @@ SDXO_API int64_t sdxo_scan(const uint32_t *rows, int F, int wpr, int S, const do
     for (int i = n; i < topn; ++i) { outW[i] = -INFINITY; outCov[i] = 0; outF[3*i] = outF[3*i+1] = outF[3*i+2] = -1; }
     free(top);
     return rank;
+}
+
+SDXO_API int64_t sdxo_scan(const uint32_t *rows, int F, int wpr, int S, const double *w, const uint32_t *mask,
+                           int k, int topn, double *outW, int32_t *outF, int32_t *outCov) {
+    return sdxo_scan_range(rows, F, wpr, S, w, mask, k, topn, 0, F, outW, outF, outCov);
 }
 
 /* ------------------------------------------------------------------ */

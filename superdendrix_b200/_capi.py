@@ -69,6 +69,7 @@ PROTOTYPES = {
     "sdx_curveball_replay": (C.c_int, [_ctx, _u32p, _i32p, _i32p, _u32p, C.c_int64, _u32p, _i64p]),
     "sdx_null_pvalue": (C.c_int, [_ctx, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _i32p,
                                   C.c_int, _f64p, _i64p, _f64p, _f64p]),
+    "sdx_null_pvalue_rows": (C.c_int, [_ctx, _u32p, C.c_int64, C.c_int, _i32p, C.c_int, _f64p, _i64p, _f64p, _f64p]),
     "sdx_scan": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.POINTER(Hit), _i64p]),
     "sdx_scan_range": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Hit), _i64p]),
     "sdx_condperm": (C.c_int, [_ctx, C.c_int, _i32p, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _i64p, _f64p]),

@@ -429,8 +429,11 @@ bool sdx_lanes_applicable(sdx_ctx *c, int64_t n_chains, int64_t T, bool fused_sc
     if (ln_layout(c) != SDX_OK || c->ln_state != 1) return false;
     if (fused_scoring && c->rows_are_samples) return false;      // the fused scorer reads feature rows
     if (T > 0x7fffffff) return false;
-    const int64_t min_chains = c->knobs.lane_min_chains > 0 ? c->knobs.lane_min_chains : 64;
-    if (n_chains < min_chains) return false;                     // a handful of chains is latency bound: k_trade runs them level-parallel
+    // A warp runs the 1 920 trades of a C1 round one after the other (6.8 ms alone), k_trade runs a null level-parallel on
+    // a CTA (0.3 ms): below ~4 groups per SM the request is latency bound and k_trade is faster (C1, measured: 12 500
+    // nulls 5.6 vs 7.3 ms, 25 000 nulls 10.4 vs 8.3 ms).  Both kernels produce the same nulls.
+    const int64_t min_chains = c->knobs.lane_min_chains > 0 ? c->knobs.lane_min_chains : (int64_t)4 * LN_W * c->sm_count;
+    if (n_chains < min_chains) return false;
     LnGeom g;
     return ln_geometry(c, (n_chains + LN_W - 1) / LN_W, &g);
 }

@@ -624,9 +624,10 @@ __global__ void k_maxk_finalize(const unsigned long long *__restrict__ best, int
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_ge, (unsigned long long)__popc(m));
 }
 
-int sdx_null_pvalue_maxk(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
-                         const int32_t *modules, int k, const double *z_obs, int64_t *n_ge, double *null_scores,
-                         double *z_obs_out) {
+// rows_src == nullptr: the nulls are generated (sdx_null_pvalue); otherwise they are the caller's n_nulls x F x wprS packed
+// feature rows, host or device memory (sdx_null_pvalue_rows: the reference's loop over null files, src/superdendrix.py:175-192)
+static int maxk_impl(sdx_ctx *c, const uint32_t *rows_src, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
+                     const int32_t *modules, int k, const double *z_obs, int64_t *n_ge, double *null_scores, double *z_obs_out) {
     SDX_REQUIRE(c, c->d_trade_obs && c->d_w, SDX_ERR_STATE, "matrix and weights must be uploaded first");
     SDX_REQUIRE(c, modules && n_ge && k >= 1 && k <= SDX_MAX_K, SDX_ERR_INVALID, "modules / n_ge / k invalid");
     SDX_REQUIRE(c, n_nulls >= 0 && chain_len >= 1, SDX_ERR_INVALID, "n_nulls must be >= 0 and chain_len >= 1");
@@ -722,11 +723,16 @@ int sdx_null_pvalue_maxk(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nu
     int launches = c->timing.launches;
     for (int64_t b0 = 0; b0 < n_nulls; b0 += B) {
         const int nb = (int)std::min<int64_t>(B, n_nulls - b0);
-        if ((rc = sdx_generate_to_device(c, seed, null0 + (uint64_t)b0, nb, n_trades, chain_len, d_a))) return rc;
-        gen_ms += c->timing.trade_ms; plan_ms += c->timing.plan_ms; launches += c->timing.launches;
-        c->timing.launches = 0;
-        if (c->rows_are_samples) rc = sdx_transpose_batch(c, d_a, S, wprF, F, d_b, wprS, nb);     // sample rows -> feature rows
-        else rc = sdx_transpose_batch(c, d_a, F, wprS, S, d_b, wprF, nb);                         // feature rows -> sample rows
+        if (rows_src) {
+            SDX_CUDA(c, cudaMemcpyAsync(d_featB, rows_src + (size_t)b0 * feat_words, sizeof(uint32_t) * feat_words * nb, cudaMemcpyDefault, c->stream));
+            rc = sdx_transpose_batch(c, d_featB, F, wprS, S, d_sampB, wprF, nb);                  // feature rows -> sample rows
+        } else {
+            if ((rc = sdx_generate_to_device(c, seed, null0 + (uint64_t)b0, nb, n_trades, chain_len, d_a))) return rc;
+            gen_ms += c->timing.trade_ms; plan_ms += c->timing.plan_ms; launches += c->timing.launches;
+            c->timing.launches = 0;
+            if (c->rows_are_samples) rc = sdx_transpose_batch(c, d_a, S, wprF, F, d_b, wprS, nb);     // sample rows -> feature rows
+            else rc = sdx_transpose_batch(c, d_a, F, wprS, S, d_b, wprF, nb);                         // feature rows -> sample rows
+        }
         if (rc) return rc;
         ++launches;
         for (int p = 0; p < P; ++p) {
@@ -751,4 +757,93 @@ int sdx_null_pvalue_maxk(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nu
     c->timing.trade_ms = gen_ms; c->timing.plan_ms = plan_ms; c->timing.launches = launches;
     c->timing.score_ms = c->timing.total_ms - gen_ms - plan_ms;
     return SDX_OK;
+}
+
+int sdx_null_pvalue_maxk(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
+                         const int32_t *modules, int k, const double *z_obs, int64_t *n_ge, double *null_scores,
+                         double *z_obs_out) {
+    return maxk_impl(c, nullptr, seed, null0, n_nulls, n_trades, chain_len, modules, k, z_obs, n_ge, null_scores, z_obs_out);
+}
+
+// ---------------------------------------------------------------------------
+// sdx_null_pvalue_rows: the null loop of src/superdendrix.py:175-192 on nulls the CALLER supplies (the reference reads
+// them from <nm><i>.tsv; here they are packed feature rows, e.g. from sdx_read_nulls_tsv): every null scored for every
+// profile in one call.  stat = fixed: one warp per (null, profile) runs score_module on the null's rows.
+// ---------------------------------------------------------------------------
+__global__ void k_score_null_rows(const uint32_t *__restrict__ feat, size_t feat_b, int wprS, int S, int P, int k, int64_t nb,
+                                  const int32_t *__restrict__ modules, const double *__restrict__ w, const uint32_t *__restrict__ mask,
+                                  const double *__restrict__ z_obs, unsigned long long *__restrict__ n_ge, double *__restrict__ scores,
+                                  int64_t n_total, int64_t b0) {
+    const int lane = threadIdx.x & 31;
+    const int64_t job = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (job >= nb * P) return;
+    const int64_t b = job / P;
+    const int p = (int)(job - b * P);
+    const SetScore sc = score_module(feat + (size_t)b * feat_b, wprS, false, modules + (size_t)p * k, k, w + (size_t)p * S, mask + (size_t)p * wprS, S, lane);
+    if (lane == 0) {
+        if (scores) scores[(size_t)p * n_total + b0 + b] = sc.W;
+        if (sc.W >= z_obs[p]) atomicAdd(&n_ge[p], 1ull);
+    }
+}
+
+__global__ void k_score_observed_rows(const uint32_t *__restrict__ feat, int wprS, int S, int P, int k, const int32_t *__restrict__ modules,
+                                      const double *__restrict__ w, const uint32_t *__restrict__ mask, double *__restrict__ z) {
+    const int lane = threadIdx.x & 31, p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= P) return;
+    const SetScore sc = score_module(feat, wprS, false, modules + (size_t)p * k, k, w + (size_t)p * S, mask + (size_t)p * wprS, S, lane);
+    if (lane == 0) z[p] = sc.W;
+}
+
+extern "C" int sdx_null_pvalue_rows(sdx_ctx *c, const uint32_t *feature_rows, int64_t n_nulls, int stat, const int32_t *modules, int k,
+                                    const double *z_obs, int64_t *n_ge, double *null_scores, double *z_obs_out) {
+    if (!c) return SDX_ERR_INVALID;
+    SDX_REQUIRE(c, c->d_feat && c->d_w, SDX_ERR_STATE, "matrix and weights must be uploaded first");
+    SDX_REQUIRE(c, modules && n_ge && k >= 1 && k <= SDX_MAX_K && n_nulls >= 0, SDX_ERR_INVALID, "modules / n_ge / k / n_nulls invalid");
+    SDX_REQUIRE(c, feature_rows || n_nulls == 0, SDX_ERR_INVALID, "feature_rows is NULL");
+    SDX_REQUIRE(c, stat == SDX_STAT_FIXED || stat == SDX_STAT_MAXK, SDX_ERR_INVALID, "unknown statistic");
+    const int F = c->F, S = c->S, wprS = c->wprS, P = c->P;
+    for (int i = 0; i < P * k; ++i) SDX_REQUIRE(c, modules[i] >= -1 && modules[i] < F, SDX_ERR_INVALID, "module feature index out of range");
+    if (stat == SDX_STAT_MAXK) return maxk_impl(c, feature_rows, 0, 0, n_nulls, 0, 1, modules, k, z_obs, n_ge, null_scores, z_obs_out);
+    LaunchTimer timer(c);
+    const size_t feat_words = (size_t)F * wprS;
+    int64_t B = (int64_t)(((size_t)1 << 30) / (sizeof(uint32_t) * feat_words + 1));      // ~1 GB of staging per batch
+    if (B < 1) B = 1;
+    if (B > n_nulls && n_nulls > 0) B = n_nulls;
+    cudaPointerAttributes at{};
+    const bool on_device = n_nulls > 0 && cudaPointerGetAttributes(&at, feature_rows) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    void *p_small, *p_rows = nullptr, *p_sc = nullptr;
+    const size_t off_z = ((sizeof(int32_t) * (size_t)P * k + 15) / 16) * 16, off_ge = off_z + sizeof(double) * P;
+    SDX_TRY(sdx_scratch(c, 14, off_ge + sizeof(unsigned long long) * P + 64, &p_small));
+    if (!on_device && n_nulls > 0) SDX_TRY(sdx_scratch(c, 11, sizeof(uint32_t) * feat_words * B + 64, &p_rows));
+    if (null_scores && n_nulls > 0) SDX_TRY(sdx_scratch(c, 15, sizeof(double) * (size_t)P * n_nulls + 64, &p_sc));
+    int32_t *d_mod = (int32_t *)p_small;
+    double *d_z = (double *)((char *)p_small + off_z);
+    unsigned long long *d_ge = (unsigned long long *)((char *)p_small + off_ge);
+    SDX_CUDA(c, cudaMemcpyAsync(d_mod, modules, sizeof(int32_t) * (size_t)P * k, cudaMemcpyHostToDevice, c->stream));
+    SDX_CUDA(c, cudaMemsetAsync(d_ge, 0, sizeof(unsigned long long) * P, c->stream));
+    if (z_obs) SDX_CUDA(c, cudaMemcpyAsync(d_z, z_obs, sizeof(double) * P, cudaMemcpyHostToDevice, c->stream));
+    else { k_score_observed_rows<<<ceil_div(P, 4), 128, 0, c->stream>>>(c->d_feat, wprS, S, P, k, d_mod, c->d_w, c->d_mask, d_z); timer.count(); }
+    for (int64_t b0 = 0; b0 < n_nulls; b0 += B) {
+        const int64_t nb = std::min<int64_t>(B, n_nulls - b0);
+        const uint32_t *d_rows = feature_rows + (size_t)b0 * feat_words;
+        if (!on_device) {
+            SDX_CUDA(c, cudaMemcpyAsync(p_rows, d_rows, sizeof(uint32_t) * feat_words * nb, cudaMemcpyHostToDevice, c->stream));
+            d_rows = (const uint32_t *)p_rows;
+        }
+        k_score_null_rows<<<(unsigned)ceil_div(nb * P, 8), 256, 0, c->stream>>>(d_rows, feat_words, wprS, S, P, k, nb, d_mod, c->d_w, c->d_mask, d_z, d_ge,
+                                                                                (double *)p_sc, n_nulls, b0);
+        timer.count();
+        SDX_CUDA(c, cudaGetLastError());
+        if (!on_device) SDX_CUDA(c, cudaStreamSynchronize(c->stream));      // the staging buffer is reused by the next batch
+    }
+    std::vector<unsigned long long> ge((size_t)P);
+    SDX_CUDA(c, cudaMemcpyAsync(ge.data(), d_ge, sizeof(unsigned long long) * P, cudaMemcpyDeviceToHost, c->stream));
+    if (z_obs_out) SDX_CUDA(c, cudaMemcpyAsync(z_obs_out, d_z, sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
+    if (null_scores && n_nulls > 0)
+        SDX_CUDA(c, cudaMemcpyAsync(null_scores, p_sc, sizeof(double) * (size_t)P * n_nulls, cudaMemcpyDeviceToHost, c->stream));
+    int rc = timer.finish();
+    for (int p = 0; p < P; ++p) n_ge[p] = (int64_t)ge[p];
+    c->timing.score_ms = c->timing.total_ms;
+    return rc;
 }

@@ -212,6 +212,25 @@ class Engine:
         return {"n_ge": n_ge, "z_obs": zout, "null_scores": scores}
 
     # -- scan / model selection / rank-sum -------------------------------------
+    def null_pvalue_rows(self, feature_rows, modules, stat: int = SDX_STAT_FIXED, z_obs=None, want_scores: bool = False):
+        """The null loop on caller-supplied nulls: feature_rows (n, F, ceil(S/32)) uint32 packed feature rows, every null
+        scored for every uploaded profile.  Returns dict(n_ge (P,), z_obs (P,), null_scores (P, n) or None)."""
+        rows = np.ascontiguousarray(feature_rows, dtype=np.uint32)
+        if rows.ndim != 3 or rows.shape[1] != self.F or rows.shape[2] != bitpack.words_for(self.S):
+            raise ValueError("feature_rows must be (n, %d, %d)" % (self.F, bitpack.words_for(self.S)))
+        mods = np.ascontiguousarray(np.atleast_2d(np.asarray(modules, dtype=np.int32)))
+        P, k = mods.shape
+        if P != self.P:
+            raise ValueError("modules must have one row per uploaded profile (%d), got %d" % (self.P, P))
+        n = rows.shape[0]
+        zin = None if z_obs is None else np.ascontiguousarray(np.atleast_1d(z_obs), dtype=np.float64)
+        n_ge = np.zeros(P, dtype=np.int64)
+        scores = np.zeros((P, n)) if want_scores else None
+        zout = np.zeros(P)
+        self._check(self._lib.sdx_null_pvalue_rows(self._ctx, _ptr(rows, C.c_uint32), n, int(stat), _ptr(mods, C.c_int32), k,
+                                                   _ptr(zin, C.c_double), _ptr(n_ge, C.c_int64), _ptr(scores, C.c_double), _ptr(zout, C.c_double)))
+        return {"n_ge": n_ge, "z_obs": zout, "null_scores": scores}
+
     def scan(self, profile: int = 0, k: int = 3, topn: int = 8, g_lo: int = 0, g_hi: int | None = None):
         """Exhaustive scan over subsets of size <= k whose smallest feature index is in [g_lo, g_hi)."""
         hits = (_capi.Hit * topn)()

@@ -19,9 +19,12 @@ Added, non-breaking flags:
                             reference's per-null ILP computes, :191).  Default max_k for k <= 3.
   --null-source generate|files   generate: nulls are produced and scored on the GPU, no files;
                             files: read ``<-nm><i>.tsv`` as the reference does (:186).
-  --mode parallel|chained|restart   generated nulls: parallel (default) = chains of 16 nulls that start from burnt-in
-                            pool states (6 dense-favouring rounds) — stationary like the reference's long chain and enough chains to
-                            fill the GPUs; chained = ONE chain from the observed matrix, exactly the reference's
+  --null-scope full|restricted   generate: Curveball on the full feature matrix, scored on the profiled samples (the
+                            reference's generator + driver, default) or on the matrix restricted to the profiled samples
+  --null-batch N            files: null files parsed and scored per library call (sdx_null_pvalue_rows)
+  --mode parallel|chained|restart   generated nulls: parallel (default) = every null one ordinary round away from a burnt-in
+                            pool state (6 dense-favouring rounds), blocks of 32 nulls sharing their row pairs — stationary like
+                            the reference's long chain and enough independent units to fill the GPUs; chained = ONE chain from the observed matrix, exactly the reference's
                             semantics (src/generate_null_matrices.py:71-74); restart = every null 5*min(S,F) trades from
                             the observed matrix (src/curveball_main.py:136; NOT mixed for dense features)
   --device N
@@ -95,9 +98,13 @@ def get_parser():
     parser.add_argument("-t", "--threads", type=int, default=-1, help="Number of threads to use ([-1] = all).")
     parser.add_argument("--null-stat", default=None, choices=["fixed", "max_k"])
     parser.add_argument("--null-source", default=None, choices=["generate", "files"])
+    parser.add_argument("--null-scope", default="full", choices=["full", "restricted"],
+                        help="generate mode: randomise the full feature matrix and restrict to the profiled samples when scoring, as the "
+                             "reference's generator + driver do [full], or randomise the matrix already restricted to the profiled samples")
     parser.add_argument("--mode", default="parallel", choices=["parallel", "chained", "restart"])
     parser.add_argument("--burn-in", type=int, default=6, help="burn-in rounds of the pool states (parallel mode)")
     parser.add_argument("--device", type=int, default=0)
+    parser.add_argument("--null-batch", type=int, default=1024, help="null files parsed and scored per library call (--null-source files)")
     return parser
 
 
@@ -186,13 +193,21 @@ def conditional_permutation_test(module, eventToCases, profile, samples, num_per
     return worst_event, worst_count
 
 
-def optimize_model(genes, samples, w, events_to_samples, samples_to_genes, args, logger=None):
+def optimize_model(genes, samples, w, events_to_samples, samples_to_genes, args, logger=None, k=None):
     """Same return tuple as src/superdendrix.py:267-357 — (z, module, best_single, cov, act_cov, act_sample, x, y, m) —
     computed by exhaustive scan over all subsets of size <= k (k <= 3).  x, y, m (Gurobi objects) are None.
-    M = {} is feasible for the ILP (z = 0), so a negative scan optimum yields the empty module."""
-    k = getattr(args, "cardinality", -1)
+    M = {} is feasible for the ILP (z = 0), so a negative scan optimum yields the empty module.
+
+    k: the cardinality bound.  The reference's optimize_model reads the MODULE-LEVEL global k (src/superdendrix.py:306),
+    which run() sets to args.cardinality (:73) and resets to len(module) before the null loop (:173) so that every null is
+    re-optimised over |M| <= len(module) (:191).  A caller that swaps this function into the reference must therefore pass
+    k=len(module) inside the null loop; k=None falls back to args.cardinality, the value of the first
+    call (:131)."""
+    if k is None:
+        k = getattr(args, "cardinality", -1)
     if not 1 <= k <= 3:
-        raise NotImplementedError("the exhaustive scan certifies k = 1..3; use the reference's Gurobi ILP for k = %r" % k)
+        raise NotImplementedError("the exhaustive scan certifies k = 1..3 (got k = %r): for the reference's default -k -1 (no cardinality "
+                                  "bound) or k > 3 call the reference's own Gurobi optimize_model, optionally warm-started by mip_start()" % (k,))
     eng = _engine()
     genes = list(genes)
     samples = list(samples)
@@ -263,12 +278,28 @@ def null_loop(genes, samples, profile, events_to_samples, module, zP, args, logg
     gidx = {g: i for i, g in enumerate(genes)}
     w_vec = np.array([profile[s] for s in samples], dtype=np.float64)
     if source == "generate":
-        # nulls of the FULL feature matrix restricted to the profiled samples afterwards is what the reference
-        # does; generating on the restricted matrix keeps the margins of the matrix that is scored.
-        eng.upload_matrix(pack_features(genes, samples, events_to_samples), len(samples))
-        eng.upload_weights(w_vec)
-        mod = np.array([[gidx[g] for g in module] + [-1] * (max(k, 1) - k)], dtype=np.int32)
         chain, burn = {"parallel": (defaults.CHAIN_LEN, args.burn_in), "chained": (max(n, 1), 0), "restart": (1, 0)}[args.mode]
+        if args.null_scope == "full":
+            # What the reference does: its generator randomises the FULL feature matrix — every sample of the file,
+            # no profile in sight (src/generate_null_matrices.py:53,62) — and the driver restricts each null to the profiled
+            # samples when it loads it (src/superdendrix.py:186, src/i_o.py:57).  Same here: the full matrix is uploaded, the
+            # profile is a weight vector with a sample mask, so the nulls keep the margins of the full matrix.
+            _, _, genes_f, samples_f, e2s_f, _ = load_mutation_data(args.mutation_matrix, None, args.gene_file, args.mutations_only,
+                                                                     args.min_freq, args.max_freq)
+            fidx = {g: i for i, g in enumerate(genes_f)}
+            missing = [g for g in module if g not in fidx]
+            if missing:                                     # frequency window applied to the full matrix dropped a module feature
+                raise ValueError("features %s of the module are not in the unrestricted matrix (-min_f / -max_f): use --null-scope restricted" % missing)
+            in_profile = np.array([s in profile for s in samples_f], dtype=bool)
+            w_full = np.array([profile.get(s, 0.0) for s in samples_f], dtype=np.float64)
+            eng.upload_matrix(pack_features(genes_f, samples_f, e2s_f), len(samples_f))
+            eng.upload_weights(w_full, in_profile[None, :])
+            mod = np.array([[fidx[g] for g in module] + [-1] * (max(k, 1) - k)], dtype=np.int32)
+        else:
+            # nulls of the matrix already restricted to the profiled samples: keeps the margins of the matrix that is scored
+            eng.upload_matrix(pack_features(genes, samples, events_to_samples), len(samples))
+            eng.upload_weights(w_vec)
+            mod = np.array([[gidx[g] for g in module] + [-1] * (max(k, 1) - k)], dtype=np.int32)
         eng.set_burn_in(burn, defaults.POOL_SIZE)
         eng.set_pair_group(defaults.PAIR_GROUP if args.mode == "parallel" else 1)
         res = eng.null_pvalue(args.random_seed, 0, n, mod, chain_len=chain, stat=stat, z_obs=np.array([zP]), want_scores=True)
@@ -276,21 +307,19 @@ def null_loop(genes, samples, profile, events_to_samples, module, zP, args, logg
     # files: <-nm><i>.tsv, restricted to the profiled samples as src/superdendrix.py:186 does.  Read in batches by the
     # library's multi-threaded parser straight into packed rows over this run's sample / event tables (events with no
     # carrier among the profiled samples are all-zero rows, which is what "missing from p_genes" means for W).
+    # every batch of parsed nulls is scored in ONE library call (sdx_null_pvalue_rows): fixed = the module on the null,
+    # max_k = the per-null optimum over |M| <= len(module) that the reference's ILP returns (src/superdendrix.py:173,191)
+    eng.upload_matrix(pack_features(genes, samples, events_to_samples), len(samples))
+    eng.upload_weights(w_vec)
+    mod = np.array([[gidx[g] for g in module] + [-1] * (max(k, 1) - k)], dtype=np.int32)
     scores = []
     no_better = 0
-    mod_idx = [gidx[g] for g in module]
-    for i0 in range(0, n, 256):
-        rows, _ = read_nulls_tsv(args.null_matrices, i0, min(256, n - i0), samples, genes)
-        for r in rows:
-            eng.upload_matrix(r, len(samples))
-            eng.upload_weights(w_vec)
-            if stat == SDX_STAT_MAXK:
-                p_z = max(float(eng.scan(0, k, 1)["W"][0]), 0.0)
-            else:
-                p_z = float(eng.score_sets(np.array([mod_idx + [-1] * (max(k, 1) - k)], dtype=np.int32))["W"][0])
-            scores.append(p_z)
-            no_better += p_z >= zP
-    return int(no_better), n, np.array(scores)
+    for i0 in range(0, n, args.null_batch):
+        rows, _ = read_nulls_tsv(args.null_matrices, i0, min(args.null_batch, n - i0), samples, genes)
+        res = eng.null_pvalue_rows(rows, mod, stat=stat, z_obs=np.array([zP]), want_scores=True)
+        scores.append(res["null_scores"][0])
+        no_better += int(res["n_ge"][0])
+    return int(no_better), n, np.concatenate(scores) if scores else np.zeros(0)
 
 
 def run(args):

@@ -19,6 +19,7 @@ pins are made here from the reference's own functions:
   loader.json           src/i_o.py:18-88 on a small TSV with every filter.
   generator/            src/generate_null_matrices.py run as a subprocess.
   nulldist.npz          null distribution of SuperW of a fixed module over 2000 nulls of the reference's own chain.
+  nulldist_c0.npz       the same on the bench workload (770 x ~400, bench module): 4000 nulls of the reference's chain.
 
 Nothing from the reference is copied into the repo: only inputs and outputs.
 """
@@ -339,9 +340,44 @@ def make_nulldist():
     print("nulldist.npz", n, "nulls, mean W %.4f sd %.4f" % (scores.mean(), scores.std()))
 
 
+def make_nulldist_c0():
+    """The same on the BENCH workload (BASELINE configs[0] / [1]: 770 x ~400 BRAF-shape matrix, fixed k=3 module): 4 000
+    consecutive nulls of the reference's own chain (src/generate_null_matrices.py:71-74), SuperW of the bench module on each.
+    The GPU test compares the shipped defaults (burn-in pool, one round per null, blocks of 32 nulls sharing their pairs)
+    with the stationary part of this chain; the first nulls of the chain are kept so the test can also see the relaxation."""
+    dense, samples, features = synth.feature_matrix(770, 400, seed=20)
+    S, F = dense.shape
+    w = synth.weights(S, 1, seed=3)[0]
+    module = synth.pick_module(dense, 3)
+    profile = {samples[i]: float(w[i]) for i in range(S)}
+    random.seed(1764)
+    np.random.seed(1764)
+    mat = dense.astype(np.float64)
+    presence = ref_cb.find_presences(mat)
+    n = 4000
+    scores = np.zeros(n)
+    shared = np.zeros(n, dtype=np.int32)
+    feat_shared = np.zeros((n, 3), dtype=np.int32)
+    for i in range(n):
+        null = ref_cb.curve_ball(mat, presence)
+        cases = [set(samples[r] for r in np.flatnonzero(null[:, g])) for g in module]
+        scores[i] = ref_sd.SuperW(cases, profile, samples)
+        both = (null != 0) & (dense != 0)
+        shared[i] = int(both.sum())
+        feat_shared[i] = [int(both[:, g].sum()) for g in module]
+    obs_cases = [set(samples[r] for r in np.flatnonzero(dense[:, g])) for g in module]
+    np.savez_compressed(os.path.join(HERE, "nulldist_c0.npz"), module=module, scores=scores, shared=shared, feat_shared=feat_shared,
+                        z_obs=ref_sd.SuperW(obs_cases, profile, samples), python=platform.python_version())
+    print("nulldist_c0.npz", n, "nulls, mean W %.4f sd %.4f, p %.4f" % (scores[200:].mean(), scores[200:].std(),
+                                                                        (scores[200:] >= ref_sd.SuperW(obs_cases, profile, samples)).mean()))
+
+
 if __name__ == "__main__":
     if "--nulldist-only" in sys.argv:
         make_nulldist()
+        sys.exit(0)
+    if "--nulldist-c0-only" in sys.argv:
+        make_nulldist_c0()
         sys.exit(0)
     make_curveball()
     make_superw()
@@ -351,3 +387,4 @@ if __name__ == "__main__":
     make_loader()
     make_generator()
     make_nulldist()
+    make_nulldist_c0()

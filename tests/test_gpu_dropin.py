@@ -179,12 +179,12 @@ def _write_case(tmp_path, S=120, F=40, seed=3):
     return dense, samples, features, w, mut, prof
 
 
-@pytest.mark.parametrize("stat", ["fixed", "max_k"])
-def test_driver_end_to_end_against_oracle(tmp_path, stat):
+@pytest.mark.parametrize("stat,scope", [("fixed", "restricted"), ("max_k", "restricted"), ("fixed", "full"), ("max_k", "full")])
+def test_driver_end_to_end_against_oracle(tmp_path, stat, scope):
     dense, samples, features, w, mut, prof = _write_case(tmp_path)
     out = tmp_path / "res.tsv"
     args = sd.get_parser().parse_args(["-m", str(mut), "-T", str(prof), "-Tc", "GENE1", "-k", "3", "-cp", "200", "-p", "64",
-                                       "-o", str(out), "-d", "positive", "--null-stat", stat, "-rs", "9"])
+                                       "-o", str(out), "-d", "positive", "--null-stat", stat, "-rs", "9", "--null-scope", scope])
     module = sd.run(args)
     keep = ~np.isnan(w[0])
     kept = {s for s, k_ in zip(samples, keep) if k_}
@@ -203,14 +203,25 @@ def test_driver_end_to_end_against_oracle(tmp_path, stat):
     feats = sorted(names.index(g) for g in module)
     zP, cov, _, _ = oracle.score_set(rows, d.shape[0], feats, wv)
     assert abs(last["zP"] - zP) <= 1e-9 * np.abs(wv).sum()
-    # null loop: same nulls through the oracle
-    obs = rows_of(d)
+    # null loop: same nulls through the oracle.  restricted: Curveball on the matrix of the profiled samples; full (default, what
+    # the reference's generator + driver do, src/generate_null_matrices.py:53 + src/superdendrix.py:186): Curveball on the matrix of
+    # ALL samples, every null restricted to the profiled samples before it is scored
+    if scope == "full":
+        _, _, names_f, smp_f, _, s2g_f = i_o.load_mutation_data(str(mut), None)
+        d_gen = i_o.dense_matrix(names_f, smp_f, s2g_f)
+        col_of = [smp_f.index(s_) for s_ in smp]
+        feats = sorted(names_f.index(g) for g in module)           # a null may give a feature carriers among the profiled samples that it
+    else:                                                          # did not have: the per-null optimum ranges over ALL features of the file
+        d_gen = d
+    obs = rows_of(d_gen)
     nulls, _ = oracle.curveball_nulls(obs, 9, 0, 64, 5 * obs.shape[0], defaults.CHAIN_LEN, burn=defaults.BURN_ROUNDS, pool_size=defaults.POOL_SIZE,
                                       pair_group=defaults.PAIR_GROUP)     # --mode parallel (default)
-    ras = d.shape[1] >= d.shape[0]
+    ras = d_gen.shape[1] >= d_gen.shape[0]
     sc = []
     for m in nulls:
-        fr = bitpack.pack_rows(bitpack.unpack_rows(m, max(d.shape)).T) if ras else m
+        fr = bitpack.pack_rows(bitpack.unpack_rows(m, max(d_gen.shape)).T) if ras else m
+        if scope == "full":                                        # feature rows of the driver's genes over the profiled samples
+            fr = bitpack.pack_rows(bitpack.unpack_rows(fr, d_gen.shape[0])[:, col_of])
         if stat == "fixed":
             sc.append(oracle.score_set(fr, d.shape[0], feats, wv)[0])
         else:                                                      # re-optimised with k = len(module), as :173,191
@@ -246,6 +257,146 @@ def test_driver_reads_null_files_like_the_reference(tmp_path):
         sc.append(refport.super_w([e2s[g] for g in module if g in e2s], profile))
     assert np.allclose(last["null_scores"], sc, rtol=0, atol=1e-9 * np.abs(w[1]).sum())
     assert float(open(out).read().splitlines()[1].split("\t")[6]) == float((np.array(sc) >= last["zP"]).sum()) / 12
+
+
+def test_driver_reads_null_files_max_k_in_batches(tmp_path):
+    """--null-source files with the reference-faithful statistic: every null file re-optimised over |M| <= len(module)
+    (src/superdendrix.py:173,191), the files scored in batches by sdx_null_pvalue_rows"""
+    dense, samples, features, w, mut, prof = _write_case(tmp_path, S=90, F=30, seed=8)
+    nm = tmp_path / "rand_mat"
+    nm.mkdir()
+    gnm.main(["-m", str(mut), "-p", "10", "-o", str(nm) + "/", "-rs", "4"])
+    out = tmp_path / "res.tsv"
+    args = sd.get_parser().parse_args(["-m", str(mut), "-nm", str(nm) + "/", "-T", str(prof), "-Tc", "GENE1", "-k", "3", "-cp", "-1",
+                                       "-p", "10", "-o", str(out), "-d", "positive", "--null-stat", "max_k", "--null-batch", "4"])
+    module = sd.run(args)
+    last = sd.run.last
+    keep = ~np.isnan(w[0])
+    kept = [s for s, k_ in zip(samples, keep) if k_]
+    _, _, names, smp, _, _ = i_o.load_mutation_data(str(mut), set(kept))
+    wv = w[0][keep]
+    want = []
+    for i in range(10):
+        _, _, _, _, e2s, _ = i_o.load_mutation_data(str(nm / ("%d.tsv" % i)), set(kept))
+        d = np.array([[1 if s in e2s.get(g, ()) else 0 for g in names] for s in smp], dtype=np.uint8)
+        want.append(max(float(oracle.scan(bitpack.pack_rows(d.T), len(smp), wv, len(module), 1)[0][0]), 0.0))
+    assert np.allclose(last["null_scores"], want, rtol=0, atol=1e-9 * np.abs(wv).sum())
+
+
+def test_null_pvalue_rows_equals_per_null_scoring():
+    """sdx_null_pvalue_rows: a batch of caller-supplied nulls for several profiles in one call == score_sets / scan per null"""
+    dense, _, _ = synth.feature_matrix(200, 60, seed=2)
+    S, F = dense.shape
+    w = synth.weights(S, 3, seed=6)
+    mask = np.ones((3, S), dtype=bool)
+    mask[2, ::5] = False
+    modules = np.array([[0, 1, 2], [3, 4, -1], [7, -1, -1]], dtype=np.int32)
+    with Engine(0) as eng:
+        eng.upload_dense(dense)
+        eng.upload_weights(w, mask)
+        nulls, _ = eng.curveball(5, 0, 40, chain_len=40)                    # feature rows (F < S)
+        res = eng.null_pvalue_rows(nulls, modules, want_scores=True)
+        mk = eng.null_pvalue_rows(nulls[:12], modules, stat=1, want_scores=True)
+        z_fixed, z_maxk = res["z_obs"].copy(), mk["z_obs"].copy()
+        per_null_fixed = np.zeros((3, 40)); per_null_maxk = np.zeros((3, 12))
+        for i, rows in enumerate(nulls):
+            eng.upload_matrix(rows, S)
+            eng.upload_weights(w, mask)
+            per_null_fixed[:, i] = eng.score_sets(modules, np.arange(3, dtype=np.int32))["W"]
+            if i < 12:
+                for p in range(3):
+                    per_null_maxk[p, i] = max(float(eng.scan(p, int((modules[p] >= 0).sum()), 1)["W"][0]), 0.0)
+    assert np.array_equal(res["null_scores"], per_null_fixed)
+    assert np.allclose(mk["null_scores"], per_null_maxk, rtol=0, atol=1e-9 * np.abs(w).sum())
+    for p in range(3):
+        assert int(res["n_ge"][p]) == int((per_null_fixed[p] >= z_fixed[p]).sum())
+        assert int(mk["n_ge"][p]) == int((mk["null_scores"][p] >= z_maxk[p]).sum())
+
+
+def test_optimize_model_k_override_matches_the_drivers_null_statistic(tmp_path):
+    """the reference's null loop calls optimize_model with the global k = len(module)
+    (src/superdendrix.py:173,191); the replacement takes k=len(module) and then returns the driver's max_k statistic"""
+    import argparse
+    dense, samples, features, w, mut, prof = _write_case(tmp_path, S=90, F=30, seed=8)
+    keep = ~np.isnan(w[0])
+    kept = {s for s, k_ in zip(samples, keep) if k_}
+    profile = {s: float(w[0][i]) for i, s in enumerate(samples) if keep[i]}
+    _, _, genes, smp, e2s, s2g = i_o.load_mutation_data(str(mut), kept)
+    args = argparse.Namespace(cardinality=3)
+    z3 = sd.optimize_model(genes, smp, profile, e2s, s2g, args)[0]
+    z2 = sd.optimize_model(genes, smp, profile, e2s, s2g, args, k=2)[0]
+    rows = bitpack.pack_rows(i_o.dense_matrix(genes, smp, s2g).T)
+    wv = np.array([profile[s] for s in smp])
+    assert abs(z3 - max(oracle.scan(rows, len(smp), wv, 3, 1)[0][0], 0.0)) <= 1e-9 * np.abs(wv).sum()
+    assert abs(z2 - max(oracle.scan(rows, len(smp), wv, 2, 1)[0][0], 0.0)) <= 1e-9 * np.abs(wv).sum()
+    assert z2 <= z3 + 1e-12
+    with pytest.raises(NotImplementedError):
+        sd.optimize_model(genes, smp, profile, e2s, s2g, argparse.Namespace(cardinality=-1))
+
+
+def test_fixed_query_cli_like_utils_compute_p_value(tmp_path):
+    """utils/compute_p_value.py -q a,b,c: W of the query, Curveball p-value of the FIXED set (configs[0]), rank-sum p"""
+    import scipy.stats
+
+    from superdendrix_b200 import compute_p_value as cpv
+    dense, samples, features, w, mut, prof = _write_case(tmp_path, S=120, F=40, seed=3)
+    order = np.argsort(-dense.sum(0), kind="stable")
+    query = [features[order[1]], features[order[2]], features[order[5]]]
+    out = tmp_path / "q.tsv"
+    args = cpv.get_parser().parse_args(["-m", str(mut), "-T", str(prof), "-Tc", "GENE2", "-q", ",".join(query), "-cp", "-1", "-p", "96",
+                                        "-o", str(out), "-d", "positive", "--null-stat", "fixed", "--null-scope", "restricted", "-rs", "5"])
+    module = cpv.run(args)
+    last = cpv.run.last
+    assert sorted(module) == sorted(query)
+    # W of the query = the reference's SuperW (oracle/refport.py restates src/superdendrix.py:387-391)
+    profile = {s: float(w[1][i]) for i, s in enumerate(samples)}
+    cases = [set(samples[i] for i in np.flatnonzero(dense[:, features.index(g)])) for g in query]
+    assert abs(last["zP"] - refport.super_w(cases, profile)) <= 1e-9 * np.abs(w[1]).sum()
+    # the nulls of the fixed set through the oracle (defaults of --mode parallel)
+    _, _, names, smp, _, s2g = i_o.load_mutation_data(str(mut), set(samples))
+    d = i_o.dense_matrix(names, smp, s2g)
+    obs = rows_of(d)
+    nulls, _ = oracle.curveball_nulls(obs, 5, 0, 96, 5 * obs.shape[0], defaults.CHAIN_LEN, burn=defaults.BURN_ROUNDS, pool_size=defaults.POOL_SIZE,
+                                      pair_group=defaults.PAIR_GROUP)
+    feats = sorted(names.index(g) for g in query)
+    ras = d.shape[1] >= d.shape[0]
+    sc = [oracle.score_set(bitpack.pack_rows(bitpack.unpack_rows(m_, max(d.shape)).T) if ras else m_, d.shape[0], feats, w[1])[0] for m_ in nulls]
+    assert np.allclose(last["null_scores"], sc, rtol=0, atol=1e-9 * np.abs(w[1]).sum())
+    assert float(last["p_value"]) == float((np.array(sc) >= last["zP"]).sum()) / 96
+    union = dense[:, [features.index(g) for g in query]].any(axis=1)
+    assert abs(last["ranksum_pval"] - scipy.stats.ranksums(w[1][union], w[1][~union])[1]) < 1e-12
+    head, row = open(out).read().splitlines()
+    assert head.split("\t")[:5] == ["target", "aberrations", "#sample", "scores", "p-value"] and row.split("\t")[0] == "GENE2"
+
+
+def test_ranksum_table_cli_like_utils_compute_ranksum_pval_iter(tmp_path):
+    """utils/compute_ranksum_pval_iter.py: rank-sum and Welch t p-values for every row of a results table"""
+    import scipy.stats
+
+    from superdendrix_b200 import compute_ranksum_pval_iter as cri
+    dense, samples, features, w, mut, prof = _write_case(tmp_path, S=120, F=40, seed=3)
+    w = np.nan_to_num(w, nan=0.3)
+    synth.write_profile_tsv(str(prof), samples, w, ["GENE1", "GENE2"])
+    order = np.argsort(-dense.sum(0), kind="stable")
+    table = tmp_path / "results.tsv"
+    rows = [("GENE1", [features[order[0]], features[order[3]]], "positive"), ("GENE2_x", [features[order[2]]], "negative"),
+            ("GENE9", [features[order[1]]], "positive")]
+    with open(table, "w") as fh:
+        fh.write("\t".join("c%d" % i for i in range(13)) + "\n")
+        for t, mod, dr in rows:
+            f = ["."] * 13
+            f[1], f[2], f[12] = t, ",".join(mod), dr
+            fh.write("\t".join(f) + "\n")
+    out = tmp_path / "rs.tsv"
+    res = cri.run(cri.get_parser().parse_args(["-m", str(mut), "-q", str(table), "-T", str(prof), "-o", str(out)]))
+    assert res[2][3] == "FALSE" and res[2][-1] == "NA"
+    for (t, mod, dr), line in zip(rows[:2], res[:2]):
+        col = 0 if t.startswith("GENE1") else 1
+        vals = (-1.0 if dr == "negative" else 1.0) * w[col]
+        union = dense[:, [features.index(g) for g in mod]].any(axis=1)
+        assert abs(float(line[5]) - scipy.stats.ranksums(vals[union], vals[~union])[1]) < 1e-12
+        assert abs(float(line[6]) - scipy.stats.ttest_ind(vals[union], vals[~union], equal_var=False, nan_policy="omit")[1]) < 1e-10
+    assert open(out).read().splitlines()[0] == "profile\tfeatures\tdirection\tprofile_is_in_data\tfeature_is_in_data\tranksum_pval\tt_pval"
 
 
 def test_too_many_bad_profile_values_aborts_like_the_reference(tmp_path):

@@ -167,3 +167,60 @@ def test_c1_defaults_p_value_is_independent_of_the_kernel_and_of_batching(monkey
         b = eng.null_pvalue(1764, lo1, hi1 - lo1, module, chain_len=defaults.CHAIN_LEN, z_obs=one["z_obs"])
     assert int(one["n_ge"][0]) == int(a["n_ge"][0]) + int(b["n_ge"][0])
     assert 0.3 < one["p"][0] < 0.95
+
+
+def _autocorr_inflation(x, max_lag=200):
+    """integrated autocorrelation time 1 + 2 sum rho_k of a chain (truncated at the first non-positive estimate)"""
+    x = np.asarray(x, dtype=np.float64) - np.mean(x)
+    v = float(np.dot(x, x)) / len(x)
+    tau = 1.0
+    for k in range(1, min(max_lag, len(x) // 4)):
+        r = float(np.dot(x[:-k], x[k:])) / (len(x) - k) / v
+        if r <= 0:
+            break
+        tau += 2 * r
+    return tau
+
+
+def test_c0_shipped_defaults_sample_the_reference_chains_null_distribution():
+    """North star (3) on the bench workload: tests/golden/nulldist_c0.npz holds SuperW of the bench module on 4 000
+    CONSECUTIVE nulls of the reference's own chain (src/generate_null_matrices.py:71-74 driving src/curveball.py:17-40 with
+    CPython's random; made by tests/golden/make_golden.py).  The shipped defaults — burn-in pool of 1 472 states, 6
+    dense-favouring rounds, every null ONE ordinary round from a pool state, blocks of 32 nulls sharing their row pairs, the
+    lane kernel — must sample the same stationary distribution: p-value, mean, spread and exceedance probabilities at three
+    reference quantiles within Monte-Carlo error.  The reference series is one Markov chain: its error is inflated by its
+    integrated autocorrelation time; ours by the nulls that share a pool state (68 per state at 100 000 nulls)."""
+    from conftest import load_npz
+    from superdendrix_b200 import dist
+    z = load_npz("nulldist_c0.npz")
+    ref_all, z_obs = z["scores"], float(z["z_obs"])
+    ref = ref_all[200:]                                      # the chain's first nulls still remember the observed matrix
+    dense, _, _ = synth.feature_matrix(770, 400, seed=20)
+    w = synth.weights(dense.shape[0], 1, seed=3)
+    module = synth.pick_module(dense, 3)
+    assert np.array_equal(module, z["module"])
+    n = 100_000
+    with Engine(0) as eng:
+        eng.upload_dense(dense)
+        eng.upload_weights(w)
+        eng.set_pair_group(defaults.PAIR_GROUP)
+        eng.set_burn_in(defaults.BURN_ROUNDS, defaults.POOL_SIZE)
+        res = eng.null_pvalue(1764, 0, n, module[None, :].astype(np.int32), chain_len=defaults.CHAIN_LEN, want_scores=True)
+        assert eng.timing()["plan_ms"] == 0.0               # the lane kernel ran
+    sc = res["null_scores"][0]
+    assert abs(res["z_obs"][0] - z_obs) <= 1e-9 * np.abs(w).sum()
+    tau = _autocorr_inflation(ref)
+    # ours: nulls of one pool state are one round apart from it; treat each pool state's 68 nulls as one cluster
+    per_state = sc[: (n // defaults.POOL_SIZE) * defaults.POOL_SIZE].reshape(-1, defaults.POOL_SIZE)        # null i starts from state i % pool
+    cluster_means = per_state.mean(axis=0)
+    se_ours_mean = cluster_means.std(ddof=1) / np.sqrt(defaults.POOL_SIZE)
+    se_mean = np.sqrt(ref.var() * tau / len(ref) + se_ours_mean ** 2)
+    assert abs(sc.mean() - ref.mean()) < 4.5 * se_mean
+    assert 0.9 < sc.std() / ref.std() < 1.1
+    for thr in [z_obs] + [float(np.quantile(ref, q)) for q in (0.1, 0.5, 0.9)]:
+        p_ref, p_new = float((ref >= thr).mean()), float((sc >= thr).mean())
+        cl = (per_state >= thr).mean(axis=0)
+        se = np.sqrt(p_ref * (1 - p_ref) * tau / len(ref) + cl.var(ddof=1) / defaults.POOL_SIZE)
+        assert abs(p_ref - p_new) < 4.5 * se, (thr, p_ref, p_new, se)
+    # the chain's own relaxation is visible in the fixture: its first nulls are closer to the observed score than to the stationary mean
+    assert abs(ref_all[:3].mean() - z_obs) < abs(ref_all[:3].mean() - ref.mean())
