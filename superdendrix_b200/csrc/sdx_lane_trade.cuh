@@ -412,9 +412,10 @@ LN_HD void ln_bl_phase2(uint32_t *D, int nw, const uint16_t *Lst, int sl, uint16
 // ---------------------------------------------------------------------------------------------------------------
 // One trade of one lane.  Staged lists: inA / inB as they arrive from the group state, outA / outB the new lists.  The
 // bit-packed row of a bit-packed x list trade is staged in X and updated there; the two rows of a bit-packed x
-// bit-packed trade are read and written in place through gA / gB (the lane's column of the row in the group state).
-// Scratch, all at stride 32 and already offset to the lane: PF4 ((nw + 3) / 4 + 1 u16), RK / PK (TS u16 each; the kernel
-// puts them into the list buffers the bit-packed row does not use), C (nw + 2 u32 words of the group state).
+// bit-packed trade are read and written in place in `state` (the lane's column of the row in the group state).
+// Scratch, all at stride 32 and already offset to the lane: PF4 ((nw + 3) / 4 + 1 u16); RK / PK (TS u16 each) live in
+// the list buffers the bit-packed row does not use (its input buffer, its output buffer); C = nw + 2 u32 words of the
+// group state at c_off.  Pointers that only the rare kinds need are formed inside their branches (registers).
 // Phase 1 only reads the rows (and writes the list sentinels), phase 2 writes; the kernel waits for the previous bulk
 // store between the two.
 // ---------------------------------------------------------------------------------------------------------------
@@ -426,8 +427,8 @@ struct LnTrade {
 };
 
 template <bool M64>
-LN_HD void ln_trade_phase1(LnTrade<M64> &tr, uint2 dA, uint2 dB, uint16_t *inA, uint16_t *inB, uint32_t *gA, uint32_t *gB, const uint32_t *X,
-                           uint16_t *PF, uint16_t *RK, uint16_t *PK, uint32_t *C, int nw, const LnRng &g, uint32_t &kmax) {
+LN_HD void ln_trade_phase1(LnTrade<M64> &tr, uint2 dA, uint2 dB, uint16_t *inA, uint16_t *inB, uint16_t *outA, uint16_t *outB, uint8_t *state,
+                           uint32_t c_off, int lane, const uint32_t *X, uint16_t *PF, int nw, const LnRng &g, uint32_t &kmax) {
     const int sa = (int)ln_size(dA), sb = (int)ln_size(dB);
     const bool ba = ln_is_bits(dA), bb = ln_is_bits(dB);
     const int kind = ba == bb ? (ba ? 2 : 0) : 1;        // 0: list x list, 1: bit-packed x list, 2: bit-packed x bit-packed
@@ -442,9 +443,9 @@ LN_HD void ln_trade_phase1(LnTrade<M64> &tr, uint2 dA, uint2 dB, uint16_t *inA, 
         const uint32_t c = ln_ll_common(inA, sa, inB, sb);
         La = (uint32_t)sa - c; Lb = (uint32_t)sb - c;
     } else if (kind == 2) {
-        ln_bb_count(gA, gB, nw, La, Lb);
-    } else {
-        const uint32_t c = ln_bl_prepare(X, nw, ba ? inB : inA, ba ? sb : sa, PF, RK, tr.deal.cmn);
+        ln_bb_count(reinterpret_cast<const uint32_t *>(state + dA.x) + lane, reinterpret_cast<const uint32_t *>(state + dB.x) + lane, nw, La, Lb);
+    } else {                                            // RK: the list buffer the bit-packed row does not use
+        const uint32_t c = ln_bl_prepare(X, nw, ba ? inB : inA, ba ? sb : sa, PF, ba ? inA : inB, tr.deal.cmn);
         La = (uint32_t)sa - c; Lb = (uint32_t)sb - c;
     }
     const uint32_t n = La + Lb;
@@ -456,6 +457,8 @@ LN_HD void ln_trade_phase1(LnTrade<M64> &tr, uint2 dA, uint2 dB, uint16_t *inA, 
     tr.toA = LnMask<M64>::fill(Lb == 0);
     kmax = LN_WARP_MAX(k);
     if (kmax == 0) return;                              // warp-uniform: nobody trades
+    uint32_t *C = reinterpret_cast<uint32_t *>(state + c_off) + lane;      // rank mask of a bit-packed x bit-packed trade
+    uint16_t *PK = ba ? outA : outB;                    // picks of a bit-packed x list trade: the output buffer of the bit-packed row
     if (kind == 2) {
 #pragma unroll 1
         for (int w = 0; w < nw + 2; ++w) C[w * LN_W] = 0u;
@@ -501,14 +504,15 @@ LN_HD void ln_trade_phase1(LnTrade<M64> &tr, uint2 dA, uint2 dB, uint16_t *inA, 
 }
 
 template <bool M64>
-LN_HD void ln_trade_phase2(const LnTrade<M64> &tr, uint2 dA, uint2 dB, const uint16_t *inA, const uint16_t *inB, uint16_t *outA, uint16_t *outB,
-                           uint32_t *gA, uint32_t *gB, uint32_t *X, const uint16_t *PF, const uint16_t *RK, uint16_t *PK, const uint32_t *C,
-                           int nw, uint32_t kmax) {
+LN_HD void ln_trade_phase2(const LnTrade<M64> &tr, uint2 dA, uint2 dB, uint16_t *inA, uint16_t *inB, uint16_t *outA, uint16_t *outB,
+                           uint8_t *state, uint32_t c_off, int lane, uint32_t *X, const uint16_t *PF, int nw, uint32_t kmax) {
     const int sa = (int)ln_size(dA), sb = (int)ln_size(dB);
     const bool ba = ln_is_bits(dA), bb = ln_is_bits(dB);
     if (!ba && !bb) ln_ll_phase2<M64>(inA, sa, inB, sb, outA, outB, tr.toA);
-    else if (ba && bb) ln_bb_phase2(gA, gB, nw, C, tr.deal, tr.small_is_a);
-    else ln_bl_phase2(X, nw, ba ? inB : inA, ba ? sb : sa, ba ? outB : outA, PF, RK, PK, tr.deal, kmax);
+    else if (ba && bb)
+        ln_bb_phase2(reinterpret_cast<uint32_t *>(state + dA.x) + lane, reinterpret_cast<uint32_t *>(state + dB.x) + lane, nw,
+                     reinterpret_cast<const uint32_t *>(state + c_off) + lane, tr.deal, tr.small_is_a);
+    else ln_bl_phase2(X, nw, ba ? inB : inA, ba ? sb : sa, ba ? outB : outA, PF, ba ? inA : inB, ba ? outA : outB, tr.deal, kmax);
 }
 
 // entry of the trade schedule: rows a, b (14 bits each) and, in bits 28..30, whether the trade shares a row with the

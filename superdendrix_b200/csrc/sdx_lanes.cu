@@ -179,8 +179,6 @@ __global__ void __maxnreg__(REGS) k_trade_lanes(const __grid_constant__ LaneArgs
         const uint64_t c_base = p.chain0 + (uint64_t)g * LN_W;
         const uint64_t my_chain = c_base + (uint64_t)lane;
         uint8_t *state = p.states + (size_t)g * p.gsb;
-        uint32_t *C = reinterpret_cast<uint32_t *>(state + p.c_off) + lane;
-        double *PP = reinterpret_cast<double *>(state + p.pp_off) + lane, *PN = PP + 32 * LN_W;
         if (p.seg_off == 0) {
             if (p.src_groups) {                             // the 32 start states are one block of the pool: copy it
                 const uint4 *src = reinterpret_cast<const uint4 *>(p.src_states + (size_t)((c_base / LN_W) % (uint64_t)p.n_src) * p.rows_bytes);
@@ -248,10 +246,8 @@ __global__ void __maxnreg__(REGS) k_trade_lanes(const __grid_constant__ LaneArgs
 
                 uint8_t *sA8 = wbase + (size_t)(st ? 4 : 0) * SLOT;
                 uint16_t *inA = reinterpret_cast<uint16_t *>(sA8) + lane, *inB = reinterpret_cast<uint16_t *>(sA8 + SLOT) + lane;
-                uint32_t *gA = reinterpret_cast<uint32_t *>(state + dA.x) + lane, *gB = reinterpret_cast<uint32_t *>(state + dB.x) + lane;
                 // a bit-packed x list trade keeps RK in the list buffer the bit-packed row does not use and PK in its output
                 // buffer: that one must not be under a bulk store any more
-                uint16_t *RK = ba ? inA : inB, *PK = ba ? outA : outB;
                 if (use_x) {
                     if (lane == 0) bulk_wait_read<0>();
                     __syncwarp();
@@ -259,12 +255,12 @@ __global__ void __maxnreg__(REGS) k_trade_lanes(const __grid_constant__ LaneArgs
                 const LnRng rng{&p.keys, null_id, (uint32_t)t};
                 uint32_t kmax = 0;
                 LnTrade<M64> tr;
-                ln_trade_phase1<M64>(tr, dA, dB, inA, inB, gA, gB, X, PF, RK, PK, C, nw, rng, kmax);
+                ln_trade_phase1<M64>(tr, dA, dB, inA, inB, outA, outB, state, p.c_off, lane, X, PF, nw, rng, kmax);
                 // the output buffers are free once the previous bulk store has read them; every store but the latest is complete
                 if (lane == 0) { bulk_wait<1>(); bulk_wait_read<0>(); }
                 __syncwarp();
                 if (kmax != 0) {
-                    ln_trade_phase2<M64>(tr, dA, dB, inA, inB, outA, outB, gA, gB, X, PF, RK, PK, C, nw, kmax);
+                    ln_trade_phase2<M64>(tr, dA, dB, inA, inB, outA, outB, state, p.c_off, lane, X, PF, nw, kmax);
                     applied += tr.deal.go ? 1u : 0u;
                 }
                 fence_proxy_async_smem();                   // bulk stores read, and the next bulk load overwrites, what the lanes just wrote
@@ -308,6 +304,7 @@ __global__ void __maxnreg__(REGS) k_trade_lanes(const __grid_constant__ LaneArgs
             if (emit && p.applied) p.applied[null_id - p.null_lo] = applied;
             if (emit && p.out_rows) ln_emit_rows(state, lane, s_desc, R, nw, p.out_rows + (size_t)(null_id - p.null_lo) * R * nw);
             if (p.sc.n_profiles > 0) {
+                double *PP = reinterpret_cast<double *>(state + p.pp_off) + lane, *PN = PP + 32 * LN_W;
                 for (int pr = 0; pr < p.sc.n_profiles; ++pr) {
                     double W = 0.0;
                     if (emit)

@@ -97,16 +97,16 @@ extern "C" int lane_host_run(const uint32_t *start, int n_start, int R, int nw, 
                 uint16_t *pinA, *pinB, *poA, *poB, *PF, *RK, *PK; uint32_t *gA, *gB, *X;
                 ptrs(lane, pinA, pinB, poA, poB, gA, gB, PF, RK, PK, X);
                 uint32_t km = 0;
-                if (m64) ln_trade_phase1<true>(tr64[lane], dA, dB, pinA, pinB, gA, gB, X, PF, RK, PK, C + lane, nw, g, km);
-                else ln_trade_phase1<false>(tr32[lane], dA, dB, pinA, pinB, gA, gB, X, PF, RK, PK, C + lane, nw, g, km);
+                if (m64) ln_trade_phase1<true>(tr64[lane], dA, dB, pinA, pinB, poA, poB, state.data(), lay.c_off, lane, X, PF, nw, g, km);
+                else ln_trade_phase1<false>(tr32[lane], dA, dB, pinA, pinB, poA, poB, state.data(), lay.c_off, lane, X, PF, nw, g, km);
                 if (km > kmax) kmax = km;
             }
             if (kmax != 0) {
                 for (int lane = 0; lane < LN_W; ++lane) {
                     uint16_t *pinA, *pinB, *poA, *poB, *PF, *RK, *PK; uint32_t *gA, *gB, *X;
                     ptrs(lane, pinA, pinB, poA, poB, gA, gB, PF, RK, PK, X);
-                    if (m64) ln_trade_phase2<true>(tr64[lane], dA, dB, pinA, pinB, poA, poB, gA, gB, X, PF, RK, PK, C + lane, nw, kmax);
-                    else ln_trade_phase2<false>(tr32[lane], dA, dB, pinA, pinB, poA, poB, gA, gB, X, PF, RK, PK, C + lane, nw, kmax);
+                    if (m64) ln_trade_phase2<true>(tr64[lane], dA, dB, pinA, pinB, poA, poB, state.data(), lay.c_off, lane, X, PF, nw, kmax);
+                    else ln_trade_phase2<false>(tr32[lane], dA, dB, pinA, pinB, poA, poB, state.data(), lay.c_off, lane, X, PF, nw, kmax);
                     ap[lane] += (m64 ? tr64[lane].deal.go : tr32[lane].deal.go) ? 1 : 0;
                 }
                 if (!guard_ok(inA, SLOT, 0xAB) || !guard_ok(inB, SLOT, 0xAB) || !guard_ok(outA, SLOT, 0xCD) || !guard_ok(outB, SLOT, 0xCD) ||
