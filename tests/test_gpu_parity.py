@@ -482,6 +482,29 @@ def test_scan_full_size_properties(eng):
         assert eng.score_sets(cand[ok].astype(np.int32))["W"].max() <= got["W"][0] + tol
 
 
+def test_scan_full_size_equals_the_oracles_top_16(eng):
+    """C2 at FULL size against the oracle: tests/golden/scan_c2.npz holds the 16 best of all 1 274 230 475 subsets, every one
+    scored by oracle/sdx_oracle.c with the plain definition of SuperW (src/superdendrix.py:387-391; no inclusion-exclusion,
+    ~15 core-hours, made once by tests/golden/make_scan_c2.py).  The GPU scan must return exactly those subsets in that
+    order, with the same coverage and W within 1e-9 * sum|w| — whole, and sharded by smallest feature index and merged."""
+    from superdendrix_b200 import dist
+    z = load_npz("scan_c2.npz")
+    dense, _, _ = synth.feature_matrix(1000, 2000, seed=20)
+    S, F = dense.shape
+    assert F == int(z["F"]) and S == int(z["S"])
+    w = synth.weights(S, 1, seed=3)
+    upload_dense(eng, dense)
+    eng.upload_weights(w)
+    tol = 1e-9 * np.abs(w).sum()
+    got = eng.scan(0, 3, 16)
+    assert got["n_scored"] == int(z["n_scored"])
+    assert np.array_equal(got["features"], z["features"]) and np.array_equal(got["coverage"], z["coverage"])
+    assert np.allclose(got["W"], z["W"], rtol=0, atol=tol)
+    parts = [eng.scan(0, 3, 16, g_lo=lo, g_hi=hi) for lo, hi in dist.scan_feature_ranges(F, 3, 8)]
+    merged = dist.merge_hits(parts, 16)
+    assert np.array_equal(merged["features"], z["features"]) and sum(p_["n_scored"] for p_ in parts) == int(z["n_scored"])
+
+
 # ---------------------------------------------------------------- conditional permutation
 def _condperm_inputs():
     z = load_npz("condperm_data.npz")
