@@ -87,6 +87,8 @@ static void free_matrix(sdx_ctx *c) {
     if (c->d_pool) cudaFree(c->d_pool);
     c->d_pool = nullptr;
     c->pool_valid = false;
+    if (c->resume.d_state) cudaFree(c->resume.d_state);
+    c->resume.d_state = nullptr; c->resume.cap = 0; c->resume.valid = false;
     if (c->d_top) cudaFree(c->d_top);
     c->d_top = nullptr; c->cap_top = 0; c->top_K = 0;
     c->cap_feat = c->cap_samp = c->cap_obs = c->cap_rowsize = c->cap_pool = 0;
@@ -97,6 +99,7 @@ static void invalidate_matrix(sdx_ctx *c) {
     c->ln_state = 0; c->ln_geo_valid = false;                  // the lane layout (row kinds and offsets) is rebuilt on first use
     c->ln_pool_valid = false;
     c->pool_valid = false;
+    c->resume.valid = false;
     c->top_K = 0;
 }
 
@@ -133,7 +136,7 @@ extern "C" int sdx_set_burn_in(sdx_ctx *c, int64_t burn_rounds, int pool_size) {
     if (!c) return SDX_ERR_INVALID;
     SDX_REQUIRE(c, burn_rounds >= 0 && burn_rounds <= 256, SDX_ERR_INVALID, "burn_rounds must be in 0..256");
     SDX_REQUIRE(c, burn_rounds == 0 || (pool_size >= 1 && pool_size <= 65536), SDX_ERR_INVALID, "pool_size must be in 1..65536");
-    if (burn_rounds != c->burn || pool_size != c->pool_size) { c->pool_valid = false; c->ln_pool_valid = false; }
+    if (burn_rounds != c->burn || pool_size != c->pool_size) { c->pool_valid = false; c->ln_pool_valid = false; c->resume.valid = false; }
     c->burn = burn_rounds;
     c->pool_size = burn_rounds > 0 ? pool_size : 0;
     if (burn_rounds == 0) c->top_K = 0;          // no burn-in trades: the dense-row table of the pool is not in use

@@ -75,6 +75,16 @@ struct sdx_ctx {
     size_t cap_top = 0;
     int top_K = 0;
 
+    // a request inside one long chain continues where the previous call stopped (run_nulls_bits)
+    struct Resume {
+        bool valid = false, use_pool = false;
+        uint64_t seed = 0, chain = 0;
+        int64_t T = 0, chain_len = 0, round = 0;         // round: rounds of the chain already applied to d_state
+        int pair_group = 1;
+        size_t words = 0, cap = 0;
+        uint32_t *d_state = nullptr;
+    } resume;
+
     // weights
     int P = 0;
     double *d_w = nullptr;        // P x S  (0 where masked out)

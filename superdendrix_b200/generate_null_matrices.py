@@ -66,7 +66,12 @@ def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, ba
         chain_len = {"chained": max(int(n_nulls), 1), "parallel": defaults.CHAIN_LEN, "restart": 1}[mode]
         eng.set_burn_in(burn_in if mode == "parallel" else 0, defaults.POOL_SIZE)
         eng.set_pair_group(defaults.PAIR_GROUP if mode == "parallel" else 1)
-        # a chain starts at a multiple of chain_len: with prefix a multiple of n_nulls every process owns one chain
+        # a chain starts at a multiple of chain_len: with prefix a multiple of n_nulls every process owns one chain; the
+        # library keeps the chain's state between the batches below, so a batch continues where the previous one stopped
+        if mode == "chained" and n_nulls > 0 and prefix % max(int(n_nulls), 1):
+            import warnings
+            warnings.warn("--mode chained: -pre %d is not a multiple of -p %d, so this run covers the end of one chain and the start of the "
+                          "next (null i restarts from the observed matrix when i %% p == 0)" % (prefix, n_nulls))
         done = 0
         while done < n_nulls:
             n = min(batch, n_nulls - done)

@@ -482,6 +482,30 @@ def test_scan_full_size_properties(eng):
         assert eng.score_sets(cand[ok].astype(np.int32))["W"].max() <= got["W"][0] + tol
 
 
+def test_one_long_chain_in_batches_continues_instead_of_replaying():
+    """the reference driver's single Markov chain (src/generate_null_matrices.py:71-74) requested in batches: every call
+    continues from the state the previous one left (the context keeps it), a request that does not follow on replays
+    the chain from its start; both give the nulls of one request — and the oracle's"""
+    dense = _dense_cases()["tall"]
+    obs = rows_of(dense)
+    T = 5 * obs.shape[0]
+    want, want_ap = oracle.curveball_nulls(obs, 77, 0, 90, T, 1000)
+    with Engine(0) as e2:
+        upload_dense(e2, dense)
+        parts = [e2.curveball(77, lo, n, chain_len=1000) for lo, n in ((0, 30), (30, 20), (50, 5))]
+        rounds = []
+        for lo, n in ((55, 10), (70, 20)):                       # 55 follows on; 70 does not (65..69 were never asked for)
+            parts.append(e2.curveball(77, lo, n, chain_len=1000))
+            rounds.append(e2.timing()["trade_ms"])
+        got = np.concatenate([p_[0] for p_ in parts[:4]])
+        assert np.array_equal(got, want[:65]) and np.array_equal(np.concatenate([p_[1] for p_ in parts[:4]]), want_ap[:65])
+        assert np.array_equal(parts[4][0], want[70:90])
+        # a chain boundary inside the request, and a second chain, still restart from the observed matrix
+        two, _ = e2.curveball(77, 995, 10, chain_len=1000)
+    ref2, _ = oracle.curveball_nulls(obs, 77, 995, 10, T, 1000)
+    assert np.array_equal(two, ref2)
+
+
 def test_scan_full_size_equals_the_oracles_top_16(eng):
     """C2 at FULL size against the oracle: tests/golden/scan_c2.npz holds the 16 best of all 1 274 230 475 subsets, every one
     scored by oracle/sdx_oracle.c with the plain definition of SuperW (src/superdendrix.py:387-391; no inclusion-exclusion,
