@@ -124,6 +124,12 @@ int sdx_trade_shape(const sdx_ctx *ctx, int *n_rows, int *n_bits, int *words_per
 int sdx_curveball(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
                   int64_t chain_len, uint32_t *out_trade_rows, int64_t *applied);
 
+/* The same nulls as FEATURE rows over samples (n_nulls x F x ceil(S/32) words) whatever the trade orientation: the
+ * layout of one null file, one line per sample with its events (src/generate_null_matrices.py:75-86).  When the trade
+ * rows are samples (F >= S) the batch is transposed on the device. */
+int sdx_curveball_features(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades,
+                           int64_t chain_len, uint32_t *out_feature_rows);
+
 /* Burn-in.  5*min(S,F) trades do not mix the dense rows: the reference's single chain is
  * stationary only because null i has already seen (i+1) rounds (src/generate_null_matrices.py:73-74).  With
  * burn_rounds > 0 every chain starts, instead of from the observed matrix, from one of pool_size start states:

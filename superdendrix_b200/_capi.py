@@ -60,6 +60,7 @@ PROTOTYPES = {
     "sdx_feature_scores": (C.c_int, [_ctx, C.c_int, _f64p, _f64p, _i32p, _i32p]),
     "sdx_trade_shape": (C.c_int, [_ctx, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sdx_curveball": (C.c_int, [_ctx, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, _u32p, _i64p]),
+    "sdx_curveball_features": (C.c_int, [_ctx, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, _u32p]),
     "sdx_set_burn_in": (C.c_int, [_ctx, C.c_int64, C.c_int]),
     "sdx_set_pair_group": (C.c_int, [_ctx, C.c_int]),
     "sdx_pool_begin": (C.c_int, [_ctx, C.c_uint64, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),

@@ -847,3 +847,38 @@ extern "C" int sdx_null_pvalue_rows(sdx_ctx *c, const uint32_t *feature_rows, in
     c->timing.score_ms = c->timing.total_ms;
     return rc;
 }
+
+// ---------------------------------------------------------------------------
+// sdx_curveball_features: sdx_curveball with the nulls returned as FEATURE rows over samples whatever the trade
+// orientation — the layout the driver's file format wants (one line per sample, src/generate_null_matrices.py:75-86).  When
+// the trade rows are samples (F >= S) the batch is transposed on the device.
+// ---------------------------------------------------------------------------
+extern "C" int sdx_curveball_features(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
+                                      uint32_t *out_feature_rows) {
+    if (!c) return SDX_ERR_INVALID;
+    SDX_REQUIRE(c, c->d_trade_obs, SDX_ERR_STATE, "sdx_upload_matrix has not been called");
+    SDX_REQUIRE(c, out_feature_rows || n_nulls == 0, SDX_ERR_INVALID, "out_feature_rows is NULL");
+    if (!c->rows_are_samples) return sdx_curveball(c, seed, null0, n_nulls, n_trades, chain_len, out_feature_rows, nullptr);
+    const int F = c->F, S = c->S, wprS = c->wprS, wprF = c->wprF;
+    const size_t feat_words = (size_t)F * wprS, samp_words = (size_t)S * wprF;
+    int64_t B = (int64_t)(((size_t)1 << 30) / (sizeof(uint32_t) * (feat_words + samp_words) + 1));
+    if (B < 1) B = 1;
+    if (B > n_nulls) B = n_nulls;
+    void *p_mat = nullptr;
+    if (n_nulls > 0) SDX_TRY(sdx_scratch(c, 11, sizeof(uint32_t) * (feat_words + samp_words) * B + 64, &p_mat));
+    uint32_t *d_samp = (uint32_t *)p_mat, *d_feat = d_samp + samp_words * B;
+    float trade_ms = 0, plan_ms = 0;
+    int launches = 0, tl = 0;
+    for (int64_t b0 = 0; b0 < n_nulls; b0 += B) {
+        const int nb = (int)std::min<int64_t>(B, n_nulls - b0);
+        SDX_TRY(sdx_generate_to_device(c, seed, null0 + (uint64_t)b0, nb, n_trades, chain_len, d_samp));
+        trade_ms += c->timing.trade_ms; plan_ms += c->timing.plan_ms; launches += c->timing.launches; tl += c->timing.trade_launches;
+        SDX_CUDA(c, cudaMemsetAsync(d_feat, 0, sizeof(uint32_t) * feat_words * nb, c->stream));
+        SDX_TRY(sdx_transpose_batch(c, d_samp, S, wprF, F, d_feat, wprS, nb));
+        SDX_CUDA(c, cudaMemcpyAsync(out_feature_rows + (size_t)b0 * feat_words, d_feat, sizeof(uint32_t) * feat_words * nb, cudaMemcpyDefault, c->stream));
+        SDX_CUDA(c, cudaStreamSynchronize(c->stream));
+        ++launches;
+    }
+    c->timing.trade_ms = trade_ms; c->timing.plan_ms = plan_ms; c->timing.launches = launches; c->timing.trade_launches = tl;
+    return SDX_OK;
+}

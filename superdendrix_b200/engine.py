@@ -178,6 +178,14 @@ class Engine:
                                             chain_len, _ptr(out, C.c_uint32), _ptr(ap, C.c_int64)))
         return out, ap
 
+    def curveball_features(self, seed: int, null0: int, n_nulls: int, n_trades: int = -1, chain_len: int = 1):
+        """The nulls of ``curveball`` as packed FEATURE rows over samples, (n, F, ceil(S/32)) uint32, whatever the trade
+        orientation (transposed on the device when the trade rows are samples)."""
+        out = np.zeros((n_nulls, self.F, bitpack.words_for(self.S)), dtype=np.uint32)
+        self._check(self._lib.sdx_curveball_features(self._ctx, C.c_uint64(seed), C.c_uint64(null0), n_nulls, n_trades, chain_len,
+                                                     _ptr(out, C.c_uint32)))
+        return out
+
     def curveball_replay(self, a, b, to_a, start_rows=None):
         R, _, wpr, _ = self.trade_shape()
         a = np.ascontiguousarray(a, dtype=np.int32)

@@ -75,10 +75,7 @@ def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, ba
         done = 0
         while done < n_nulls:
             n = min(batch, n_nulls - done)
-            rows, _ = eng.curveball(seed, prefix + done, n, n_trades=-1, chain_len=chain_len, want_applied=False)
-            if rows_are_samples:                      # trade rows are samples: transpose to feature rows on the host
-                bits = bitpack.unpack_rows(rows, L)   # (n, S, F)
-                rows = np.stack([bitpack.pack_rows(b.T) for b in bits])
+            rows = eng.curveball_features(seed, prefix + done, n, n_trades=-1, chain_len=chain_len)      # feature rows; transposed on the device if needed
             yield prefix + done, rows
             done += n
     finally:

@@ -130,7 +130,9 @@ def write_results(path, names, genes, res, n_samples_of_profile, direction):
             feats = [int(f) for f in res["modules"][p] if f >= 0]
             # the reference orders features by per-feature score (descending, rounded to 2 dp), :221-227
             score = [float(round(float(res["single_W"][p][i]), 2)) for i in range(len(feats))]
-            order = sorted(range(len(feats)), key=lambda i: -score[i])
+            # two stable sorts as the reference's: by carrier count, then by rounded score (ties keep the carrier-count order, :202,227)
+            order = sorted(range(len(feats)), key=lambda i: -int(res["single_n"][p][i]))
+            order = sorted(order, key=lambda i: -score[i])
             cols = [name]
             if feats:
                 cols += [",".join(genes[feats[i]] for i in order), ",".join(str(int(res["single_n"][p][i])) for i in order),
@@ -163,6 +165,8 @@ def get_parser():
                     choices=["increased_dependency", "decreased_dependency", "positive", "negative"])
     ap.add_argument("-o", "--output_file", required=True)
     ap.add_argument("-rs", "--random_seed", type=int, default=1764)
+    ap.add_argument("-u", "--unit_weights", default=False, action="store_true", help="Use unit weights and simple binarization [False]")
+    ap.add_argument("-O", "--offset", type=float, default=0, help="manual weight offset [0]")
     ap.add_argument("--null-stat", default="fixed", choices=["fixed", "max_k"])
     ap.add_argument("--device", type=int, default=0)
     return ap
@@ -177,14 +181,36 @@ def main(argv=None):
     row = {s: i for i, s in enumerate(psamples)}
     idx = np.array([row[s] for s in samples])
     flip = -1.0 if args.direction in ("negative", "increased_dependency") else 1.0            # src/superdendrix.py:97-98,105-106
-    W = np.stack([flip * profiles[nm][idx] for nm in names])
-    W = np.where(np.isinf(W), np.sign(W) * 100.0, W)                                           # +-inf -> +-100 (:96)
-    mask = ~np.isnan(W)                                                                        # NaN / blank: sample not in the profile (:92-94)
-    W = np.where(mask, W, 0.0)
+    raw = np.stack([profiles[nm][idx] for nm in names])
+    inf = np.isinf(raw)
+    mask = ~np.isnan(raw)                                                                      # NaN / blank: sample not in the profile (:92-94)
+    # per profile, exactly as parse_profile: +-inf -> +-100 then the sign flip, no offset / unit weights for those (:96-99); others:
+    # offset, flip, then unit weights (:103-109)
+    val = np.where(inf, np.sign(raw) * 100.0, np.where(mask, raw, 0.0) + args.offset) * flip
+    if args.unit_weights:
+        val = np.where(inf, val, np.where(val <= 0, -1.0, 1.0))
+    W = np.where(mask, val, 0.0)
+    # the reference gives up on a profile with more than 10 % NaN / Inf entries (:115-123): those profiles are reported, not screened
+    all_rows = np.stack([profiles[nm] for nm in names])
+    bad_frac = (np.isnan(all_rows) | np.isinf(all_rows)).mean(axis=1) if all_rows.shape[1] else np.zeros(len(names))
+    skipped = [(nm, float(bf)) for nm, bf in zip(names, bad_frac) if bf > 0.1]
+    keep = [i for i, bf in enumerate(bad_frac) if bf <= 0.1]
+    names = [names[i] for i in keep]
+    W, mask = W[keep], mask[keep]
+    if not names:
+        with open(args.output_file, "w") as fh:
+            fh.write(HEADER)
+            for nm, bf in skipped:
+                fh.write("%s\tincomplete due to high Nan, Inf\tNan, Inf fraction: %s\n" % (nm, bf))
+        return 1
     with Engine(args.device) as eng:
         res = screen(eng, pack_features(genes, samples, g2c), len(samples), W, mask, args.cardinality, args.cond_it, args.p_val_it,
                      args.random_seed, args.null_stat, log=print)
     write_results(args.output_file, names, genes, res, mask.sum(axis=1), args.direction)
+    if skipped:
+        with open(args.output_file, "a") as fh:
+            for nm, bf in skipped:
+                fh.write("%s\tincomplete due to high Nan, Inf\tNan, Inf fraction: %s\n" % (nm, bf))
     return 0
 
 
