@@ -5,17 +5,20 @@
 
 Workload (BASELINE.json configs[1]): the BRAF-shape matrix (synthetic DepMap-20Q2
 shape, 770 cell lines x ~400 OncoKB-like features), a fixed k=3 module, and
-100 000 Curveball nulls per GPU per step, each generated (5*min(S,F) trades) and
-scored with the SuperDendrix set objective, exceedances counted for the
-permutation p-value.  One step = one such pass.  Ranks shard the null index
-range (weak scaling: 100 000 nulls per rank per step); the only exchange is the
-all-reduce of the exceedance counts.
+100 000 Curveball nulls per GPU per step, each generated (5*min(S,F) trades, one
+round from a burnt-in pool state) and scored with the SuperDendrix set objective,
+exceedances counted for the permutation p-value.  One step = one such pass = one
+launch of k_trade_lanes.  Ranks shard the null index range (weak scaling: 100 000
+nulls per rank per step); the only exchange is the all-reduce of the counts.
 
-Prints ONE JSON line on rank 0.  `value` = nulls/s with matrix and weights
-resident in HBM; `e2e` = the same call sequence a user makes through the C ABI
-from host buffers (upload matrix + weights, run, read counts) every step.
-Secondary figures (exhaustive k<=3 scan over 2 000 features, conditional
-permutations, rank-sums) are in `extra`.
+Prints ONE JSON line on rank 0.  `value` = nulls/s with matrix, weights and pool
+resident in HBM; `e2e` = the same call sequence a user makes through the C ABI from
+host buffers (upload matrix + weights, rebuild the pool, run, read counts) every step.
+`roofline` = the popc fraction of SURVEY 8d against the rate measured on the box.
+`strong_scaling`: configs[1] as stated — 100 000 nulls IN TOTAL over the N GPUs through
+superdendrix_b200.dist.null_pvalue, collectives inside the timed region.
+`full_size_configs`: configs[2..4] at full size through superdendrix_b200.dist.
+`extra` (N = 1): secondary figures with the CPU port beside them.
 """
 from __future__ import annotations
 

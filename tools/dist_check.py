@@ -7,7 +7,7 @@ import numpy as np
 import torch
 import torch.distributed as tdist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from superdendrix_b200 import bitpack, dist, synth
+from superdendrix_b200 import bitpack, defaults, dist, synth
 from superdendrix_b200.engine import Engine
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -21,7 +21,7 @@ with Engine(local) as eng:
     eng.upload_dense(dense)
     eng.upload_weights(w)
     pv = dist.null_pvalue(eng, 1764, 20001, mods)
-    one = eng.null_pvalue(1764, 0, 20001, mods, chain_len=16)["n_ge"]          # dist.null_pvalue has set the same burn-in pool
+    one = eng.null_pvalue(1764, 0, 20001, mods, chain_len=defaults.CHAIN_LEN)["n_ge"]   # dist.null_pvalue has set the same burn-in pool (built in slices + all-gather) and pair groups
     assert np.array_equal(pv["n_ge"], one), (pv["n_ge"], one)
     sc = dist.scan(eng, 1, 3, 8)
     whole = eng.scan(1, 3, 8)
