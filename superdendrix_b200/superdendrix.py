@@ -103,6 +103,8 @@ def get_parser():
                              "reference's generator + driver do [full], or randomise the matrix already restricted to the profiled samples")
     parser.add_argument("--mode", default="parallel", choices=["parallel", "chained", "restart"])
     parser.add_argument("--burn-in", type=int, default=6, help="burn-in rounds of the pool states (parallel mode)")
+    parser.add_argument("--check-mixing", action="store_true",
+                        help="parallel mode: probe whether the burn-in pool is stationary for this matrix (a few hundred extra nulls) and say so in the log")
     parser.add_argument("--device", type=int, default=0)
     parser.add_argument("--null-batch", type=int, default=1024, help="null files parsed and scored per library call (--null-source files)")
     return parser
@@ -302,6 +304,10 @@ def null_loop(genes, samples, profile, events_to_samples, module, zP, args, logg
             mod = np.array([[gidx[g] for g in module] + [-1] * (max(k, 1) - k)], dtype=np.int32)
         eng.set_burn_in(burn, defaults.POOL_SIZE)
         eng.set_pair_group(defaults.PAIR_GROUP if args.mode == "parallel" else 1)
+        if args.check_mixing and args.mode == "parallel":
+            from . import mixing
+            fr = pack_features(genes_f, samples_f, e2s_f) if args.null_scope == "full" else pack_features(genes, samples, events_to_samples)
+            mixing.check(eng, fr, len(samples_f) if args.null_scope == "full" else len(samples), args.random_seed, log=logger.info if logger else None)
         res = eng.null_pvalue(args.random_seed, 0, n, mod, chain_len=chain, stat=stat, z_obs=np.array([zP]), want_scores=True)
         return int(res["n_ge"][0]), n, res["null_scores"][0]
     # files: <-nm><i>.tsv, restricted to the profiled samples as src/superdendrix.py:186 does.  Read in batches by the

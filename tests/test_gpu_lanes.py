@@ -224,3 +224,21 @@ def test_c0_shipped_defaults_sample_the_reference_chains_null_distribution():
         assert abs(p_ref - p_new) < 4.5 * se, (thr, p_ref, p_new, se)
     # the chain's own relaxation is visible in the fixture: its first nulls are closer to the observed score than to the stationary mean
     assert abs(ref_all[:3].mean() - z_obs) < abs(ref_all[:3].mean() - ref.mean())
+
+
+def test_mixing_check_flags_a_pool_that_remembers_the_observed_matrix():
+    """superdendrix_b200.mixing: from stationary pool states the overlap with the observed matrix does not drift along a chain;
+    without burn-in (chains start from the observed matrix itself) it falls round after round"""
+    from superdendrix_b200 import mixing
+    dense, _, _ = synth.feature_matrix(770, 400, seed=20)
+    frows = bitpack.pack_rows(dense.T)
+    with Engine(0) as eng:
+        eng.upload_dense(dense)
+        eng.set_pair_group(defaults.PAIR_GROUP)
+        eng.set_burn_in(0, 0)
+        raw = mixing.overlap_drift(eng, frows, dense.shape[0])
+        eng.set_burn_in(defaults.BURN_ROUNDS, defaults.POOL_SIZE)
+        mixed = mixing.overlap_drift(eng, frows, dense.shape[0])
+        assert mixing.check(eng, frows, dense.shape[0], log=lambda m: None)
+    assert raw["z"] > 20 and raw["first"] > raw["last"] + 300
+    assert abs(mixed["z"]) < 4 and abs(mixed["first"] - 558) < 15
