@@ -227,3 +227,29 @@ def test_property_shard_ranges_partition(n, world):
     r = [dist.shard_range(n, k, world) for k in range(world)]
     assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
     assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_fdr_and_result_parsing_cli_like_the_reference_utils(tmp_path):
+    """utils/compute_FDR.py (BH column; 'na' counts as 1.0) and utils/parse_SD_results.py (profiles with FDR <= 0.20, pairs, tallies)"""
+    import scipy.stats
+
+    from superdendrix_b200 import compute_FDR, parse_SD_results, synth
+    res = tmp_path / "all.tsv"
+    rows = [("P%d" % i, "G%d_A_MUT,G%d_I_MUT" % (i % 3 + 1, i % 2 + 1), "3,4", "1.0,0.5", p) for i, p in enumerate(["0.001", "0.2", "na", "0.01", "0.04", "0.9"])]
+    with open(res, "w") as fh:
+        fh.write("profile\tfeatures\t#samples\tscores\tP_value\n")
+        fh.write("\n".join("\t".join(r) for r in rows))
+    out = tmp_path / "fdr.tsv"
+    adj = compute_FDR.run(compute_FDR.get_parser().parse_args(["-i", str(res), "-p", "4", "-o", str(out)]))
+    want = scipy.stats.false_discovery_control([0.001, 0.2, 1.0, 0.01, 0.04, 0.9], method="bh")
+    assert np.allclose(adj, want)
+    lines = open(out).read().split("\n")
+    assert lines[0].split("\t")[-1] == "FDR" and len(lines) == 7 and float(lines[1].split("\t")[-1]) == adj[0]
+    dense, samples, features = synth.feature_matrix(30, 12, seed=1)
+    mut = tmp_path / "f.tsv"
+    synth.write_features_tsv(str(mut), dense, samples, features)
+    r = parse_SD_results.run(parse_SD_results.get_parser().parse_args(["-i", str(out), "-ef", str(mut), "-o", str(tmp_path) + "/x_", "-find", "5"]))
+    sig = [i for i in range(6) if adj[i] <= 0.20]
+    assert [p[0] for p in r["profiles"]] == ["P%d" % i for i in sig]
+    assert len(r["pairs"]) == 2 * len(sig) and sum(r["mutated_genes"].values()) == 2 * len(sig)
+    assert open(str(tmp_path) + "/x_profiles.tsv").read().splitlines()[0] == "profile\tfdr"
