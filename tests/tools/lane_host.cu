@@ -53,7 +53,6 @@ extern "C" int lane_host_run(const uint32_t *start, int n_start, int R, int nw, 
     const size_t SLOT = (size_t)lay.slot_bytes, PFB = (size_t)lay.pf_bytes, XB = (size_t)lay.x_bytes;
     std::vector<uint8_t> inA(SLOT + 64), inB(SLOT + 64), outA(SLOT + 64), outB(SLOT + 64), pf(PFB + 64), xb(XB + 64);
     auto guard_ok = [&](const std::vector<uint8_t> &v, size_t n, uint8_t fill) { for (size_t q = n; q < v.size(); ++q) if (v[q] != fill) return false; return true; };
-    uint32_t *C = reinterpret_cast<uint32_t *>(state.data() + lay.c_off);
     double *PP = reinterpret_cast<double *>(state.data() + lay.pp_off), *PN = PP + 32 * LN_W;
     std::vector<uint32_t> ent((size_t)T + 1);
     for (int j = 0; j < rounds; ++j) {
@@ -82,20 +81,17 @@ extern "C" int lane_host_run(const uint32_t *start, int n_start, int R, int nw, 
             std::vector<LnTrade<false>> tr32(LN_W);
             std::vector<LnTrade<true>> tr64(LN_W);
             uint32_t kmax = 0;
-            auto ptrs = [&](int lane, uint16_t *&pinA, uint16_t *&pinB, uint16_t *&poA, uint16_t *&poB, uint32_t *&gA, uint32_t *&gB, uint16_t *&PF,
-                            uint16_t *&RK, uint16_t *&PK, uint32_t *&X) {
-                X = reinterpret_cast<uint32_t *>(xb.data()) + lane;
+            auto ptrs = [&](int lane, uint16_t *&pinA, uint16_t *&pinB, uint16_t *&poA, uint16_t *&poB, uint16_t *&PF, uint32_t *&X) {
                 pinA = reinterpret_cast<uint16_t *>(inA.data()) + lane; pinB = reinterpret_cast<uint16_t *>(inB.data()) + lane;
                 poA = reinterpret_cast<uint16_t *>(outA.data()) + lane; poB = reinterpret_cast<uint16_t *>(outB.data()) + lane;
-                gA = reinterpret_cast<uint32_t *>(state.data() + dA.x) + lane; gB = reinterpret_cast<uint32_t *>(state.data() + dB.x) + lane;
                 PF = reinterpret_cast<uint16_t *>(pf.data()) + lane;
-                RK = ba ? pinA : pinB; PK = ba ? poA : poB;
+                X = reinterpret_cast<uint32_t *>(xb.data()) + lane;
             };
             // phase 1 of all lanes (reads only; scratch is per lane: stride 32), the vote, then phase 2 of all lanes
             for (int lane = 0; lane < LN_W; ++lane) {
                 const LnRng g{&keys, (chain0 + (uint64_t)lane) * (uint64_t)chain_len + round, (uint32_t)t};
-                uint16_t *pinA, *pinB, *poA, *poB, *PF, *RK, *PK; uint32_t *gA, *gB, *X;
-                ptrs(lane, pinA, pinB, poA, poB, gA, gB, PF, RK, PK, X);
+                uint16_t *pinA, *pinB, *poA, *poB, *PF; uint32_t *X;
+                ptrs(lane, pinA, pinB, poA, poB, PF, X);
                 uint32_t km = 0;
                 if (m64) ln_trade_phase1<true>(tr64[lane], dA, dB, pinA, pinB, poA, poB, state.data(), lay.c_off, lane, X, PF, nw, g, km);
                 else ln_trade_phase1<false>(tr32[lane], dA, dB, pinA, pinB, poA, poB, state.data(), lay.c_off, lane, X, PF, nw, g, km);
@@ -103,8 +99,8 @@ extern "C" int lane_host_run(const uint32_t *start, int n_start, int R, int nw, 
             }
             if (kmax != 0) {
                 for (int lane = 0; lane < LN_W; ++lane) {
-                    uint16_t *pinA, *pinB, *poA, *poB, *PF, *RK, *PK; uint32_t *gA, *gB, *X;
-                    ptrs(lane, pinA, pinB, poA, poB, gA, gB, PF, RK, PK, X);
+                    uint16_t *pinA, *pinB, *poA, *poB, *PF; uint32_t *X;
+                    ptrs(lane, pinA, pinB, poA, poB, PF, X);
                     if (m64) ln_trade_phase2<true>(tr64[lane], dA, dB, pinA, pinB, poA, poB, state.data(), lay.c_off, lane, X, PF, nw, kmax);
                     else ln_trade_phase2<false>(tr32[lane], dA, dB, pinA, pinB, poA, poB, state.data(), lay.c_off, lane, X, PF, nw, kmax);
                     ap[lane] += (m64 ? tr64[lane].deal.go : tr32[lane].deal.go) ? 1 : 0;
