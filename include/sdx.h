@@ -133,13 +133,18 @@ int sdx_curveball_features(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t 
 /* Burn-in.  5*min(S,F) trades do not mix the dense rows: the reference's single chain is
  * stationary only because null i has already seen (i+1) rounds (src/generate_null_matrices.py:73-74).  With
  * burn_rounds > 0 every chain starts, instead of from the observed matrix, from one of pool_size start states:
- * state j = the observed matrix after burn_rounds rounds of n_trades trades drawn from reserved stream ids
- * ((2^61 / burn_rounds + j) * burn_rounds + r, r < burn_rounds); chain c uses state c % pool_size.  A burn-in trade
- * takes both rows from the max(2, ceil(R / 10)) densest rows with probability 1/4 and a uniform pair otherwise (a fixed
- * pair distribution: the stationary distribution stays uniform, and the dense rows forget the observed matrix in
- * ~3 rounds instead of ~30; the high-level paths use burn_rounds = 6).  Null indices must stay below 2^61 - 256.  Null i keeps the
- * stream id i, so results still depend only on (seed, i, chain_len, burn_rounds, pool_size) and not on batching or
- * on the GPU count.  The pool is built on first use and cached until the matrix, the seed or n_trades change.
+ * state j = the observed matrix after burn_rounds burn-in rounds drawn from reserved stream ids
+ * ((2^61 / burn_rounds + j) * burn_rounds + r, r < burn_rounds); chain c uses state c % pool_size.
+ * The burn-in rounds trade the rows of the orientation of the matrix whose largest row is the smaller multiple of
+ * its mean row — the transpose of the trade orientation iff L <= 12000 and max_col * L < max_row * R (R x L = the
+ * trade orientation): both orientations keep both margins and have the uniform stationary distribution, but a row
+ * far denser than its partners mixes slowly (C0: feature rows need ~30 rounds, sample rows 2).  A burn-in round
+ * is 5 * R_b trades (R_b rows of that orientation; at most 60000), independent of n_trades; its pairs are uniform,
+ * unless even that orientation has a row above 8 x the mean row: then a trade takes both rows from the
+ * max(2, ceil(R_b / 10)) densest rows with probability 1/4.  The high-level paths use burn_rounds = 3.
+ * Null indices must stay below 2^61 - 256.  Null i keeps the stream id i, so results still depend only on
+ * (seed, i, chain_len, burn_rounds, pool_size) and not on batching or on the GPU count.  The pool is built on first
+ * use and cached until the matrix or the seed change.
  * burn_rounds = 0 (default) starts every chain from the observed matrix. */
 int sdx_set_burn_in(sdx_ctx *ctx, int64_t burn_rounds, int pool_size);
 

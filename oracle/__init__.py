@@ -99,30 +99,42 @@ def trade_pair(seed, null_id, t, R):
     return a.value, b.value
 
 
-def curveball_nulls(observed, seed, null0, n, n_trades, chain_len=1, want_matrices=True, burn=0, pool_size=1024, pair_group=1):
+def curveball_nulls(observed, seed, null0, n, n_trades, chain_len=1, want_matrices=True, burn=0, pool_size=1024, pair_group=1, L=None):
     """observed: (R, wpr) uint32 packed rows over the longer dimension.
-    burn > 0: chains start from the burn-in pool (see sdx_oracle.c).
+    burn > 0: chains start from the burn-in pool (see sdx_oracle.c); L = bits per row (the burn-in may run on the transpose,
+    so the number of columns must be known exactly).
     pair_group > 1: aligned blocks of that many chains draw their row pairs from the stream of the block's first chain.
     Returns (nulls (n, R, wpr) or None, applied (n,))."""
     obs = _u32(observed)
     R, wpr = obs.shape
+    if burn > 0 and L is None:
+        raise ValueError("burn > 0 needs L (bits per row)")
     out = np.zeros((n, R, wpr), dtype=np.uint32) if want_matrices else None
     applied = np.zeros(n, dtype=np.int64)
-    lib().sdxo_curveball_nulls_group(_p(obs, C.c_uint32), C.c_int(R), C.c_int(wpr), C.c_uint64(seed),
+    lib().sdxo_curveball_nulls_group(_p(obs, C.c_uint32), C.c_int(R), C.c_int(wpr), C.c_int(wpr * 32 if L is None else L), C.c_uint64(seed),
                                      C.c_uint64(null0), C.c_int64(n), C.c_int64(n_trades), C.c_int64(chain_len),
                                      C.c_int64(burn), C.c_int(pool_size), C.c_int(pair_group), _p(out, C.c_uint32),
                                      _p(applied, C.c_int64))
     return out, applied
 
 
-def pool_state(observed, seed, n_trades, burn, j):
-    """start state j of the burn-in pool: the observed matrix after `burn` dense-favouring rounds on reserved streams"""
+def pool_state(observed, L, seed, burn, j):
+    """start state j of the burn-in pool: the observed matrix (R rows of L bits) after `burn` burn-in rounds on reserved streams"""
     obs = _u32(observed)
     R, wpr = obs.shape
     out = np.zeros_like(obs)
-    lib().sdxo_pool_state(_p(obs, C.c_uint32), C.c_int(R), C.c_int(wpr), C.c_uint64(seed), C.c_int64(n_trades),
+    lib().sdxo_pool_state(_p(obs, C.c_uint32), C.c_int(R), C.c_int(wpr), C.c_int(L), C.c_uint64(seed),
                           C.c_int64(burn), C.c_int(j), _p(out, C.c_uint32))
     return out
+
+
+def burn_plan(observed, L):
+    """what the burn-in of this matrix looks like: dict(alt, rows, trades_per_round, dense_rows)"""
+    obs = _u32(observed)
+    R, wpr = obs.shape
+    info = np.zeros(4, dtype=np.int64)
+    lib().sdxo_burn_plan(_p(obs, C.c_uint32), C.c_int(R), C.c_int(wpr), C.c_int(L), _p(info, C.c_int64))
+    return {"alt": bool(info[0]), "rows": int(info[1]), "trades_per_round": int(info[2]), "dense_rows": int(info[3])}
 
 
 def curveball_replay(rows, a, b, to_a):

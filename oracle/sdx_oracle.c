@@ -231,16 +231,20 @@ static int trade_canonical(uint32_t *ra, uint32_t *rb, int wpr, uint64_t seed, u
     return 1;
 }
 
-/* Pair of a BURN-IN trade: with probability 1/4 both rows come from the K densest rows (top[], by size
- * descending, index ascending), otherwise the pair is uniform as in sdxo_trade_pair.  Row sizes are invariants of the
- * chain, so this is a fixed pair distribution and the stationary distribution stays uniform; dense x dense trades move
- * ~100 elements at once, which is what makes the dense rows forget the observed matrix in 3 rounds instead of 30. */
+/* ------------------------------------------------------------------ */
+/* Burn-in of the pool states                          */
+/* ------------------------------------------------------------------ */
+/* Pair of a BURN-IN trade when the burn orientation still has dominant rows: with probability 1/4 both rows come from
+ * the K densest rows (top[], by size descending, index ascending), otherwise the pair is uniform as in sdxo_trade_pair.
+ * Row sizes are invariants of the chain, so this is a fixed pair distribution and the stationary distribution stays
+ * uniform.  K < 2: the plain uniform pair of sdxo_trade_pair (same draws). */
 static void trade_pair_burn(uint64_t seed, uint64_t null_id, uint32_t t, uint32_t R, const uint16_t *top, uint32_t K,
                             uint32_t *a, uint32_t *b) {
+    if (K < 2) { sdxo_trade_pair(seed, null_id, t, R, a, b); return; }
     stream_t s;
     stream_init(&s, seed, STREAM_PAIR, null_id, t);
     uint32_t u = stream_next(&s);
-    if (K >= 2 && u < 0x40000000u) {
+    if (u < 0x40000000u) {
         uint32_t i = stream_below(&s, K), j = stream_below(&s, K - 1);
         if (j >= i) j++;
         *a = top[i]; *b = top[j];
@@ -265,17 +269,11 @@ static int64_t curveball_burn_round(uint32_t *rows, int R, int wpr, uint64_t see
 }
 
 /* the K = max(2, ceil(R / 10)) densest rows, by size descending then index ascending */
-static uint32_t dense_rows(const uint32_t *rows, int R, int wpr, uint16_t *top) {
+static uint32_t dense_rows(const int *size, int R, uint16_t *top) {
     uint32_t K = (uint32_t)((R + 9) / 10);
     if (K < 2) K = 2;
     if (K > (uint32_t)R) K = (uint32_t)R;
-    int *size = (int *)malloc(sizeof(int) * (size_t)R);
     char *used = (char *)calloc((size_t)R, 1);
-    for (int r = 0; r < R; ++r) {
-        int c = 0;
-        for (int i = 0; i < wpr; ++i) c += __builtin_popcount(rows[(size_t)r * wpr + i]);
-        size[r] = c;
-    }
     for (uint32_t q = 0; q < K; ++q) {
         int best = -1;
         for (int r = 0; r < R; ++r)
@@ -283,8 +281,84 @@ static uint32_t dense_rows(const uint32_t *rows, int R, int wpr, uint16_t *top) 
         used[best] = 1;
         top[q] = (uint16_t)best;
     }
-    free(size); free(used);
+    free(used);
     return K;
+}
+
+/* out (n_cols rows x wpr_out words) = bit transpose of in (n_rows rows x wpr_in words) */
+static void transpose_bits(const uint32_t *in, int n_rows, int wpr_in, int n_cols, uint32_t *out, int wpr_out) {
+    memset(out, 0, sizeof(uint32_t) * (size_t)n_cols * wpr_out);
+    for (int r = 0; r < n_rows; ++r)
+        for (int c = 0; c < n_cols; ++c)
+            if ((in[(size_t)r * wpr_in + (c >> 5)] >> (c & 31)) & 1u) out[(size_t)c * wpr_out + (r >> 5)] |= 1u << (r & 31);
+}
+
+/* How the pool states of one matrix are burnt in.  Curveball may trade the rows of either orientation of
+ * the matrix: both chains keep both margins and have the uniform distribution as their stationary distribution.  What
+ * mixes slowly is a row far larger than its partners (it exchanges at most |partner| elements per trade), so the
+ * burn-in runs in the orientation whose largest row is the smaller multiple of the mean row:
+ *     transposed (rows over the LONGER dimension)  iff  L <= 12000  and  max_col * L < max_row * R
+ * (R x L = the trade orientation of src/curveball.py:10-11).  A burn-in round is 5 * R_b trades (at most 60000), R_b the
+ * rows of that orientation; its pairs are uniform unless even there the largest row exceeds 8 x the mean row
+ * (max_b * R_b > 8 * ones), in which case they favour the densest tenth of the rows (trade_pair_burn). */
+typedef struct {
+    int alt;                /* 1: rows over the longer dimension */
+    int Rb, Lb, wprb;       /* rows, bits per row, words per row of the burn orientation */
+    int64_t Tb;             /* trades per burn-in round */
+    uint32_t *obs;          /* the observed matrix in the burn orientation */
+    uint16_t *top;
+    uint32_t K;             /* 0: uniform pairs */
+} burn_plan;
+
+static void burn_plan_init(burn_plan *bp, const uint32_t *observed, int R, int wpr, int L) {
+    int *rs = (int *)calloc((size_t)R, sizeof(int)), *cs = (int *)calloc((size_t)L, sizeof(int));
+    int64_t ones = 0;
+    int max_r = 0, max_c = 0;
+    for (int r = 0; r < R; ++r)
+        for (int c = 0; c < L; ++c)
+            if ((observed[(size_t)r * wpr + (c >> 5)] >> (c & 31)) & 1u) { rs[r]++; cs[c]++; ones++; }
+    for (int r = 0; r < R; ++r) if (rs[r] > max_r) max_r = rs[r];
+    for (int c = 0; c < L; ++c) if (cs[c] > max_c) max_c = cs[c];
+    bp->alt = L <= 12000 && (int64_t)max_c * L < (int64_t)max_r * R;
+    if (bp->alt) {
+        bp->Rb = L; bp->Lb = R; bp->wprb = (R + 31) / 32;
+        bp->obs = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)bp->Rb * bp->wprb);
+        transpose_bits(observed, R, wpr, L, bp->obs, bp->wprb);
+    } else {
+        bp->Rb = R; bp->Lb = L; bp->wprb = wpr;
+        bp->obs = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)R * wpr);
+        memcpy(bp->obs, observed, sizeof(uint32_t) * (size_t)R * wpr);
+    }
+    bp->Tb = 5 * (int64_t)bp->Rb;
+    if (bp->Tb > 60000) bp->Tb = 60000;
+    const int *size = bp->alt ? cs : rs;
+    const int max_b = bp->alt ? max_c : max_r;
+    bp->top = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)bp->Rb);
+    bp->K = ((int64_t)max_b * bp->Rb > 8 * ones) ? dense_rows(size, bp->Rb, bp->top) : 0;
+    free(rs); free(cs);
+}
+
+static void burn_plan_free(burn_plan *bp) { free(bp->obs); free(bp->top); }
+
+/* start state j of the pool, in the trade orientation (R x wpr): `burn` rounds on the reserved stream ids
+ * ((2^61 / burn + j) * burn + r), r < burn, from the observed matrix */
+static void burn_state(const burn_plan *bp, int R, int wpr, uint64_t seed, int64_t burn, int j, uint32_t *out) {
+    size_t wb = (size_t)bp->Rb * bp->wprb;
+    uint32_t *st = (uint32_t *)malloc(sizeof(uint32_t) * wb);
+    memcpy(st, bp->obs, sizeof(uint32_t) * wb);
+    uint64_t base = ((1ull << 61) / (uint64_t)burn + (uint64_t)j) * (uint64_t)burn;
+    for (int64_t r = 0; r < burn; ++r) curveball_burn_round(st, bp->Rb, bp->wprb, seed, base + (uint64_t)r, bp->Tb, bp->top, bp->K);
+    if (bp->alt) transpose_bits(st, bp->Rb, bp->wprb, R, out, wpr);
+    else memcpy(out, st, sizeof(uint32_t) * wb);
+    free(st);
+}
+
+/* what burn_plan_init decided, for the tests: info = {alt, Rb, Tb, K} */
+SDXO_API void sdxo_burn_plan(const uint32_t *observed, int R, int wpr, int L, int64_t *info) {
+    burn_plan bp;
+    burn_plan_init(&bp, observed, R, wpr, L);
+    info[0] = bp.alt; info[1] = bp.Rb; info[2] = bp.Tb; info[3] = bp.K;
+    burn_plan_free(&bp);
 }
 
 /* curve_ball(input_matrix, r_hp, num_iterations) — src/curveball.py:17-40 —
@@ -323,21 +397,19 @@ static uint64_t pair_stream_id(uint64_t id, int64_t chain_len, int pair_group) {
  * independent restarts of src/curveball_main.py:136).
  * Burn-in: with burn > 0 a chain does not start from the
  * observed matrix but from start state (c % pool_size) of its chain index c,
- * where state j = the observed matrix after `burn` rounds drawn from the
- * reserved stream ids ((2^61 / burn + j) * burn + r), r < burn.
+ * where state j = the observed matrix after `burn` burn-in rounds (burn_state;
+ * L = bits per row is needed there: the burn-in may run on the transpose).
  * out = n packed matrices (may be NULL); applied[n] optional. */
-SDXO_API void sdxo_curveball_nulls_group(const uint32_t *observed, int R, int wpr, uint64_t seed,
+SDXO_API void sdxo_curveball_nulls_group(const uint32_t *observed, int R, int wpr, int L, uint64_t seed,
                                          uint64_t null0, int64_t n, int64_t n_trades, int64_t chain_len,
                                          int64_t burn, int pool_size, int pair_group, uint32_t *out, int64_t *applied) {
     size_t msz = (size_t)R * wpr;
     uint32_t *cur = (uint32_t *)malloc(sizeof(uint32_t) * msz);
     uint32_t **pool = NULL;
-    uint16_t *top = NULL;
-    uint32_t K = 0;
+    burn_plan bp;
     if (burn > 0) {
         pool = (uint32_t **)calloc((size_t)pool_size, sizeof(uint32_t *));
-        top = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)R);
-        K = dense_rows(observed, R, wpr, top);
+        burn_plan_init(&bp, observed, R, wpr, L);
     }
     for (int64_t i = 0; i < n; ++i) {
         uint64_t id = null0 + (uint64_t)i;
@@ -347,9 +419,7 @@ SDXO_API void sdxo_curveball_nulls_group(const uint32_t *observed, int R, int wp
                 int j = (int)(chain % (uint64_t)pool_size);
                 if (!pool[j]) {
                     pool[j] = (uint32_t *)malloc(sizeof(uint32_t) * msz);
-                    memcpy(pool[j], observed, sizeof(uint32_t) * msz);
-                    uint64_t base = ((1ull << 61) / (uint64_t)burn + (uint64_t)j) * (uint64_t)burn;
-                    for (int64_t r = 0; r < burn; ++r) curveball_burn_round(pool[j], R, wpr, seed, base + (uint64_t)r, n_trades, top, K);
+                    burn_state(&bp, R, wpr, seed, burn, j, pool[j]);
                 }
                 memcpy(cur, pool[j], sizeof(uint32_t) * msz);
             } else {
@@ -366,32 +436,24 @@ SDXO_API void sdxo_curveball_nulls_group(const uint32_t *observed, int R, int wp
     if (pool) {
         for (int j = 0; j < pool_size; ++j) free(pool[j]);
         free(pool);
+        burn_plan_free(&bp);
     }
-    free(top);
     free(cur);
 }
 
 /* start state j of the burn-in pool, as the chains of sdxo_curveball_nulls_group use it */
-SDXO_API void sdxo_pool_state(const uint32_t *observed, int R, int wpr, uint64_t seed, int64_t n_trades, int64_t burn, int j,
+SDXO_API void sdxo_pool_state(const uint32_t *observed, int R, int wpr, int L, uint64_t seed, int64_t burn, int j,
                               uint32_t *out) {
-    uint16_t *top = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)R);
-    uint32_t K = dense_rows(observed, R, wpr, top);
-    memcpy(out, observed, sizeof(uint32_t) * (size_t)R * wpr);
-    uint64_t base = ((1ull << 61) / (uint64_t)burn + (uint64_t)j) * (uint64_t)burn;
-    for (int64_t r = 0; r < burn; ++r) curveball_burn_round(out, R, wpr, seed, base + (uint64_t)r, n_trades, top, K);
-    free(top);
-}
-
-SDXO_API void sdxo_curveball_nulls_burn(const uint32_t *observed, int R, int wpr, uint64_t seed,
-                                        uint64_t null0, int64_t n, int64_t n_trades, int64_t chain_len,
-                                        int64_t burn, int pool_size, uint32_t *out, int64_t *applied) {
-    sdxo_curveball_nulls_group(observed, R, wpr, seed, null0, n, n_trades, chain_len, burn, pool_size, 1, out, applied);
+    burn_plan bp;
+    burn_plan_init(&bp, observed, R, wpr, L);
+    burn_state(&bp, R, wpr, seed, burn, j, out);
+    burn_plan_free(&bp);
 }
 
 SDXO_API void sdxo_curveball_nulls(const uint32_t *observed, int R, int wpr, uint64_t seed,
                                    uint64_t null0, int64_t n, int64_t n_trades, int64_t chain_len,
                                    uint32_t *out, int64_t *applied) {
-    sdxo_curveball_nulls_burn(observed, R, wpr, seed, null0, n, n_trades, chain_len, 0, 0, out, applied);
+    sdxo_curveball_nulls_group(observed, R, wpr, wpr * 32, seed, null0, n, n_trades, chain_len, 0, 0, 1, out, applied);
 }
 
 /* Replay of a recorded reference schedule: trade t uses

@@ -19,7 +19,7 @@ from urllib.parse import quote, urlencode
 
 import numpy as np
 
-from . import superdendrix as sd
+from . import defaults, superdendrix as sd
 from .i_o import getLogger, load_events, load_mutation_data
 
 
@@ -49,7 +49,7 @@ def get_parser():
     p.add_argument("--null-scope", default="full", choices=["full", "restricted"])
     p.add_argument("--null-batch", type=int, default=1024)
     p.add_argument("--mode", default="parallel", choices=["parallel", "chained", "restart"])
-    p.add_argument("--burn-in", type=int, default=6)
+    p.add_argument("--burn-in", type=int, default=defaults.BURN_ROUNDS)
     p.add_argument("--check-mixing", action="store_true")
     p.add_argument("--device", type=int, default=0)
     return p

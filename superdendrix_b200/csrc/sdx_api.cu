@@ -91,6 +91,9 @@ static void free_matrix(sdx_ctx *c) {
     c->resume.d_state = nullptr; c->resume.cap = 0; c->resume.valid = false;
     if (c->d_top) cudaFree(c->d_top);
     c->d_top = nullptr; c->cap_top = 0; c->top_K = 0;
+    if (c->d_burn_obs) cudaFree(c->d_burn_obs);
+    if (c->d_burn_rowsize) cudaFree(c->d_burn_rowsize);
+    c->d_burn_obs = nullptr; c->d_burn_rowsize = nullptr; c->cap_burn_obs = c->cap_burn_rowsize = 0;
     c->cap_feat = c->cap_samp = c->cap_obs = c->cap_rowsize = c->cap_pool = 0;
 }
 
@@ -196,7 +199,16 @@ __global__ void k_row_sizes(const uint32_t *__restrict__ rows, int R, int RS, in
     if (lane == 0) size[r] = c;
 }
 
-// batch of nb bit matrices (n_rows x wpr_in words each, dense) -> their transposes (n_cols x wpr_out words each)
+int sdx_row_sizes(sdx_ctx *c, const uint32_t *d_rows, int R, int RS, int *d_size) {
+    k_row_sizes<<<ceil_div(R, 8), 256, 0, c->stream>>>(d_rows, R, RS, d_size);
+    c->total_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return sdx_fail(c, SDX_ERR_CUDA, std::string("k_row_sizes launch failed: ") + cudaGetErrorString(e));
+    return SDX_OK;
+}
+
+// batch of nb bit matrices (n_rows x wpr_in words each, dense) -> their transposes (n_cols x wpr_out words each).  Every word of
+// the output is written (n_cols <= 32 * wpr_in), so it needs no clearing; row strides padded with zero words are fine.
 int sdx_transpose_batch(sdx_ctx *c, const uint32_t *d_in, int n_rows, int wpr_in, int n_cols, uint32_t *d_out, int wpr_out, int nb) {
     const int tiles = wpr_out * wpr_in;
     k_transpose_bits<<<dim3(ceil_div(tiles, 8), nb), 256, 0, c->stream>>>(d_in, n_rows, wpr_in, n_cols, d_out, wpr_out);

@@ -71,7 +71,16 @@ struct sdx_ctx {
     bool pool_valid = false;
     uint64_t pool_seed = 0;
     int64_t pool_T = 0;
-    uint16_t *d_top = nullptr;    // the top_K densest trade rows (size descending, index ascending): pair set of the burn-in trades
+    // Burn orientation (pool_begin): the burn-in rounds trade the rows of the orientation whose largest row
+    // is the smaller multiple of the mean row — the trade orientation itself (burn_alt = 0) or its transpose.
+    int burn_alt = 0;
+    int bR = 0, bwpr = 0, bRS = 0;        // rows, words per row, padded row stride of the burn orientation
+    int64_t burn_T = 0;                   // trades per burn-in round: 5 * bR (at most 60000)
+    uint32_t *d_burn_obs = nullptr;       // bR x bRS (burn_alt only; otherwise d_trade_obs serves)
+    int *d_burn_rowsize = nullptr;        // bR
+    size_t cap_burn_obs = 0, cap_burn_rowsize = 0;
+    uint16_t *d_top = nullptr;    // the top_K densest rows of the burn orientation (size descending, index ascending): pair set of the
+                                  // dense-favouring burn-in trades; top_K = 0: uniform pairs
     size_t cap_top = 0;
     int top_K = 0;
 

@@ -31,12 +31,15 @@ struct HostScore {               // optional fused scoring request
 };
 
 // scratch slots of the null paths (sdx_ctx::scratch); 10, 11, 14, 15 belong to sdx_scan.cu
-enum { SL_LVL = 0, SL_PLAN, SL_AUX, SL_MOD, SL_Z, SL_SCORES, SL_CARRY, SL_OUT, SL_APPLIED, SL_WORK, SL_PAIRS = 13, SL_RT = 16, SL_LN_STATE = 17, SL_LN_TMP = 18 };
+enum { SL_LVL = 0, SL_PLAN, SL_AUX, SL_MOD, SL_Z, SL_SCORES, SL_CARRY, SL_OUT, SL_APPLIED, SL_WORK, SL_PAIRS = 13, SL_RT = 16, SL_LN_STATE = 17, SL_LN_TMP = 18, SL_BURN = 19 };
 
 // sdx_curveball.cu
 int sdx_run_nulls(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t n_trades, int64_t chain_len,
                   uint32_t *out_rows, int64_t *applied, const HostScore *hs);
 int sdx_ensure_pool(sdx_ctx *c, uint64_t seed, int64_t T);      // burn-in pool as bit-packed states in c->d_pool
+// sdx_api.cu
+int sdx_row_sizes(sdx_ctx *c, const uint32_t *d_rows, int R, int RS, int *d_size);
+int sdx_transpose_batch(sdx_ctx *c, const uint32_t *d_in, int n_rows, int wpr_in, int n_cols, uint32_t *d_out, int wpr_out, int nb);
 // sdx_lanes.cu
 bool sdx_lanes_applicable(sdx_ctx *c, int64_t n_chains, int64_t T, bool fused_scoring);
 int sdx_run_nulls_lanes(sdx_ctx *c, uint64_t seed, uint64_t null0, int64_t n_nulls, int64_t T, int64_t chain_len,

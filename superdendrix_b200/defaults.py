@@ -6,5 +6,5 @@ sdx_set_pair_group) — the layout of the one-thread-per-null kernel k_trade_lan
 so that the start states of a block are one contiguous group of the pool."""
 PAIR_GROUP = 32
 CHAIN_LEN = 1
-BURN_ROUNDS = 6
+BURN_ROUNDS = 3          # burn-in rounds in the balanced orientation of the matrix (DESIGN.md 3b): stationary after 2 at C0
 POOL_SIZE = 1472         # 46 groups of 32 states

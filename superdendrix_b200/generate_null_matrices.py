@@ -48,7 +48,7 @@ def get_parser():
     parser.add_argument("-v", "--verbosity", default=logging.INFO, type=int, help="Flag verbose output")
     parser.add_argument("-rs", "--random_seed", default=1764, type=int, help="Seed for random number generator")
     parser.add_argument("--mode", default="chained", choices=["chained", "parallel", "restart"])
-    parser.add_argument("--burn-in", type=int, default=6, help="burn-in rounds of the pool states (parallel mode)")
+    parser.add_argument("--burn-in", type=int, default=defaults.BURN_ROUNDS, help="burn-in rounds of the pool states (parallel mode)")
     parser.add_argument("--device", type=int, default=0)
     parser.add_argument("--packed", default=None, help="write the packed nulls to this .npz")
     parser.add_argument("--no-tsv", action="store_true")
@@ -56,7 +56,7 @@ def get_parser():
     return parser
 
 
-def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None, burn_in=6):
+def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None, burn_in=defaults.BURN_ROUNDS):
     """Yields (first global null index, packed feature rows (n, F, ceil(S/32)) uint32) per device batch."""
     S, F = dense.shape
     eng = engine or Engine(device)
@@ -83,7 +83,7 @@ def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, ba
             eng.close()
 
 
-def generate(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None, burn_in=6):
+def generate(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None, burn_in=defaults.BURN_ROUNDS):
     """Yields (global null index, S x F uint8 matrix) for n_nulls nulls of ``dense`` (S x F)."""
     S = dense.shape[0]
     for first, rows in generate_packed(dense, n_nulls, seed, prefix, mode, device, batch, engine, burn_in):

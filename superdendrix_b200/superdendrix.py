@@ -102,7 +102,7 @@ def get_parser():
                         help="generate mode: randomise the full feature matrix and restrict to the profiled samples when scoring, as the "
                              "reference's generator + driver do [full], or randomise the matrix already restricted to the profiled samples")
     parser.add_argument("--mode", default="parallel", choices=["parallel", "chained", "restart"])
-    parser.add_argument("--burn-in", type=int, default=6, help="burn-in rounds of the pool states (parallel mode)")
+    parser.add_argument("--burn-in", type=int, default=defaults.BURN_ROUNDS, help="burn-in rounds of the pool states (parallel mode)")
     parser.add_argument("--check-mixing", action="store_true",
                         help="parallel mode: probe whether the burn-in pool is stationary for this matrix (a few hundred extra nulls) and say so in the log")
     parser.add_argument("--device", type=int, default=0)

@@ -32,7 +32,7 @@ class OracleEngine:
         n_ge = np.zeros(self.P, dtype=np.int64)
         if n_nulls:
             nulls, _ = oracle.curveball_nulls(self.trows, seed, null0, n_nulls, T, chain_len, burn=self.burn, pool_size=self.pool,
-                                              pair_group=self.pair_group)
+                                              pair_group=self.pair_group, L=max(self.S, self.F))
             for m in nulls:
                 fr = bitpack.pack_rows(bitpack.unpack_rows(m, max(self.S, self.F)).T) if self.ras else m
                 for p, mod in enumerate(modules):

@@ -162,7 +162,7 @@ def test_generate_null_matrices_cli_writes_reference_format(tmp_path):
     out4.mkdir()
     gnm.main(["-m", os.path.join(gdir, "features.tsv"), "-p", "5", "-o", str(out4) + "/", "-rs", "5", "--mode", "parallel", "--burn-in", "4"])
     want, _ = oracle.curveball_nulls(rows_of(dense), 5, 0, 5, 5 * R, defaults.CHAIN_LEN, burn=4, pool_size=defaults.POOL_SIZE,
-                                     pair_group=defaults.PAIR_GROUP)
+                                     pair_group=defaults.PAIR_GROUP, L=max(dense.shape))
     nd = i_o.dense_matrix(genes, samples, i_o.load_mutation_data(str(out4 / "4.tsv"))[5])
     assert np.array_equal(bitpack.pack_rows(nd if ras else nd.T), want[4])
 
@@ -215,7 +215,7 @@ def test_driver_end_to_end_against_oracle(tmp_path, stat, scope):
         d_gen = d
     obs = rows_of(d_gen)
     nulls, _ = oracle.curveball_nulls(obs, 9, 0, 64, 5 * obs.shape[0], defaults.CHAIN_LEN, burn=defaults.BURN_ROUNDS, pool_size=defaults.POOL_SIZE,
-                                      pair_group=defaults.PAIR_GROUP)     # --mode parallel (default)
+                                      pair_group=defaults.PAIR_GROUP, L=max(d_gen.shape))     # --mode parallel (default)
     ras = d_gen.shape[1] >= d_gen.shape[0]
     sc = []
     for m in nulls:
@@ -369,7 +369,7 @@ def test_fixed_query_cli_like_utils_compute_p_value(tmp_path):
     d = i_o.dense_matrix(names, smp, s2g)
     obs = rows_of(d)
     nulls, _ = oracle.curveball_nulls(obs, 5, 0, 96, 5 * obs.shape[0], defaults.CHAIN_LEN, burn=defaults.BURN_ROUNDS, pool_size=defaults.POOL_SIZE,
-                                      pair_group=defaults.PAIR_GROUP)
+                                      pair_group=defaults.PAIR_GROUP, L=max(d.shape))
     feats = sorted(names.index(g) for g in query)
     ras = d.shape[1] >= d.shape[0]
     sc = [oracle.score_set(bitpack.pack_rows(bitpack.unpack_rows(m_, max(d.shape)).T) if ras else m_, d.shape[0], feats, w[1])[0] for m_ in nulls]
@@ -464,7 +464,7 @@ def test_batched_screen_equals_per_profile_pipeline(tmp_path):
     obs = rows_of(dense)
     ras = F >= S
     nulls, _ = oracle.curveball_nulls(obs, seed, 0, n_nulls, 5 * obs.shape[0], defaults.CHAIN_LEN, burn=defaults.BURN_ROUNDS,
-                                      pool_size=defaults.POOL_SIZE, pair_group=defaults.PAIR_GROUP)
+                                      pool_size=defaults.POOL_SIZE, pair_group=defaults.PAIR_GROUP, L=max(dense.shape))
     for p in range(P):
         wm = np.where(mask[p], w[p], 0.0)
         mk = bitpack.pack_mask(np.nonzero(mask[p])[0], S)

@@ -55,7 +55,7 @@ def test_lane_kernel_matches_oracle_bit_for_bit(name, monkeypatch):
         eng.set_burn_in(burn, pool)
         got, ap = eng.curveball(1764, null0, n, chain_len=chain_len)
         assert eng.timing()["plan_ms"] == 0.0, "the request did not run on the lane kernel"
-    want, wap = oracle.curveball_nulls(obs, 1764, null0, n, 5 * R, chain_len, burn=burn, pool_size=pool, pair_group=32)
+    want, wap = oracle.curveball_nulls(obs, 1764, null0, n, 5 * R, chain_len, burn=burn, pool_size=pool, pair_group=32, L=max(dense.shape))
     assert np.array_equal(ap, wap)
     assert np.array_equal(got, want)
     L = max(dense.shape)
@@ -83,7 +83,7 @@ def test_lane_kernel_fused_scores_and_counts_match_oracle(monkeypatch):
         res = eng.null_pvalue(11, 32, n, modules, chain_len=1, want_scores=True)
         assert eng.timing()["plan_ms"] == 0.0
     obs = rows_of(dense)
-    nulls, _ = oracle.curveball_nulls(obs, 11, 32, n, 5 * obs.shape[0], 1, burn=2, pool_size=64, pair_group=32)
+    nulls, _ = oracle.curveball_nulls(obs, 11, 32, n, 5 * obs.shape[0], 1, burn=2, pool_size=64, pair_group=32, L=max(dense.shape))
     frows = bitpack.pack_rows(dense.T)
     for p in range(3):
         wm = np.where(mask[p], w[p], 0.0)

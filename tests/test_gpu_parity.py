@@ -7,10 +7,10 @@ import numpy as np
 import pytest
 
 import oracle
-from superdendrix_b200 import bitpack, synth
+from superdendrix_b200 import bitpack, defaults, synth
 from superdendrix_b200.engine import SDX_STAT_FIXED, SDX_STAT_MAXK, Engine, SdxError
 
-from conftest import GOLDEN, curveball_cases, load_npz, rows_of
+from conftest import GOLDEN, burn_cases, curveball_cases, load_npz, rows_of
 
 pytestmark = pytest.mark.gpu
 
@@ -780,7 +780,7 @@ def test_work_queue_kernel_is_bit_identical(monkeypatch):
                 assert np.array_equal(got_ap, want_ap), name
                 assert np.array_equal(got, want), name
             e2.set_burn_in(3, 7)
-            want, _ = oracle.curveball_nulls(obs, 5, 2, 20, 5 * R, 4, burn=3, pool_size=7)
+            want, _ = oracle.curveball_nulls(obs, 5, 2, 20, 5 * R, 4, burn=3, pool_size=7, L=max(S, F))
             got, _ = e2.curveball(5, 2, 20, -1, 4, want_applied=False)
             assert np.array_equal(got, want), name
             e2.set_burn_in(0)
@@ -1007,11 +1007,11 @@ def test_burn_in_pool_matches_oracle(monkeypatch, sparse):
         e2.upload_weights(w)
         e2.set_burn_in(6, 8)
         for seed, chain_len, null0, n in ((1764, 5, 3, 17), (99, 1, 0, 11), (1764, 4, 40, 9)):
-            want, want_ap = oracle.curveball_nulls(obs, seed, null0, n, 5 * R, chain_len, burn=6, pool_size=8)
+            want, want_ap = oracle.curveball_nulls(obs, seed, null0, n, 5 * R, chain_len, burn=6, pool_size=8, L=max(S, F))
             got, got_ap = e2.curveball(seed, null0, n, -1, chain_len)
             assert np.array_equal(got_ap, want_ap) and np.array_equal(got, want), (seed, chain_len)
         res = e2.null_pvalue(7, 0, 24, modules, chain_len=4, want_scores=True)
-        nulls, _ = oracle.curveball_nulls(obs, 7, 0, 24, 5 * R, 4, burn=6, pool_size=8)
+        nulls, _ = oracle.curveball_nulls(obs, 7, 0, 24, 5 * R, 4, burn=6, pool_size=8, L=max(S, F))
         frows = bitpack.pack_rows(dense.T)
         for p in range(2):
             feats = modules[p][modules[p] >= 0]
@@ -1026,7 +1026,7 @@ def test_burn_in_pool_matches_oracle(monkeypatch, sparse):
         upload_dense(e2, small)
         e2.upload_weights(ws)
         mk = e2.null_pvalue(7, 0, 6, np.array([[0, 1, 2]], dtype=np.int32), chain_len=3, stat=SDX_STAT_MAXK, want_scores=True)
-        nulls6, _ = oracle.curveball_nulls(rows_of(small), 7, 0, 6, 5 * 40, 3, burn=6, pool_size=8)
+        nulls6, _ = oracle.curveball_nulls(rows_of(small), 7, 0, 6, 5 * 40, 3, burn=6, pool_size=8, L=120)
         want_mk = [max(oracle.scan(m, 120, ws[0], 3, 1)[0][0], 0.0) for m in nulls6]
         assert np.allclose(mk["null_scores"][0], want_mk, rtol=0, atol=1e-9 * np.abs(ws[0]).sum())
         upload_dense(e2, dense)
@@ -1039,8 +1039,8 @@ def test_burn_in_pool_matches_oracle(monkeypatch, sparse):
 
 def test_burn_in_removes_the_memory_of_the_observed_matrix(eng):
     """C0: after 5*min(S,F) trades the densest feature still shares ~440 of its 469 carriers with the observed
-    matrix; the stationary overlap is ~296 (reached after ~30 rounds of uniform pairs, after ~3 burn-in rounds that take a
-    quarter of their pairs from the densest rows).  With the default burn-in of 6 rounds the nulls are there."""
+    matrix; the stationary overlap is ~296 (reached after ~30 rounds of feature-row trades, after 2 burn-in rounds of
+    sample-row trades: DESIGN.md 3b).  With the default burn-in the nulls are there."""
     dense, _, _ = synth.feature_matrix(770, 400)
     S, F = dense.shape
     upload_dense(eng, dense)
@@ -1054,9 +1054,33 @@ def test_burn_in_removes_the_memory_of_the_observed_matrix(eng):
         return float((bitpack.unpack_rows(rows[:, g, :], L).astype(np.int64) * obs_row).sum(1).mean())
     try:
         raw = overlap(0, 1, 200)
-        mixed = overlap(6, 8, 400)
+        mixed = overlap(defaults.BURN_ROUNDS, 8, 400)
         longer = overlap(32, 8, 400)
     finally:
         eng.set_burn_in(0)
     assert raw > mixed + 80                       # restart nulls remember the observed matrix
-    assert abs(mixed - longer) < 6                # 6 rounds are enough: five times the burn-in changes nothing
+    assert abs(mixed - longer) < 6                # the default is enough: ten times the burn-in changes nothing
+
+
+def test_burn_in_orientation_branches_match_oracle():
+    """The four ways a pool is burnt in (oracle: burn_plan_init): on the trade rows or on their transpose,
+    with uniform or with dense-favouring pairs.  Pool-started nulls are bit-identical to the oracle's in every branch,
+    on k_trade (pair_group 1) and with blocks of 32 chains sharing their row pairs."""
+    seen = set()
+    with Engine(0) as e2:
+        for name, (dense, alt, fav) in burn_cases().items():
+            obs = rows_of(dense)
+            R, L = obs.shape[0], max(dense.shape)
+            plan = oracle.burn_plan(obs, L)
+            assert (plan["alt"], plan["dense_rows"] > 0) == (alt, fav), name
+            seen.add((alt, fav))
+            upload_dense(e2, dense)
+            for pg, burn, pool, chain_len, null0, n in ((1, 2, 5, 3, 1, 11), (32, 3, 64, 1, 32, 70)):
+                e2.set_pair_group(pg)
+                e2.set_burn_in(burn, pool)
+                want, want_ap = oracle.curveball_nulls(obs, 41, null0, n, 5 * R, chain_len, burn=burn, pool_size=pool, pair_group=pg, L=L)
+                got, got_ap = e2.curveball(41, null0, n, -1, chain_len)
+                assert np.array_equal(got_ap, want_ap) and np.array_equal(got, want), (name, pg)
+            e2.set_pair_group(1)
+            e2.set_burn_in(0)
+    assert seen == {(False, False), (False, True), (True, False), (True, True)}

@@ -126,10 +126,10 @@ def test_lane_code_from_pool_states():
     R = obs.shape[0]
     T = 5 * R
     burn, pool_size, chain_len, seed = 2, 7, 2, 99
-    pool = np.stack([oracle.pool_state(obs, seed, T, burn, j) for j in range(pool_size)])
+    pool = np.stack([oracle.pool_state(obs, max(dense.shape), seed, burn, j) for j in range(pool_size)])
     got, got_ap, _, _ = run_group(lib, pool, ts, seed, 32, chain_len, 0, chain_len, T)
     want, want_ap = oracle.curveball_nulls(obs, seed, 32 * chain_len, 32 * chain_len, T, chain_len, burn=burn, pool_size=pool_size,
-                                           pair_group=32)
+                                           pair_group=32, L=max(dense.shape))
     want = want.reshape(32, chain_len, *obs.shape).transpose(1, 0, 2, 3)
     assert np.array_equal(got, want)
     assert np.array_equal(got_ap, want_ap.reshape(32, chain_len).T)

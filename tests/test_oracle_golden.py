@@ -10,7 +10,7 @@ import pytest
 
 import oracle
 from oracle import refport
-from superdendrix_b200 import bitpack, synth
+from superdendrix_b200 import bitpack, defaults, synth
 
 from conftest import GOLDEN, curveball_cases, load_npz, rows_of
 
@@ -289,7 +289,7 @@ def _autocorr_inflation(x, max_lag=20):
 
 
 def _null_sample(obs, S, F, module, w, n, **kw):
-    nulls, _ = oracle.curveball_nulls(obs, 31337, 0, n, 5 * obs.shape[0], **kw)
+    nulls, _ = oracle.curveball_nulls(obs, 31337, 0, n, 5 * obs.shape[0], L=max(S, F), **kw)
     ras = F >= S
     L = max(S, F)
     sc = np.array([oracle.score_set(bitpack.pack_rows(bitpack.unpack_rows(m, L).T) if ras else m, S, module, w)[0] for m in nulls])
@@ -330,3 +330,45 @@ def test_without_burn_in_restart_nulls_are_not_mixed():
     _, occ = _null_sample(rows_of(dense), S, F, module, w, 400, chain_len=1)
     diff = np.abs(occ - z["cell_mean"])
     assert diff.max() > 0.3                 # e.g. carriers of the densest feature keep it with p ~0.8 instead of ~0.36
+
+
+def test_burn_plan_branches_keep_the_margins():
+    """DESIGN.md 3b: the pool is burnt in on the trade rows or on their transpose, with uniform or dense-favouring pairs;
+    every branch returns states in the trade orientation with both margins of the observed matrix."""
+    from conftest import burn_cases
+    for name, (dense, alt, fav) in burn_cases().items():
+        obs = rows_of(dense)
+        L = max(dense.shape)
+        plan = oracle.burn_plan(obs, L)
+        assert (plan["alt"], plan["dense_rows"] > 0) == (alt, fav), name
+        assert plan["rows"] == (L if alt else obs.shape[0]) and plan["trades_per_round"] == 5 * plan["rows"]
+        ob = bitpack.unpack_rows(obs, L)
+        for j in range(3):
+            st = bitpack.unpack_rows(oracle.pool_state(obs, L, 5, 2, j), L)
+            assert np.array_equal(st.sum(0), ob.sum(0)) and np.array_equal(st.sum(1), ob.sum(1)), name
+            assert not np.array_equal(st, ob)
+        # state j is a pure function of (matrix, seed, burn, j) and is what the chains start from
+        nulls, _ = oracle.curveball_nulls(obs, 5, 0, 1, 0, 1, burn=2, pool_size=3, L=L)          # 0 trades: the null is its start state
+        assert np.array_equal(nulls[0], oracle.pool_state(obs, L, 5, 2, 0))
+
+
+def test_burn_in_on_the_balanced_orientation_is_stationary_after_two_rounds():
+    """C0 (770 x 384): feature rows reach 469 carriers (44 x the mean row), sample rows 13 features (2.5 x), so the
+    burn-in trades sample rows.  Ones shared with the observed matrix, one ordinary round after the pool state: 567 after
+    one burn-in round, 558 after two, three and eight (stationary; 30 rounds of feature-row trades get there)."""
+    dense, _, _ = synth.feature_matrix(770, 400, seed=20)
+    S, F = dense.shape
+    obs = rows_of(dense)
+    assert oracle.burn_plan(obs, S) == {"alt": True, "rows": S, "trades_per_round": 5 * S, "dense_rows": 0}
+    n = 500
+
+    def shared(burn):
+        nulls, _ = oracle.curveball_nulls(obs, 77, 0, n, 5 * F, 1, burn=burn, pool_size=n, L=S)
+        ov = bitpack.popcount_rows(nulls & obs[None]).sum(1)
+        return ov.mean(), ov.std() / np.sqrt(n)
+    m2, s2 = shared(2)
+    m3, s3 = shared(defaults.BURN_ROUNDS)
+    m8, s8 = shared(8)
+    assert abs(m2 - m8) < 4.5 * np.hypot(s2, s8) and abs(m3 - m8) < 4.5 * np.hypot(s3, s8)
+    raw, _ = oracle.curveball_nulls(obs, 77, 0, 100, 5 * F, 1)
+    assert bitpack.popcount_rows(raw & obs[None]).sum(1).mean() > m8 + 500        # restarts from the observed matrix: ~1 285 shared ones

@@ -26,7 +26,7 @@ def check(S, F, n, chain_len, null0, burn=0, pool=7, dens=None, seed=1764):
         eng.set_burn_in(burn, pool)
         R = obs.shape[0]
         got, ap = eng.curveball(seed, null0, n, chain_len=chain_len)
-        want, wap = oracle.curveball_nulls(obs, seed, null0, n, 5 * R, chain_len, burn=burn, pool_size=pool, pair_group=32)
+        want, wap = oracle.curveball_nulls(obs, seed, null0, n, 5 * R, chain_len, burn=burn, pool_size=pool, pair_group=32, L=max(S, F))
         ok = np.array_equal(got, want) and np.array_equal(ap, wap)
         print("parity S=%d F=%d n=%d chain=%d null0=%d burn=%d: %s  (launches %d, trade %.2f ms)" % (
             S, F, n, chain_len, null0, burn, "OK" if ok else "MISMATCH", eng.timing()["trade_launches"], eng.timing()["trade_ms"]), flush=True)
@@ -55,7 +55,7 @@ def main():
     with Engine(0) as eng:
         eng.upload_dense(dense)
         eng.upload_weights(w)
-        eng.set_burn_in(6, 1472)
+        eng.set_burn_in(defaults.BURN_ROUNDS, defaults.POOL_SIZE)
         res = {}
         for pg, cl in ((1, 16), (32, 16), (32, 4), (32, 3), (32, 2), (32, 1)):
             eng.set_pair_group(pg)

@@ -15,7 +15,7 @@ with Engine(0) as eng:
     eng.upload_dense(dense)
     eng.upload_weights(w)
     eng.set_pair_group(32)
-    eng.set_burn_in(6, 1472)
+    eng.set_burn_in(defaults.BURN_ROUNDS, defaults.POOL_SIZE)
     for _ in range(2):
         r = eng.null_pvalue(1764, 0, n, [module], chain_len=cl)
     print(r["n_ge"], eng.timing())
