@@ -95,6 +95,66 @@ __global__ void __launch_bounds__(PL_NT) k_plan_levels(const __grid_constant__ P
     if (n < n_local) depth[n] = d;
 }
 
+// One WARP per null — the variant for few nulls (the burn-in pool: a few thousand rounds of 5 * R_b trades), where the
+// kernel above is pure latency (one thread draws and walks ~4 000 trades: 1.3 ms however few nulls there are).  The lanes
+// draw the pairs of 32 trades at once, lane 0 walks them through the warp's last[] table (a single thread: program
+// order, no barrier inside the walk), and pairs and levels leave coalesced.  Same schedule as k_plan_levels with cap = 0.
+// Shared memory per warp: last[R] (LT, padded to 16 bytes) | 32 pairs u32 | 32 levels u16.
+#define PLW_WARPS 4
+template <typename LT>
+__global__ void __launch_bounds__(PLW_WARPS * 32) k_plan_levels_warp(const __grid_constant__ PhiloxKeys keys, NullIndexing ix, int n_local, int R, int T,
+                                                                     int Tp, uint32_t *__restrict__ pairs, uint16_t *__restrict__ lvl,
+                                                                     int *__restrict__ depth, int dcap, const uint16_t *__restrict__ top, int top_K) {
+    extern __shared__ __align__(16) uint16_t plan_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n = blockIdx.x * PLW_WARPS + wid;
+    if (n >= n_local) return;                                      // whole warps
+    const size_t last_bytes = (((size_t)R * sizeof(LT) + 15) / 16) * 16;
+    unsigned char *base = reinterpret_cast<unsigned char *>(plan_smem) + (size_t)wid * (last_bytes + 32 * 4 + 32 * 2);
+    LT *last = reinterpret_cast<LT *>(base);
+    volatile uint32_t *st_p = reinterpret_cast<uint32_t *>(base + last_bytes);
+    volatile uint16_t *st_l = reinterpret_cast<uint16_t *>(base + last_bytes + 32 * 4);
+    for (int r = lane; r < R; r += 32) last[r] = 0;
+    const uint64_t null_id = ix.id(n);
+    const bool burn = top_K >= 2 && null_id >= SDX_BURN_ID_MIN;
+    const uint64_t pair_id = ix.pair_id(null_id);
+    int d = 0;
+    __syncwarp();
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        const int t = t0 + lane, cnt = T - t0 < 32 ? T - t0 : 32;
+        uint32_t e = 0;
+        if (t < T) {
+            uint32_t a, b;
+            if (burn) trade_pair_burn(keys, null_id, (uint32_t)t, (uint32_t)R, top, (uint32_t)top_K, a, b);
+            else trade_pair(keys, pair_id, (uint32_t)t, (uint32_t)R, a, b);
+            e = a | (b << 16);
+        }
+        st_p[lane] = e;
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const uint32_t q = st_p[i];
+                const uint32_t a = q & 0xffffu, b = q >> 16;
+                const int la = last[a], lb = last[b];
+                int l = (la > lb ? la : lb) + 1;
+                if (l > dcap) l = dcap;
+                last[a] = (LT)l;
+                last[b] = (LT)l;
+                st_l[i] = (uint16_t)l;
+                d = l > d ? l : d;
+            }
+        }
+        __syncwarp();
+        if (t < T) {
+            lvl[(size_t)n * T + t] = st_l[lane];
+            pairs[(size_t)n * Tp + t] = e;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) depth[n] = d;
+}
+
 // ---------------------------------------------------------------------------
 // plan: counting sort by level (one warp per null)
 // ---------------------------------------------------------------------------
