@@ -236,7 +236,7 @@ LN_HD void ln_bb_count(const uint32_t *A, const uint32_t *B, int nw, uint32_t &L
     La = 0; Lb = 0;
 #pragma unroll 1
     for (int w = 0; w < nw; ++w) {
-        const uint32_t a = A[w * LN_W], b = B[w * LN_W];
+        const uint32_t a = LN_LDCG32(A + w * LN_W), b = LN_LDCG32(B + w * LN_W);      // L2: the rows are also rewritten by bulk stores
         La += LN_POPC(a & ~b);
         Lb += LN_POPC(b & ~a);
     }
@@ -247,7 +247,7 @@ LN_HD void ln_bb_phase2(uint32_t *A, uint32_t *B, int nw, const uint32_t *C, con
     uint32_t rank = 0;
 #pragma unroll 1
     for (int w = 0; w < nw; ++w) {
-        const uint32_t a = A[w * LN_W], b = B[w * LN_W];
+        const uint32_t a = LN_LDCG32(A + w * LN_W), b = LN_LDCG32(B + w * LN_W);
         const uint32_t sym = a ^ b, cnt = LN_POPC(sym);
         if (cnt) {
             const uint32_t w0 = rank >> 5;

@@ -264,6 +264,7 @@ __global__ void __maxnreg__(REGS) k_trade_lanes(const __grid_constant__ LaneArgs
                     applied += tr.deal.go ? 1u : 0u;
                 }
                 fence_proxy_async_smem();                   // bulk stores read, and the next bulk load overwrites, what the lanes just wrote
+                if (ba && bb) fence_proxy_async();          // two bit-packed rows were rewritten in place (generic proxy): a later bulk load of one must see it
                 __syncwarp();
                 // the rows of trade t + 1 / t + 2 that are fetched now
                 const uint32_t u1 = (uint32_t)t + 1, u2 = (uint32_t)t + 2;

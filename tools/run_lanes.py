@@ -9,7 +9,7 @@ os.environ.setdefault("SDX_LANE_MIN_CHAINS", "1")
 import numpy as np
 
 import oracle
-from superdendrix_b200 import bitpack, synth
+from superdendrix_b200 import bitpack, defaults, synth
 from superdendrix_b200.engine import Engine
 
 

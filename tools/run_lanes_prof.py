@@ -3,7 +3,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from superdendrix_b200 import synth
+from superdendrix_b200 import defaults, synth
 from superdendrix_b200.engine import Engine
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 37888
