@@ -174,7 +174,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "nulls/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -356,7 +356,7 @@ def run_ours(args):
                                 "sample": "%d chained nulls of the same matrix/module in %.1f s, oracle/refport.py (the reference's "
                                           "Python algorithm, CPython %s)" % (args.cpu_nulls, cpu_dt, sys.version.split()[0])}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -684,9 +684,23 @@ def main():
     ap.add_argument("--cpu-nulls", type=int, default=300, help="size of the CPU baseline sample")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print there (NCCL's version banner under NCCL_DEBUG, CLI
+    # logs) goes to stderr; the line itself is written to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
+
+
+_OUT = sys.stdout
+
+
+def emit(line):
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
 
 
 if __name__ == "__main__":

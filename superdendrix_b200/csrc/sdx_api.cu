@@ -166,8 +166,10 @@ extern "C" int sdx_total_launches(const sdx_ctx *c, int64_t *n) {
 }
 
 // ---------------------------------------------------------------------------
-// bit transpose: F x wprS (feature rows) -> S x wprF (sample rows).
-// One warp per (feature word fw, sample word sw) tile of 32 x 32 bits.
+// bit transpose: n_rows x wpr_in (rows over n_cols bits) -> n_cols x wpr_out.
+// One warp per 32 x 32 bit tile (row word rw of the output, column word cw of the input): lane l loads word cw of row
+// 32 rw + l, five shuffle-and-mask steps swap ever smaller off-diagonal blocks (the recursive transpose), after which
+// lane l holds word rw of output row 32 cw + l.
 // ---------------------------------------------------------------------------
 __global__ void k_transpose_bits(const uint32_t *__restrict__ in, int n_rows, int wpr_in, int n_cols,
                                  uint32_t *__restrict__ out, int wpr_out) {
@@ -179,13 +181,16 @@ __global__ void k_transpose_bits(const uint32_t *__restrict__ in, int n_rows, in
     const int rw = tile / tiles_c, cw = tile - rw * tiles_c;     // row word (of out), col word (of in)
     if (rw >= wpr_out) return;
     const int r = rw * 32 + lane;
-    const uint32_t x = (r < n_rows) ? in[(size_t)r * wpr_in + cw] : 0u;
+    uint32_t x = (r < n_rows) ? in[(size_t)r * wpr_in + cw] : 0u;
+    uint32_t m = 0x0000ffffu;
 #pragma unroll
-    for (int b = 0; b < 32; ++b) {
-        uint32_t v = __ballot_sync(0xffffffffu, (x >> b) & 1u);
-        int col = cw * 32 + b;
-        if (lane == 0 && col < n_cols) out[(size_t)col * wpr_out + rw] = v;
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t p = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? (((p >> j) & m) | (x & ~m)) : ((x & m) | ((p & m) << j));
+        m ^= m << (j >> 1);
     }
+    const int col = cw * 32 + lane;
+    if (col < n_cols) out[(size_t)col * wpr_out + rw] = x;
 }
 
 // popcount of every trade row: one warp per row
