@@ -50,6 +50,7 @@ def get_parser():
     p.add_argument("--null-batch", type=int, default=1024)
     p.add_argument("--mode", default="parallel", choices=["parallel", "chained", "restart"])
     p.add_argument("--burn-in", type=int, default=defaults.BURN_ROUNDS)
+    p.add_argument("--pool-size", type=int, default=defaults.POOL_SIZE)
     p.add_argument("--check-mixing", action="store_true")
     p.add_argument("--device", type=int, default=0)
     return p

@@ -49,6 +49,7 @@ def get_parser():
     parser.add_argument("-rs", "--random_seed", default=1764, type=int, help="Seed for random number generator")
     parser.add_argument("--mode", default="chained", choices=["chained", "parallel", "restart"])
     parser.add_argument("--burn-in", type=int, default=defaults.BURN_ROUNDS, help="burn-in rounds of the pool states (parallel mode)")
+    parser.add_argument("--pool-size", type=int, default=defaults.POOL_SIZE, help="pool states the chains start from (parallel mode; a multiple of 32).  Nulls that share a state are correlated: a larger pool raises the effective sample size of large -p runs at ~1.4 us per state (DESIGN.md 3b)")
     parser.add_argument("--device", type=int, default=0)
     parser.add_argument("--packed", default=None, help="write the packed nulls to this .npz")
     parser.add_argument("--no-tsv", action="store_true")
@@ -56,7 +57,8 @@ def get_parser():
     return parser
 
 
-def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None, burn_in=defaults.BURN_ROUNDS):
+def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, batch=1024, engine=None, burn_in=defaults.BURN_ROUNDS,
+                    pool_size=defaults.POOL_SIZE):
     """Yields (first global null index, packed feature rows (n, F, ceil(S/32)) uint32) per device batch."""
     S, F = dense.shape
     eng = engine or Engine(device)
@@ -64,7 +66,7 @@ def generate_packed(dense, n_nulls, seed, prefix=0, mode="chained", device=0, ba
         eng.upload_dense(dense)
         R, L, wpr, rows_are_samples = eng.trade_shape()
         chain_len = {"chained": max(int(n_nulls), 1), "parallel": defaults.CHAIN_LEN, "restart": 1}[mode]
-        eng.set_burn_in(burn_in if mode == "parallel" else 0, defaults.POOL_SIZE)
+        eng.set_burn_in(burn_in if mode == "parallel" else 0, pool_size)
         eng.set_pair_group(defaults.PAIR_GROUP if mode == "parallel" else 1)
         # a chain starts at a multiple of chain_len: with prefix a multiple of n_nulls every process owns one chain; the
         # library keeps the chain's state between the batches below, so a batch continues where the previous one stopped
@@ -107,7 +109,8 @@ def main(argv=None):
     dense = dense_matrix(genes, samples, samples_to_genes)
     print(len(samples), len(genes))
     packed, ids = [], []
-    for first, rows in generate_packed(dense, max(args.p_val_it, 0), args.random_seed, args.prefix, args.mode, args.device, args.batch, burn_in=args.burn_in):
+    for first, rows in generate_packed(dense, max(args.p_val_it, 0), args.random_seed, args.prefix, args.mode, args.device, args.batch, burn_in=args.burn_in,
+                                       pool_size=args.pool_size):
         if not args.no_tsv:
             write_nulls_tsv(args.output_file, first, rows, samples, genes)      # multi-threaded C++ writer, reference format
         if args.packed:

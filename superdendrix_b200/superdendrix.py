@@ -23,7 +23,7 @@ Added, non-breaking flags:
                             reference's generator + driver, default) or on the matrix restricted to the profiled samples
   --null-batch N            files: null files parsed and scored per library call (sdx_null_pvalue_rows)
   --mode parallel|chained|restart   generated nulls: parallel (default) = every null one ordinary round away from a burnt-in
-                            pool state (6 dense-favouring rounds), blocks of 32 nulls sharing their row pairs — stationary like
+                            pool state (3 burn-in rounds on the balanced orientation), blocks of 32 nulls sharing their row pairs — stationary like
                             the reference's long chain and enough independent units to fill the GPUs; chained = ONE chain from the observed matrix, exactly the reference's
                             semantics (src/generate_null_matrices.py:71-74); restart = every null 5*min(S,F) trades from
                             the observed matrix (src/curveball_main.py:136; NOT mixed for dense features)
@@ -103,6 +103,7 @@ def get_parser():
                              "reference's generator + driver do [full], or randomise the matrix already restricted to the profiled samples")
     parser.add_argument("--mode", default="parallel", choices=["parallel", "chained", "restart"])
     parser.add_argument("--burn-in", type=int, default=defaults.BURN_ROUNDS, help="burn-in rounds of the pool states (parallel mode)")
+    parser.add_argument("--pool-size", type=int, default=defaults.POOL_SIZE, help="pool states the chains start from (parallel mode; a multiple of 32).  Nulls that share a state are correlated: a larger pool raises the effective sample size of large -p runs at ~1.4 us per state (DESIGN.md 3b)")
     parser.add_argument("--check-mixing", action="store_true",
                         help="parallel mode: probe whether the burn-in pool is stationary for this matrix (a few hundred extra nulls) and say so in the log")
     parser.add_argument("--device", type=int, default=0)
@@ -302,7 +303,7 @@ def null_loop(genes, samples, profile, events_to_samples, module, zP, args, logg
             eng.upload_matrix(pack_features(genes, samples, events_to_samples), len(samples))
             eng.upload_weights(w_vec)
             mod = np.array([[gidx[g] for g in module] + [-1] * (max(k, 1) - k)], dtype=np.int32)
-        eng.set_burn_in(burn, defaults.POOL_SIZE)
+        eng.set_burn_in(burn, args.pool_size)
         eng.set_pair_group(defaults.PAIR_GROUP if args.mode == "parallel" else 1)
         if args.check_mixing and args.mode == "parallel":
             from . import mixing
