@@ -260,9 +260,9 @@ __host__ __device__ __forceinline__ void trade_pair(const PhiloxKeys &k, uint64_
     if (b >= a) b++;
 }
 
-// Pair of a BURN-IN trade (oracle: trade_pair_burn): with probability 1/4 both rows come from the K densest
-// rows (top[]), otherwise the pair is uniform.  A fixed pair distribution (row sizes never change), so the stationary
-// distribution stays uniform, and dense x dense trades make the dense rows forget the observed matrix in ~3 rounds.
+// Pair of a BURN-IN trade when even the burn orientation has dominant rows (oracle: trade_pair_burn; the
+// caller uses the plain trade_pair when K < 2): with probability 1/4 both rows come from the K densest rows (top[]), otherwise
+// the pair is uniform.  A fixed pair distribution (row sizes never change), so the stationary distribution stays uniform.
 __device__ __forceinline__ void trade_pair_burn(const PhiloxKeys &k, uint64_t null_id, uint32_t t, uint32_t R,
                                                 const uint16_t *__restrict__ top, uint32_t K, uint32_t &a, uint32_t &b) {
     ThreadStream s(k, SDX_STREAM_PAIR, null_id, t);

@@ -23,8 +23,9 @@
 // ahead; a trade between two bit-packed rows (1 %) works in place in the group state.  A warp needs 6 list buffers + X +
 // the prefix popcounts (C1: 10 KB), so 22 warps share an SM.
 //
-// The burn-in pool (sdx_set_burn_in) is still built by k_trade — 1 480 states are too few lanes for this kernel and
-// its dense x dense trades want the cooperative kernel — and converted once to the lane layout (k_ln_compact): whole
+// The burn-in pool (sdx_set_burn_in) is built by k_trade — 1 472 states are too few lanes for this kernel (a warp needs
+// 6.8 ms per round however few groups there are), and its rounds trade the other orientation of the matrix (DESIGN.md
+// 3b) — and converted once to the lane layout (k_ln_compact): whole
 // groups when the pool size is a multiple of 32 (a chain's start state is then one block copy), compact states otherwise.
 #include <algorithm>
 

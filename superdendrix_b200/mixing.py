@@ -1,6 +1,6 @@
 """Run-time check that the burn-in pool is mixed.
 
-The pool's burn-in schedule (rounds, share of dense x dense trades) was tuned on one matrix shape.  This check costs a few
+The pool's burn-in rule (which orientation of the matrix the rounds trade, how many rounds: DESIGN.md 3b) was derived on mutation-matrix shapes.  This check costs a few
 hundred extra nulls and needs nothing but the public engine calls: chains of `rounds` nulls are started from the pool and the
 number of ones each null shares with the OBSERVED matrix is compared between the first and the last null of the chains.  From
 stationary start states the expected overlap does not depend on the position in the chain; from start states that still

@@ -185,8 +185,8 @@ def _autocorr_inflation(x, max_lag=200):
 def test_c0_shipped_defaults_sample_the_reference_chains_null_distribution():
     """North star (3) on the bench workload: tests/golden/nulldist_c0.npz holds SuperW of the bench module on 4 000
     CONSECUTIVE nulls of the reference's own chain (src/generate_null_matrices.py:71-74 driving src/curveball.py:17-40 with
-    CPython's random; made by tests/golden/make_golden.py).  The shipped defaults — burn-in pool of 1 472 states, 6
-    dense-favouring rounds, every null ONE ordinary round from a pool state, blocks of 32 nulls sharing their row pairs, the
+    CPython's random; made by tests/golden/make_golden.py).  The shipped defaults — burn-in pool of 1 472 states, 3
+    burn-in rounds on the sample rows, every null ONE ordinary round from a pool state, blocks of 32 nulls sharing their row pairs, the
     lane kernel — must sample the same stationary distribution: p-value, mean, spread and exceedance probabilities at three
     reference quantiles within Monte-Carlo error.  The reference series is one Markov chain: its error is inflated by its
     integrated autocorrelation time; ours by the nulls that share a pool state (68 per state at 100 000 nulls)."""

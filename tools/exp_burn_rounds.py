@@ -1,4 +1,4 @@
-"""Mixing after b burn-in rounds (dense-favouring pair draw), measured on the GPU path: ones shared with the
+"""Mixing after b burn-in rounds, measured on the GPU path: ones shared with the
 observed matrix by nulls that are ONE ordinary round away from a pool state.  C0 shape."""
 import os, sys
 import numpy as np
