@@ -153,12 +153,14 @@ static __device__ __noinline__ uint32_t ln_make_entries(const PhiloxKeys *keys, 
 // REGS: registers per thread.  80 keeps 22 warps (the groups of 100 000 nulls in ONE wave) resident per SM; 128 has no
 // spills and is what a launch with fewer groups than that runs (registers are allocated in units of 512 per warp, so 88
 // would already drop to 20 warps).
-template <bool M64, int REGS>
+// SLOT_C: the size of a list buffer as a compile-time constant (1 088 B = lists of up to 16 entries + sentinel, the common case:
+// every buffer of the warp is then an immediate offset from one base register), or 0 = taken from the arguments.
+template <bool M64, int REGS, int SLOT_C>
 __global__ void __maxnreg__(REGS) k_trade_lanes(const __grid_constant__ LaneArgs p) {
     extern __shared__ __align__(128) uint8_t ln_smem[];
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, WPC = blockDim.x >> 5;
-    const int R = p.R, T = p.T, nw = p.wprL, SLOT = p.slot_bytes;
+    const int R = p.R, T = p.T, nw = p.wprL, SLOT = SLOT_C ? SLOT_C : p.slot_bytes;
     uint2 *s_desc = reinterpret_cast<uint2 *>(ln_smem);
     for (int i = threadIdx.x; i < R; i += blockDim.x) s_desc[i] = p.desc[i];
     // per warp: stage 0 (lists a, b) | out (a, b) | stage 1 (a, b) | X | PF4 | three mbarriers
@@ -371,9 +373,11 @@ static int ln_layout(sdx_ctx *c) {
 
 struct LnGeom { int wpc, grid, desc_bytes, warp_bytes; size_t smem; bool m64; const void *kern; };
 
-static const void *ln_kernel(bool m64, bool wide) {
-    if (m64) return wide ? (const void *)k_trade_lanes<true, 128> : (const void *)k_trade_lanes<true, 80>;
-    return wide ? (const void *)k_trade_lanes<false, 128> : (const void *)k_trade_lanes<false, 80>;
+#define LN_SLOT_FIXED 1088
+static const void *ln_kernel(bool m64, bool wide, int slot_bytes) {
+    if (m64) return wide ? (const void *)k_trade_lanes<true, 128, 0> : (const void *)k_trade_lanes<true, 80, 0>;
+    if (slot_bytes == LN_SLOT_FIXED) return wide ? (const void *)k_trade_lanes<false, 128, LN_SLOT_FIXED> : (const void *)k_trade_lanes<false, 80, LN_SLOT_FIXED>;
+    return wide ? (const void *)k_trade_lanes<false, 128, 0> : (const void *)k_trade_lanes<false, 80, 0>;
 }
 
 // Warps per CTA and grid for n_groups groups: as many resident warps per SM as shared memory and registers allow, but
@@ -391,7 +395,7 @@ static bool ln_geometry(sdx_ctx *c, int64_t n_groups, LnGeom *g) {
     double best_cost = 1e300;
     const void *best_kern = nullptr;
     for (int wide = 1; wide >= 0; --wide) {              // the 128-register variant first: it wins ties
-        const void *kern = ln_kernel(g->m64, wide != 0);
+        const void *kern = ln_kernel(g->m64, wide != 0, c->ln_slot_bytes);
         for (int wpc : cand) {
             if (c->knobs.lane_wpc > 0 && wpc != c->knobs.lane_wpc) continue;
             const size_t need = (size_t)g->desc_bytes + (size_t)wpc * wb;
