@@ -11,8 +11,9 @@ struct NullIndexing {          // local null index (within a launch) -> global n
     int seg_len;               // nulls per chain in this launch
     uint64_t null_lo, null_hi; // requested range [null_lo, null_hi)
     int pair_group;            // sdx_set_pair_group: 1, or 32 = aligned blocks of 32 chains share the PAIR stream of their first chain
+    int chain_stride;          // 1; pair_group when the index runs over the first chains of the blocks only (the plan kernels: one plan per block)
     __host__ __device__ uint64_t id(int64_t local) const {
-        return (chain0 + (uint64_t)(local / seg_len)) * (uint64_t)chain_len + (uint64_t)seg_off + (uint64_t)(local % seg_len);
+        return (chain0 + (uint64_t)(local / seg_len) * (uint64_t)chain_stride) * (uint64_t)chain_len + (uint64_t)seg_off + (uint64_t)(local % seg_len);
     }
     // stream id the row pairs of null `id` are drawn from: round j of chain c uses the pairs of round j of
     // chain c - c % pair_group, so a block of pair_group chains walks the same schedule of row pairs

@@ -27,6 +27,7 @@ struct TradeArgs {
     ScoreArgs sc;
     const uint32_t *pool;             // burn-in pool: pool_size start states in the kernel's state layout, or null
     int pool_size;
+    int plan_group;                   // 0: one plan per null; g: the chains of an aligned block of g share their plans (pair_group), stored once per block
 };
 
 // out-of-line copy of the scorer for the trade kernel: keeps its registers out of the trade loop's budget
@@ -72,9 +73,12 @@ __global__ void __launch_bounds__(lb_threads(LB), lb_blocks(LB)) k_trade(const _
             if (T > 0) {
                 // One table entry per round (k_plan_sort): first plan entry, number of trades, "last round of its level".
                 // The next round's trade and the descriptor after that are in flight while the current trades run.
-                const uint2 *pl = p.plan + (size_t)local * T;
-                const uint32_t *rt = p.rt + (size_t)local * p.rt_stride;
-                const int NR = p.nrounds[local];
+                // blocks of chains that share their schedule of row pairs share its plan: planned once per block
+                const int64_t plocal = p.plan_group ? (int64_t)((p.ix.chain0 + (uint64_t)u) / (uint64_t)p.plan_group - p.ix.chain0 / (uint64_t)p.plan_group) * p.ix.seg_len + j
+                                                    : local;
+                const uint2 *pl = p.plan + (size_t)plocal * T;
+                const uint32_t *rt = p.rt + (size_t)plocal * p.rt_stride;
+                const int NR = p.nrounds[plocal];
                 const uint2 none = make_uint2(0u, 0u);
                 uint32_t q = NR > 0 ? rt[0] : 0u;
                 uint32_t q_n = NR > 1 ? rt[1] : 0u;
