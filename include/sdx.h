@@ -134,7 +134,9 @@ int sdx_curveball_features(sdx_ctx *ctx, uint64_t seed, uint64_t null0, int64_t 
  * stationary only because null i has already seen (i+1) rounds (src/generate_null_matrices.py:73-74).  With
  * burn_rounds > 0 every chain starts, instead of from the observed matrix, from one of pool_size start states:
  * state j = the observed matrix after burn_rounds burn-in rounds drawn from reserved stream ids
- * ((2^61 / burn_rounds + j) * burn_rounds + r, r < burn_rounds); chain c uses state c % pool_size.
+ * ((B + j) * burn_rounds + r, r < burn_rounds, B = 2^61 / burn_rounds rounded up to a multiple of 32; the states of an
+ * aligned block of 32 share their schedule of row pairs — round r of state j draws its pairs from the stream of round r
+ * of state j - j % 32 and deals the elements from its own, cf. sdx_set_pair_group); chain c uses state c % pool_size.
  * The burn-in rounds trade the rows of the orientation of the matrix whose largest row is the smaller multiple of
  * its mean row — the transpose of the trade orientation iff L <= 12000 and max_col * L < max_row * R (R x L = the
  * trade orientation): both orientations keep both margins and have the uniform stationary distribution, but a row

@@ -255,13 +255,14 @@ static void trade_pair_burn(uint64_t seed, uint64_t null_id, uint32_t t, uint32_
     }
 }
 
-static int64_t curveball_burn_round(uint32_t *rows, int R, int wpr, uint64_t seed, uint64_t null_id, int64_t n_trades,
+/* null_id: the stream the elements are dealt from (the round's own id); pair_id: the stream the row pairs are drawn from */
+static int64_t curveball_burn_round(uint32_t *rows, int R, int wpr, uint64_t seed, uint64_t null_id, uint64_t pair_id, int64_t n_trades,
                                     const uint16_t *top, uint32_t K) {
     uint32_t *chosen = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)wpr + 1));
     int64_t applied = 0;
     for (int64_t t = 0; t < n_trades; ++t) {
         uint32_t a, b;
-        trade_pair_burn(seed, null_id, (uint32_t)t, (uint32_t)R, top, K, &a, &b);
+        trade_pair_burn(seed, pair_id, (uint32_t)t, (uint32_t)R, top, K, &a, &b);
         applied += trade_canonical(rows + (size_t)a * wpr, rows + (size_t)b * wpr, wpr, seed, null_id, (uint32_t)t, chosen);
     }
     free(chosen);
@@ -340,14 +341,18 @@ static void burn_plan_init(burn_plan *bp, const uint32_t *observed, int R, int w
 
 static void burn_plan_free(burn_plan *bp) { free(bp->obs); free(bp->top); }
 
-/* start state j of the pool, in the trade orientation (R x wpr): `burn` rounds on the reserved stream ids
- * ((2^61 / burn + j) * burn + r), r < burn, from the observed matrix */
+/* start state j of the pool, in the trade orientation (R x wpr): `burn` rounds from the observed matrix on the reserved
+ * stream ids (B + j) * burn + r, r < burn, with B = 2^61 / burn rounded UP to a multiple of 32.  Like the nulls (DESIGN.md
+ * §3c) the states of an aligned block of 32 share their schedule of row pairs: round r of state j draws its pairs from the
+ * stream of round r of state j - j % 32 and deals the elements from its own stream. */
 static void burn_state(const burn_plan *bp, int R, int wpr, uint64_t seed, int64_t burn, int j, uint32_t *out) {
     size_t wb = (size_t)bp->Rb * bp->wprb;
     uint32_t *st = (uint32_t *)malloc(sizeof(uint32_t) * wb);
     memcpy(st, bp->obs, sizeof(uint32_t) * wb);
-    uint64_t base = ((1ull << 61) / (uint64_t)burn + (uint64_t)j) * (uint64_t)burn;
-    for (int64_t r = 0; r < burn; ++r) curveball_burn_round(st, bp->Rb, bp->wprb, seed, base + (uint64_t)r, bp->Tb, bp->top, bp->K);
+    uint64_t B = (((1ull << 61) / (uint64_t)burn + 31) / 32) * 32;
+    uint64_t base = (B + (uint64_t)j) * (uint64_t)burn, lead = (B + (uint64_t)(j - j % 32)) * (uint64_t)burn;
+    for (int64_t r = 0; r < burn; ++r)
+        curveball_burn_round(st, bp->Rb, bp->wprb, seed, base + (uint64_t)r, lead + (uint64_t)r, bp->Tb, bp->top, bp->K);
     if (bp->alt) transpose_bits(st, bp->Rb, bp->wprb, R, out, wpr);
     else memcpy(out, st, sizeof(uint32_t) * wb);
     free(st);

@@ -278,8 +278,9 @@ __device__ __forceinline__ void trade_pair_burn(const PhiloxKeys &k, uint64_t nu
         if (b >= a) b++;
     }
 }
-#define SDX_POOL_BASE (1ull << 61)      // stream ids of the burn-in rounds start at floor(2^61 / burn) * burn > 2^61 - burn ...
+#define SDX_POOL_BASE (1ull << 61)      // burn-in round r of pool state j has stream id (B + j) * burn + r, B = 2^61 / burn rounded up to a multiple of 32 ...
 #define SDX_BURN_ID_MIN (SDX_POOL_BASE - 256)   // ... so (burn <= 256) every id from here on is a burn-in round; null indices stay below
+static inline uint64_t sdx_pool_base_chain(int64_t burn) { return ((SDX_POOL_BASE / (uint64_t)burn + 31) / 32) * 32; }
 
 // ---------------------------------------------------------------------------
 // small device helpers
