@@ -1084,3 +1084,18 @@ def test_burn_in_orientation_branches_match_oracle():
             e2.set_pair_group(1)
             e2.set_burn_in(0)
     assert seen == {(False, False), (False, True), (True, False), (True, True)}
+
+
+@pytest.mark.parametrize("lanes", [False, True])
+def test_burn_in_pool_fuzz(lanes):
+    """tools/fuzz_burn.py: pool-started nulls vs the oracle over random shapes, densities and degenerate matrices (empty, full
+    rows / columns, two rows, word-aligned sizes), pair_group 1 and 32, on k_trade and — small requests forced onto it — on the lane kernel."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    if lanes:
+        env["SDX_LANE_MIN_CHAINS"] = "1"
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_burn.py"), "24", "31" if lanes else "5"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "mismatches 0" in r.stdout
