@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan12(const __grid_constant__ Scan
 template <bool LISTS, int NT, int NJ>
 __global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 4) k_scan3(const __grid_constant__ ScanArgs pa) {
     __shared__ uint32_t sI[SCAN_MAXW];
+    __shared__ uint32_t s_nz[(SCAN_MAXW + 31) / 32];      // which words of sI are non-zero
     __shared__ unsigned s_item;
     __shared__ double s_sgh[SCAN_GT][SCAN_HB];
     __shared__ unsigned char s_fl[SCAN_HB];
@@ -408,11 +409,22 @@ __global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 4) k_scan3(const __grid_co
                     for (int j = 0; j < NJ; ++j) p3[j] = 0.0;
                     if (slow[gi]) {                               // uniform: g∩h∩{w>0} is non-empty
                         const int g = g0 + gi;
+                        // the intersection is usually a handful of samples in one or two words: the walk visits the non-zero words only
+                        // (a ballot per 32 words), not all wprS of them — that scan was 40 % of the kernel's time at C0
                         __syncthreads();
-                        for (int wi = tid; wi < p.wprS; wi += NT)
-                            sI[wi] = p.feat[(size_t)g * p.fstride + wi] & p.feat[(size_t)h * p.fstride + wi] & p.pos[wi];
+                        for (int w0 = 0; w0 < p.wprS; w0 += NT) {        // whole warps: wprS words rounded up to 32
+                            const int wi = w0 + tid;
+                            if (w0 + (tid & ~31) < p.wprS) {
+                                const uint32_t x = wi < p.wprS ? p.feat[(size_t)g * p.fstride + wi] & p.feat[(size_t)h * p.fstride + wi] & p.pos[wi] : 0u;
+                                if (wi < p.wprS) sI[wi] = x;
+                                const uint32_t nzm = __ballot_sync(0xffffffffu, x != 0u);
+                                if (lane == 0) s_nz[wi >> 5] = nzm;
+                            }
+                        }
                         __syncthreads();
-                        for (int wi = 0; wi < p.wprS; ++wi) {
+                        for (int wq = 0; wq * 32 < p.wprS; ++wq)
+                        for (uint32_t nzm = s_nz[wq]; nzm; nzm &= nzm - 1) {
+                            const int wi = wq * 32 + __ffs(nzm) - 1;
                             uint32_t x = sI[wi];
                             while (x) {
                                 const int bp = __ffs(x) - 1;
@@ -684,9 +696,12 @@ static int maxk_impl(sdx_ctx *c, const uint32_t *rows_src, uint64_t seed, uint64
         ScanArgs a{};
         a.feat = feat; a.fstride = wprS; a.samp = samp; a.sstride = wprF; a.pos = d_pos; a.wpos = d_wpos; a.s1 = d_s1;
         a.T = (const double *)p_T; a.Fp = Fp; a.F = F; a.S = S; a.wprS = wprS; a.k = kp[p];
-        const bool narrow = F <= 512;                      // few features: 128-thread CTAs, 512-wide l-chunks
+        // few features: 128-thread CTAs and ONE l-chunk of 128 * nj >= F (nj = 1 .. 4 values of l per thread): a chunk wider than F
+        // would spend a slice of every h on l >= F (F = 384 with 512-wide chunks: a third of the issued slices)
+        const bool narrow = F <= 512;
+        const int nj = narrow ? std::max(1, ceil_div(F, 128)) : SCAN_NJ;
         a.g_lo = 0; a.g_hi = F; a.gt0 = 0; a.n_gt = ceil_div(F, SCAN_GT); a.n_hb = ceil_div(F, SCAN_HB);
-        a.n_lc = ceil_div(F, narrow ? 128 * SCAN_NJ : SCAN_NT * SCAN_NJ);
+        a.n_lc = ceil_div(F, narrow ? 128 * nj : SCAN_NT * SCAN_NJ);
         a.nb = nb; a.feat_b = feat_b; a.samp_b = samp_b; a.s1_b = (size_t)F; a.T_b = (size_t)F * Fp;
         a.best = d_best; a.item_counter = d_item;
         if ((int64_t)a.n_gt * a.n_hb * a.n_lc * nb >= (1ll << 31)) return sdx_fail(c, SDX_ERR_UNSUPPORTED, "too many scan work items");
@@ -698,7 +713,10 @@ static int maxk_impl(sdx_ctx *c, const uint32_t *rows_src, uint64_t seed, uint64
         k_scan12_max<<<dim3(std::max(1, std::min(F, c->sm_count * 2 / std::max(1, nb) + 1)), nb), SCAN_NT, 0, c->stream>>>(a);
         c->total_launches++; c->timing.launches++;
         if (kp[p] >= 3 && F >= 3) {
-            if (narrow) k_scan3<false, 128, SCAN_NJ><<<c->sm_count * 4, 128, 0, c->stream>>>(a);
+            if (narrow && nj == 1) k_scan3<false, 128, 1><<<c->sm_count * 4, 128, 0, c->stream>>>(a);
+            else if (narrow && nj == 2) k_scan3<false, 128, 2><<<c->sm_count * 4, 128, 0, c->stream>>>(a);
+            else if (narrow && nj == 3) k_scan3<false, 128, 3><<<c->sm_count * 4, 128, 0, c->stream>>>(a);
+            else if (narrow) k_scan3<false, 128, 4><<<c->sm_count * 4, 128, 0, c->stream>>>(a);
             else k_scan3<false, SCAN_NT, SCAN_NJ><<<grid3, SCAN_NT, 0, c->stream>>>(a);
             c->total_launches++; c->timing.launches++;
         }
