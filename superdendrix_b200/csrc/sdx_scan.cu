@@ -291,8 +291,6 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan12(const __grid_constant__ Scan
 // NT threads per CTA, NJ values of l per thread: one l-chunk is NT * NJ wide (small NT for small F).
 template <bool LISTS, int NT, int NJ>
 __global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 4) k_scan3(const __grid_constant__ ScanArgs pa) {
-    __shared__ uint32_t sI[SCAN_MAXW];
-    __shared__ uint32_t s_nz[(SCAN_MAXW + 31) / 32];      // which words of sI are non-zero
     __shared__ unsigned s_item;
     __shared__ double s_sgh[SCAN_GT][SCAN_HB];
     __shared__ unsigned char s_fl[SCAN_HB];
@@ -391,7 +389,7 @@ __global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 4) k_scan3(const __grid_co
                     for (int gi = 0; gi < SCAN_GT; ++gi) {
                         W[gi] = (sgh[gi] + t[j]) + c[gi][j];
                         if (LISTS) cand |= W[gi] >= top.gate;
-                        else best = fmax(best, W[gi]);
+                        else best = W[gi] > best ? W[gi] : best;          // no NaNs here: a compare and a select, not the NaN-aware fmax
                     }
                     if (LISTS && __any_sync(0xffffffffu, cand)) {
                         const int l = l0 + tid + j * NT;
@@ -409,23 +407,15 @@ __global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 4) k_scan3(const __grid_co
                     for (int j = 0; j < NJ; ++j) p3[j] = 0.0;
                     if (slow[gi]) {                               // uniform: g∩h∩{w>0} is non-empty
                         const int g = g0 + gi;
-                        // the intersection is usually a handful of samples in one or two words: the walk visits the non-zero words only
-                        // (a ballot per 32 words), not all wprS of them — that scan was 40 % of the kernel's time at C0
-                        __syncthreads();
-                        for (int w0 = 0; w0 < p.wprS; w0 += NT) {        // whole warps: wprS words rounded up to 32
-                            const int wi = w0 + tid;
-                            if (w0 + (tid & ~31) < p.wprS) {
-                                const uint32_t x = wi < p.wprS ? p.feat[(size_t)g * p.fstride + wi] & p.feat[(size_t)h * p.fstride + wi] & p.pos[wi] : 0u;
-                                if (wi < p.wprS) sI[wi] = x;
-                                const uint32_t nzm = __ballot_sync(0xffffffffu, x != 0u);
-                                if (lane == 0) s_nz[wi >> 5] = nzm;
-                            }
-                        }
-                        __syncthreads();
-                        for (int wq = 0; wq * 32 < p.wprS; ++wq)
-                        for (uint32_t nzm = s_nz[wq]; nzm; nzm &= nzm - 1) {
-                            const int wi = wq * 32 + __ffs(nzm) - 1;
-                            uint32_t x = sI[wi];
+                        // g∩h∩{w>0}: every warp forms the intersection words itself, one per lane and 32 at a time (the rows are L1 / L2
+                        // resident), and walks the non-zero ones: no shared-memory staging, no CTA barrier in the slow path, and the
+                        // usual handful of samples in one or two words costs one ballot instead of a scan over all wprS words
+                        for (int w0 = 0; w0 < p.wprS; w0 += 32) {
+                            const int wl = w0 + lane;
+                            const uint32_t xi = wl < p.wprS ? p.feat[(size_t)g * p.fstride + wl] & p.feat[(size_t)h * p.fstride + wl] & p.pos[wl] : 0u;
+                            for (uint32_t nzm = __ballot_sync(0xffffffffu, xi != 0u); nzm; nzm &= nzm - 1) {
+                            const int wsrc = __ffs(nzm) - 1, wi = w0 + wsrc;
+                            uint32_t x = __shfl_sync(0xffffffffu, xi, wsrc);
                             while (x) {
                                 const int bp = __ffs(x) - 1;
                                 x &= x - 1;
@@ -438,6 +428,7 @@ __global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 4) k_scan3(const __grid_co
                                     if (l < F && ((sr[l >> 5] >> (l & 31)) & 1u)) p3[j] += wp;
                                 }
                             }
+                            }
                         }
                     }
 #pragma unroll
@@ -449,7 +440,7 @@ __global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 4) k_scan3(const __grid_co
                             if (__any_sync(0xffffffffu, cand))
                                 top.offer(cand, W, scan_key(3, g0 + gi, h, l0 + tid + j * NT), lane);
                         } else {
-                            best = fmax(best, W);
+                            best = W > best ? W : best;
                         }
                     }
                 }
