@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan12(const __grid_constant__ Scan
 // maximum of each is kept (the max_k null statistic); `bp` below then carries the batch offsets.
 // NT threads per CTA, NJ values of l per thread: one l-chunk is NT * NJ wide (small NT for small F).
 template <bool LISTS, int NT, int NJ>
-__global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 4) k_scan3(const __grid_constant__ ScanArgs pa) {
+__global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 5) k_scan3(const __grid_constant__ ScanArgs pa) {
     __shared__ unsigned s_item;
     __shared__ double s_sgh[SCAN_GT][SCAN_HB];
     __shared__ unsigned char s_fl[SCAN_HB];
@@ -704,10 +704,10 @@ static int maxk_impl(sdx_ctx *c, const uint32_t *rows_src, uint64_t seed, uint64
         k_scan12_max<<<dim3(std::max(1, std::min(F, c->sm_count * 2 / std::max(1, nb) + 1)), nb), SCAN_NT, 0, c->stream>>>(a);
         c->total_launches++; c->timing.launches++;
         if (kp[p] >= 3 && F >= 3) {
-            if (narrow && nj == 1) k_scan3<false, 128, 1><<<c->sm_count * 4, 128, 0, c->stream>>>(a);
-            else if (narrow && nj == 2) k_scan3<false, 128, 2><<<c->sm_count * 4, 128, 0, c->stream>>>(a);
-            else if (narrow && nj == 3) k_scan3<false, 128, 3><<<c->sm_count * 4, 128, 0, c->stream>>>(a);
-            else if (narrow) k_scan3<false, 128, 4><<<c->sm_count * 4, 128, 0, c->stream>>>(a);
+            if (narrow && nj == 1) k_scan3<false, 128, 1><<<c->sm_count * 5, 128, 0, c->stream>>>(a);
+            else if (narrow && nj == 2) k_scan3<false, 128, 2><<<c->sm_count * 5, 128, 0, c->stream>>>(a);
+            else if (narrow && nj == 3) k_scan3<false, 128, 3><<<c->sm_count * 5, 128, 0, c->stream>>>(a);
+            else if (narrow) k_scan3<false, 128, 4><<<c->sm_count * 5, 128, 0, c->stream>>>(a);
             else k_scan3<false, SCAN_NT, SCAN_NJ><<<grid3, SCAN_NT, 0, c->stream>>>(a);
             c->total_launches++; c->timing.launches++;
         }
