@@ -82,7 +82,7 @@ static void free_matrix(sdx_ctx *c) {
     if (c->d_ln_pool) cudaFree(c->d_ln_pool);
     c->d_feat = c->d_samp = c->d_trade_obs = nullptr;
     c->d_rowsize = nullptr;
-    c->d_ln_desc = nullptr; c->d_ln_obs = nullptr; c->d_ln_pool = nullptr; c->cap_ln_pool = 0;
+    c->d_ln_desc = nullptr; c->d_ln_obs = nullptr; c->d_ln_pool = nullptr; c->cap_ln_pool = 0; c->cap_ln_desc = 0; c->cap_ln_obs = 0;
     c->ln_state = 0; c->ln_geo_valid = false; c->ln_pool_valid = false;
     if (c->d_pool) cudaFree(c->d_pool);
     c->d_pool = nullptr;

@@ -58,7 +58,7 @@ struct sdx_ctx {
     alignas(8) unsigned char ln_geo[64] = {};   // cached launch geometry of the lane kernel (LnGeom) for ln_geo_groups groups
     int64_t ln_geo_groups = -1;
     bool ln_geo_valid = false;
-    size_t cap_ln_pool = 0;
+    size_t cap_ln_pool = 0, cap_ln_desc = 0, cap_ln_obs = 0;      // grow-only: a re-upload of the same shape never calls the allocator
     bool ln_pool_valid = false;
     // how the PAIR stream is shared (sdx_set_pair_group): 1 = every null draws its own row pairs; 32 = the 32 chains
     // c, c+1, .. of an aligned block draw them from the stream of the block's first chain

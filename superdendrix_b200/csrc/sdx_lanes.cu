@@ -359,11 +359,8 @@ static int ln_layout(sdx_ctx *c) {
     if (lay.x_bytes > 16 * 1024) return SDX_OK;          // rows too long for the per-warp buffer of a bit-packed row: k_trade runs this matrix
     c->ln_ts = lay.ts; c->ln_slot_bytes = lay.slot_bytes; c->ln_has_bits = lay.n_bits > 0; c->ln_gsb = lay.gsb;
     c->ln_rows_bytes = lay.rows_bytes; c->ln_c_off = lay.c_off; c->ln_pp_off = lay.pp_off; c->ln_pf_bytes = lay.pf_bytes; c->ln_x_bytes = lay.x_bytes;
-    if (c->d_ln_desc) cudaFree(c->d_ln_desc);
-    if (c->d_ln_obs) cudaFree(c->d_ln_obs);
-    c->d_ln_desc = nullptr; c->d_ln_obs = nullptr;
-    SDX_CUDA(c, cudaMalloc(&c->d_ln_desc, sizeof(uint2) * R));
-    SDX_CUDA(c, cudaMalloc(&c->d_ln_obs, lay.rows_bytes));
+    SDX_TRY(sdx_reserve(c, c->d_ln_desc, c->cap_ln_desc, sizeof(uint2) * (size_t)R));
+    SDX_TRY(sdx_reserve(c, c->d_ln_obs, c->cap_ln_obs, (size_t)lay.rows_bytes));
     SDX_CUDA(c, cudaMemcpyAsync(c->d_ln_desc, desc.data(), sizeof(uint2) * R, cudaMemcpyHostToDevice, c->stream));
     SDX_CUDA(c, cudaStreamSynchronize(c->stream));       // desc goes out of scope
     SDX_TRY(ln_run_compact(c, c->d_trade_obs, 0, LN_W, true, c->d_ln_obs));
